@@ -1,0 +1,164 @@
+/* pgs.h — C-ABI of the B200-native pose-graph hot path (libpgs.so).
+ *
+ * Drop-in boundary for the Ceres path of mpkuse/solve_keyframe_pose_graph: everything the
+ * reference does between "parameter blocks + residual blocks exist" and "optimised poses are
+ * readable" (reference src/PoseGraphSLAM.cpp:1340-1367, 1550-1556, 1629-1633, 1847-1849, 1903 and
+ * the getters at :178-224) is reachable through these entry points.  Plain pointers and sizes,
+ * host memory, fp64, SoA; the caller allocates every output.  No torch / Eigen / ROS types.
+ *
+ * Conventions (reference file:line):
+ *   - quaternions are stored x,y,z,w (PoseGraphSLAM.h:153); a node pose is w_T_c = (q[4], t[3]).
+ *   - tangent ordering per node is [dtheta(3), dt(3)], dtheta being the half-angle left-multiplied
+ *     increment of ceres::EigenQuaternionParameterization (PoseGraphSLAM.cpp:1351-1353).
+ *   - an odometry edge binds parameters (c1, c2) with observation c1_T_c2 and weight w:
+ *     SixDOFError (CeresResidues.h:19-90), added at PoseGraphSLAM.cpp:1629-1633 with (c1,c2)=(u,u-f).
+ *   - a loop edge (a, b) carries b_T_a and owns one switch variable initialised to 0.99
+ *     (PoseGraphSLAM.cpp:353); it binds (c1,c2,s) = (b, a, s): SixDOFErrorWithSwitchingConstraints
+ *     (CeresResidues.h:145-222) added at PoseGraphSLAM.cpp:1550-1556.  Its weight is stored but,
+ *     as in the reference (CeresResidues.h:198), not applied.
+ *   - a regulariser anchors one node to a fixed pose: NodePoseRegularization
+ *     (CeresResidues.h:96-141) added at PoseGraphSLAM.cpp:1847-1849.
+ *   - cost = 1/2 sum ||r||^2, no loss function (all AddResidualBlock calls pass NULL).
+ *
+ * Every function returns PGS_OK (0) or a negative pgs_status; pgs_last_error() gives the text.
+ * Nothing here calls exit() or throws across the boundary (the reference exit()s on bad state,
+ * PoseGraphSLAM.cpp:1680,1711).  All compute runs on the CUDA device chosen in pgs_options.device
+ * and fails with PGS_ERR_CUDA when no device is usable — there is no CPU fallback.
+ */
+#ifndef PGS_H_
+#define PGS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgs_solver_s* pgs_handle;
+
+typedef enum pgs_status {
+  PGS_OK = 0,
+  PGS_ERR_INVALID_ARGUMENT = -1,
+  PGS_ERR_CUDA = -2,
+  PGS_ERR_OUT_OF_MEMORY = -3,
+  PGS_ERR_LINEAR_SOLVER = -4,
+  PGS_ERR_STATE = -5
+} pgs_status;
+
+typedef enum pgs_termination { PGS_CONVERGENCE = 0, PGS_NO_CONVERGENCE = 1, PGS_FAILURE = 2 } pgs_termination;
+
+typedef enum pgs_linear_solver {
+  PGS_SKYLINE_CHOLESKY = 0, /* direct: block skyline LL^T on device (stands in for SPARSE_NORMAL_CHOLESKY) */
+  PGS_BLOCK_PCG = 1         /* iterative: block-Jacobi preconditioned CG on device */
+} pgs_linear_solver;
+
+/* ceres::Solver::Options in effect in the reference (PoseGraphSLAM.cpp:1268-1272 + Ceres 1.12-1.14
+ * defaults) followed by device knobs.  pgs_default_options() fills the
+ * reference values. */
+typedef struct pgs_options {
+  int32_t max_num_iterations;               /* 10, PoseGraphSLAM.cpp:1272 */
+  double initial_trust_region_radius;       /* 1e4 */
+  double max_trust_region_radius;           /* 1e16 */
+  double min_trust_region_radius;           /* 1e-32 */
+  double min_relative_decrease;             /* 1e-3 */
+  double min_lm_diagonal;                   /* 1e-6 */
+  double max_lm_diagonal;                   /* 1e32 */
+  int32_t max_num_consecutive_invalid_steps;/* 5 */
+  double function_tolerance;                /* 1e-6 */
+  double gradient_tolerance;                /* 1e-10 */
+  double parameter_tolerance;               /* 1e-8 */
+  int32_t jacobi_scaling;                   /* 1 */
+  double switch_init;                       /* 0.99, PoseGraphSLAM.cpp:353 */
+  int32_t device;                           /* CUDA ordinal */
+  int32_t linear_solver;                    /* pgs_linear_solver */
+  int32_t pcg_max_iterations;               /* per linear solve */
+  double pcg_tolerance;                     /* relative residual ||b-Ax|| / ||b|| */
+} pgs_options;
+
+/* One row of Ceres' minimizer_progress_to_stdout table. */
+typedef struct pgs_iteration {
+  int32_t iteration;
+  double cost, cost_change, gradient_max_norm, gradient_norm, step_norm, relative_decrease, trust_region_radius;
+  int32_t step_is_valid, step_is_successful, linear_solver_iterations;
+} pgs_iteration;
+
+typedef struct pgs_summary {
+  double initial_cost, final_cost;
+  int32_t termination;                      /* pgs_termination */
+  int32_t num_successful_steps, num_unsuccessful_steps, num_iterations;
+  int32_t linear_solver_iterations;         /* total PCG iterations (0 for the direct solver) */
+  double ms_sweep, ms_assemble, ms_linear_solve, ms_total; /* device time by phase (CUDA events) */
+  int64_t factor_nnz;                       /* scalars stored by the skyline factor (0 for PCG) */
+} pgs_summary;
+
+/* Sizes of the residual/Jacobian outputs of pgs_evaluate. */
+typedef struct pgs_sizes {
+  int32_t n_nodes, n_odom, n_loop, n_reg;
+  int32_t n_pairs;                          /* distinct off-diagonal 6x6 blocks of J^T J */
+} pgs_sizes;
+
+int pgs_default_options(pgs_options* opt);
+int pgs_create(const pgs_options* opt, pgs_handle* out);
+int pgs_destroy(pgs_handle h);
+const char* pgs_last_error(pgs_handle h);   /* h may be NULL: error of the last failed pgs_create */
+int pgs_get_sizes(pgs_handle h, pgs_sizes* out);
+
+/* ---- variable store: replaces allocate_and_append_new_opt_variable_withpose / update_opt_variable_with
+ *      (PoseGraphSLAM.cpp:226-335) and allocate_and_append_new_edge_switch_var (:351-361) ---- */
+int pgs_set_nodes(pgs_handle h, int32_t n, const double* q_xyzw, const double* t);      /* replace all */
+int pgs_append_nodes(pgs_handle h, int32_t n, const double* q_xyzw, const double* t);   /* grow */
+int pgs_update_nodes(pgs_handle h, int32_t first, int32_t n, const double* q_xyzw, const double* t); /* new initial guesses */
+int pgs_get_poses(pgs_handle h, int32_t first, int32_t n, double* q_xyzw, double* t);   /* getNodePose, :197-214 */
+int pgs_set_switches(pgs_handle h, int32_t first, int32_t n, const double* s);
+int pgs_get_switches(pgs_handle h, int32_t first, int32_t n, double* s);                /* get_loopedge_switching_variable_val, PoseGraphSLAM.h:219 */
+
+/* ---- residual blocks: replace ceres::Problem::AddResidualBlock at PoseGraphSLAM.cpp:1629-1633,
+ *      :1550-1556, :1847-1849 and RemoveResidualBlock at :1803-1807 ---- */
+int pgs_add_odom_edges(pgs_handle h, int32_t m, const int32_t* c1, const int32_t* c2,
+                       const double* q_c1Tc2, const double* t_c1Tc2, const double* w);
+int pgs_add_loop_edges(pgs_handle h, int32_t m, const int32_t* a, const int32_t* b,
+                       const double* q_bTa, const double* t_bTa, const double* w);
+int pgs_set_regularizers(pgs_handle h, int32_t k, const int32_t* node, const double* q_f, const double* t_f,
+                         const double* w);                                              /* replaces the previous set */
+
+/* ---- evaluation: ceres Evaluate() semantics at the current parameters.  cost always; any other
+ *      pointer may be NULL.  Blocks come back in the caller's insertion order, row-major:
+ *      r_odom[E][6], J_odom[E][6][12] (cols th_c1,t_c1,th_c2,t_c2); r_loop[E][7], J_loop[E][7][13]
+ *      (last col = switch); r_reg[K][6], J_reg[K][6][6].  On the device the sweep writes the same
+ *      numbers in a warp-tiled SoA layout; these are re-laid-out copies. ---- */
+int pgs_evaluate(pgs_handle h, double* cost, double* r_odom, double* J_odom, double* r_loop, double* J_loop,
+                 double* r_reg, double* J_reg);
+/* J^T r in tangent space: g_pose[N][6], g_switch[n_loop]. */
+int pgs_gradient(pgs_handle h, double* g_pose, double* g_switch);
+/* Block-sparse J^T J (pose part, before scaling/damping/switch elimination): diag[N][6][6],
+ * pair_hi[n_pairs], pair_lo[n_pairs], offdiag[n_pairs][6][6] = block (row hi, col lo), and the
+ * per-loop-edge switch coupling v[n_loop][12] = J_p^T j_s, hss[n_loop] = j_s^T j_s. Any may be NULL. */
+int pgs_assemble(pgs_handle h, double* diag, int32_t* pair_hi, int32_t* pair_lo, double* offdiag,
+                 double* loop_v, double* loop_hss);
+/* One LM linear step at the current parameters with first-iteration Jacobi scaling and the given
+ * radius: unscaled tangent step delta_pose[N][6], delta_switch[n_loop], and the model cost change. */
+int pgs_linear_step(pgs_handle h, double radius, double* delta_pose, double* delta_switch, double* model_cost_change,
+                    int32_t* linear_iterations);
+
+/* ---- the solve: replaces ceres::Solve(reint_options, &reint_problem, &reint_summary)
+ *      (PoseGraphSLAM.cpp:1903).  iters may be NULL; at most iters_cap rows are written. ---- */
+int pgs_solve(pgs_handle h, pgs_summary* summary, pgs_iteration* iters, int32_t iters_cap);
+
+/* ---- measurement hooks used by bench.py ---- */
+/* Runs the residual+Jacobian sweep `reps` times with every input already resident in HBM and
+ * returns the mean device time per sweep in milliseconds (CUDA events on the solver's stream).
+ * flush_l2 != 0 writes a >L2-sized scratch buffer between repetitions (outside the timed spans).
+ * mode: 0 = residuals + Jacobians (mode J), 1 = cost only. */
+int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush_l2, double* ms_per_sweep,
+                   int64_t* kernel_launches);
+/* End-to-end step: host poses/switches (pinned or pageable) -> device, one mode-J sweep, cost back
+ * to the host.  q,t,s may be NULL to reuse the current values of that array. */
+int pgs_evaluate_from_host(pgs_handle h, const double* q_xyzw, const double* t, const double* s, double* cost);
+/* Algorithmic bytes of one mode-J sweep per SURVEY §8(d): 56N + 72 Eo + 72 El + 68 K in,
+ * 624 Eo + 784 El + 336 K out. */
+int64_t pgs_sweep_algorithmic_bytes(pgs_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGS_H_ */

@@ -1,0 +1,251 @@
+"""ctypes binding of include/pgs.h.  Mirrors the C-ABI one to one; `PoseGraphSolver` is the
+RAII convenience used by tests and bench.py.  Loading fails loudly if libpgs.so is missing —
+the product never falls back to a CPU implementation."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class PgsError(RuntimeError):
+    pass
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int32),
+        ("initial_trust_region_radius", C.c_double),
+        ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double),
+        ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double),
+        ("max_lm_diagonal", C.c_double),
+        ("max_num_consecutive_invalid_steps", C.c_int32),
+        ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double),
+        ("jacobi_scaling", C.c_int32),
+        ("switch_init", C.c_double),
+        ("device", C.c_int32),
+        ("linear_solver", C.c_int32),
+        ("pcg_max_iterations", C.c_int32),
+        ("pcg_tolerance", C.c_double),
+    ]
+
+
+class Iteration(C.Structure):
+    _fields_ = [
+        ("iteration", C.c_int32),
+        ("cost", C.c_double), ("cost_change", C.c_double), ("gradient_max_norm", C.c_double), ("gradient_norm", C.c_double),
+        ("step_norm", C.c_double), ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double),
+        ("step_is_valid", C.c_int32), ("step_is_successful", C.c_int32), ("linear_solver_iterations", C.c_int32),
+    ]
+
+
+class Summary(C.Structure):
+    _fields_ = [
+        ("initial_cost", C.c_double), ("final_cost", C.c_double),
+        ("termination", C.c_int32), ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+        ("num_iterations", C.c_int32), ("linear_solver_iterations", C.c_int32),
+        ("ms_sweep", C.c_double), ("ms_assemble", C.c_double), ("ms_linear_solve", C.c_double), ("ms_total", C.c_double),
+        ("factor_nnz", C.c_int64),
+    ]
+
+
+class Sizes(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_odom", C.c_int32), ("n_loop", C.c_int32), ("n_reg", C.c_int32), ("n_pairs", C.c_int32)]
+
+
+SKYLINE_CHOLESKY, BLOCK_PCG = 0, 1
+TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}
+
+
+def library_path():
+    return os.path.join(_PKG, "libpgs.so")
+
+
+def exported_symbols():
+    """Function names declared in include/pgs.h (what the shared library must export)."""
+    txt = open(os.path.join(_ROOT, "include", "pgs.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgs_[a-z_0-9]+)\s*\(", txt)))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        p = library_path()
+        if not os.path.exists(p):
+            raise PgsError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C solve_keyframe_pose_graph_b200/csrc). There is no CPU fallback.")
+        L = C.CDLL(p)
+        L.pgs_last_error.restype = C.c_char_p
+        L.pgs_last_error.argtypes = [C.c_void_p]
+        L.pgs_sweep_algorithmic_bytes.restype = C.c_int64
+        L.pgs_sweep_algorithmic_bytes.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_ip)
+
+
+def default_options(**kw):
+    o = Options()
+    lib().pgs_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+class PoseGraphSolver:
+    def __init__(self, options=None, **kw):
+        self.L = lib()
+        self.opt = options or default_options(**kw)
+        self.h = C.c_void_p()
+        rc = self.L.pgs_create(C.byref(self.opt), C.byref(self.h))
+        if rc != 0:
+            raise PgsError(f"pgs_create failed ({rc}): {self.L.pgs_last_error(None).decode()}")
+        self.N = 0
+        self.n_odom = self.n_loop = self.n_reg = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.pgs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PgsError(f"pgs error {rc}: {self.L.pgs_last_error(self.h).decode()}")
+
+    # ---- construction
+    def set_nodes(self, q, t):
+        q, qp = _d(q); t, tp = _d(t)
+        self._ck(self.L.pgs_set_nodes(self.h, C.c_int32(q.shape[0]), qp, tp)); self.N = q.shape[0]
+
+    def append_nodes(self, q, t):
+        q, qp = _d(q); t, tp = _d(t)
+        self._ck(self.L.pgs_append_nodes(self.h, C.c_int32(q.shape[0]), qp, tp)); self.N += q.shape[0]
+
+    def update_nodes(self, first, q, t):
+        q, qp = _d(q); t, tp = _d(t)
+        self._ck(self.L.pgs_update_nodes(self.h, C.c_int32(first), C.c_int32(q.shape[0]), qp, tp))
+
+    def add_odom_edges(self, c1, c2, q, t, w):
+        c1, c1p = _i(c1); c2, c2p = _i(c2); q, qp = _d(q); t, tp = _d(t); w, wp = _d(w)
+        self._ck(self.L.pgs_add_odom_edges(self.h, C.c_int32(len(c1)), c1p, c2p, qp, tp, wp)); self.n_odom += len(c1)
+
+    def add_loop_edges(self, a, b, q, t, w):
+        a, ap = _i(a); b, bp = _i(b); q, qp = _d(q); t, tp = _d(t); w, wp = _d(w)
+        self._ck(self.L.pgs_add_loop_edges(self.h, C.c_int32(len(a)), ap, bp, qp, tp, wp)); self.n_loop += len(a)
+
+    def set_regularizers(self, node, q, t, w):
+        node, np_ = _i(node); q, qp = _d(q); t, tp = _d(t); w, wp = _d(w)
+        self._ck(self.L.pgs_set_regularizers(self.h, C.c_int32(len(node)), np_, qp, tp, wp)); self.n_reg = len(node)
+
+    def set_switches(self, s, first=0):
+        s, sp = _d(s)
+        self._ck(self.L.pgs_set_switches(self.h, C.c_int32(first), C.c_int32(len(s)), sp))
+
+    # ---- getters
+    def poses(self, first=0, n=None):
+        n = self.N - first if n is None else n
+        q = np.empty((n, 4)); t = np.empty((n, 3))
+        self._ck(self.L.pgs_get_poses(self.h, C.c_int32(first), C.c_int32(n), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp)))
+        return q, t
+
+    def switches(self):
+        s = np.empty(self.n_loop)
+        if self.n_loop:
+            self._ck(self.L.pgs_get_switches(self.h, C.c_int32(0), C.c_int32(self.n_loop), s.ctypes.data_as(c_dp)))
+        return s
+
+    def sizes(self):
+        s = Sizes(); self._ck(self.L.pgs_get_sizes(self.h, C.byref(s))); return s
+
+    # ---- evaluation
+    def evaluate(self, jac=True, residuals=True):
+        cost = C.c_double(0)
+        out = {}
+        ptr = lambda a: a.ctypes.data_as(c_dp)
+        if residuals:
+            out.update(r_o=np.zeros((self.n_odom, 6)), r_l=np.zeros((self.n_loop, 7)), r_r=np.zeros((self.n_reg, 6)))
+        if jac:
+            out.update(J_o=np.zeros((self.n_odom, 6, 12)), J_l=np.zeros((self.n_loop, 7, 13)), J_r=np.zeros((self.n_reg, 6, 6)))
+        g = lambda k: ptr(out[k]) if k in out else None
+        self._ck(self.L.pgs_evaluate(self.h, C.byref(cost), g("r_o"), g("J_o"), g("r_l"), g("J_l"), g("r_r"), g("J_r")))
+        out["cost"] = cost.value
+        return out
+
+    def gradient(self):
+        gp = np.zeros((self.N, 6)); gs = np.zeros(max(self.n_loop, 1))
+        self._ck(self.L.pgs_gradient(self.h, gp.ctypes.data_as(c_dp), gs.ctypes.data_as(c_dp)))
+        return gp, gs[: self.n_loop]
+
+    def assemble(self):
+        sz = self.sizes(); P = sz.n_pairs
+        diag = np.zeros((self.N, 6, 6)); hi = np.zeros(max(P, 1), np.int32); lo = np.zeros(max(P, 1), np.int32)
+        off = np.zeros((max(P, 1), 6, 6)); lv = np.zeros((max(self.n_loop, 1), 12)); lh = np.zeros(max(self.n_loop, 1))
+        self._ck(self.L.pgs_assemble(self.h, diag.ctypes.data_as(c_dp), hi.ctypes.data_as(c_ip), lo.ctypes.data_as(c_ip), off.ctypes.data_as(c_dp),
+                                     lv.ctypes.data_as(c_dp), lh.ctypes.data_as(c_dp)))
+        return dict(diag=diag, pair_hi=hi[:P], pair_lo=lo[:P], offdiag=off[:P], loop_v=lv[: self.n_loop], loop_hss=lh[: self.n_loop])
+
+    def linear_step(self, radius):
+        dp = np.zeros((self.N, 6)); ds = np.zeros(max(self.n_loop, 1)); mcc = C.c_double(0); it = C.c_int32(0)
+        self._ck(self.L.pgs_linear_step(self.h, C.c_double(radius), dp.ctypes.data_as(c_dp), ds.ctypes.data_as(c_dp), C.byref(mcc), C.byref(it)))
+        return dp, ds[: self.n_loop], mcc.value, it.value
+
+    def solve(self):
+        s = Summary(); cap = self.opt.max_num_iterations + 8
+        its = (Iteration * cap)()
+        self._ck(self.L.pgs_solve(self.h, C.byref(s), its, C.c_int32(cap)))
+        rows = [{f: getattr(its[i], f) for f, _ in Iteration._fields_} for i in range(min(s.num_iterations, cap))]
+        d = {f: getattr(s, f) for f, _ in Summary._fields_}
+        d["termination"] = TERMINATION[s.termination]; d["iterations"] = rows
+        return d
+
+    # ---- measurement hooks
+    def time_sweep(self, mode=0, reps=10, flush_l2=False):
+        ms = C.c_double(0); n = C.c_int64(0)
+        self._ck(self.L.pgs_time_sweep(self.h, C.c_int32(mode), C.c_int32(reps), C.c_int32(int(flush_l2)), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def evaluate_from_host_ptr(self, q_ptr, t_ptr, s_ptr):
+        """Raw-pointer variant (pinned torch tensors): addresses as ints, 0 for 'reuse'."""
+        cost = C.c_double(0)
+        self._ck(self.L.pgs_evaluate_from_host(self.h, C.c_void_p(q_ptr), C.c_void_p(t_ptr), C.c_void_p(s_ptr), C.byref(cost)))
+        return cost.value
+
+    def evaluate_from_host(self, q, t, s=None):
+        q, qp = _d(q); t, tp = _d(t); s, sp = _d(s)
+        cost = C.c_double(0)
+        self._ck(self.L.pgs_evaluate_from_host(self.h, qp, tp, sp, C.byref(cost)))
+        return cost.value
+
+    def sweep_bytes(self):
+        return int(self.L.pgs_sweep_algorithmic_bytes(self.h))

@@ -1,0 +1,65 @@
+// extern "C" surface declared in include/pgs.h.  Thin: argument checks + dispatch into pgs::Solver.
+#include <new>
+#include <string>
+#include "pgs_solver.h"
+
+using pgs::Solver;
+static thread_local std::string g_create_error;
+struct pgs_solver_s { Solver* s; };
+
+#define H(h) do { if (!(h) || !(h)->s) return PGS_ERR_INVALID_ARGUMENT; } while (0)
+
+extern "C" {
+
+int pgs_default_options(pgs_options* o) {
+  if (!o) return PGS_ERR_INVALID_ARGUMENT;
+  o->max_num_iterations = 10;                 // reference PoseGraphSLAM.cpp:1272
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5; o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->jacobi_scaling = 1; o->switch_init = 0.99;  // reference PoseGraphSLAM.cpp:353
+  o->device = 0; o->linear_solver = PGS_SKYLINE_CHOLESKY; o->pcg_max_iterations = 20000; o->pcg_tolerance = 1e-10;
+  return PGS_OK;
+}
+
+int pgs_create(const pgs_options* opt, pgs_handle* out) {
+  if (!out) return PGS_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  pgs_options o;
+  if (opt) o = *opt; else pgs_default_options(&o);
+  Solver* s = new (std::nothrow) Solver(o);
+  if (!s) { g_create_error = "out of host memory"; return PGS_ERR_OUT_OF_MEMORY; }
+  const int rc = s->init();
+  if (rc != PGS_OK) { g_create_error = s->err; delete s; return rc; }
+  pgs_solver_s* h = new pgs_solver_s{s};
+  *out = h;
+  return PGS_OK;
+}
+int pgs_destroy(pgs_handle h) { if (!h) return PGS_OK; delete h->s; delete h; return PGS_OK; }
+const char* pgs_last_error(pgs_handle h) { return (h && h->s) ? h->s->err.c_str() : g_create_error.c_str(); }
+int pgs_get_sizes(pgs_handle h, pgs_sizes* out) { H(h); if (!out) return PGS_ERR_INVALID_ARGUMENT; h->s->sizes(out); return PGS_OK; }
+
+int pgs_set_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); return h->s->set_nodes(n, q, t, false); }
+int pgs_append_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); return h->s->set_nodes(n, q, t, true); }
+int pgs_update_nodes(pgs_handle h, int32_t first, int32_t n, const double* q, const double* t) { H(h); return h->s->update_nodes(first, n, q, t); }
+int pgs_get_poses(pgs_handle h, int32_t first, int32_t n, double* q, double* t) { H(h); return h->s->get_poses(first, n, q, t); }
+int pgs_set_switches(pgs_handle h, int32_t first, int32_t n, const double* s) { H(h); return h->s->set_switches(first, n, s); }
+int pgs_get_switches(pgs_handle h, int32_t first, int32_t n, double* s) { H(h); return h->s->get_switches(first, n, s); }
+int pgs_add_odom_edges(pgs_handle h, int32_t m, const int32_t* c1, const int32_t* c2, const double* q, const double* t, const double* w) {
+  H(h); return h->s->add_odom(m, c1, c2, q, t, w); }
+int pgs_add_loop_edges(pgs_handle h, int32_t m, const int32_t* a, const int32_t* b, const double* q, const double* t, const double* w) {
+  H(h); return h->s->add_loop(m, a, b, q, t, w); }
+int pgs_set_regularizers(pgs_handle h, int32_t k, const int32_t* node, const double* q, const double* t, const double* w) {
+  H(h); return h->s->set_regs(k, node, q, t, w); }
+int pgs_evaluate(pgs_handle h, double* cost, double* r_o, double* J_o, double* r_l, double* J_l, double* r_r, double* J_r) {
+  H(h); return h->s->evaluate(cost, r_o, J_o, r_l, J_l, r_r, J_r); }
+int pgs_gradient(pgs_handle h, double* gp, double* gs) { H(h); return h->s->gradient(gp, gs); }
+int pgs_assemble(pgs_handle h, double* diag, int32_t* phi, int32_t* plo, double* off, double* lv, double* lh) {
+  H(h); return h->s->assemble(diag, phi, plo, off, lv, lh); }
+int pgs_linear_step(pgs_handle h, double radius, double* dp, double* ds, double* mcc, int32_t* it) { H(h); return h->s->linear_step(radius, dp, ds, mcc, it); }
+int pgs_solve(pgs_handle h, pgs_summary* sum, pgs_iteration* iters, int32_t cap) { H(h); return h->s->solve(sum, iters, cap); }
+int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush, double* ms, int64_t* launches) { H(h); return h->s->time_sweep(mode, reps, flush, ms, launches); }
+int pgs_evaluate_from_host(pgs_handle h, const double* q, const double* t, const double* s, double* cost) { H(h); return h->s->evaluate_from_host(q, t, s, cost); }
+int64_t pgs_sweep_algorithmic_bytes(pgs_handle h) { if (!h || !h->s) return 0; return h->s->sweep_bytes(); }
+
+}  // extern "C"

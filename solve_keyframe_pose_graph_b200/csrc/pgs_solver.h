@@ -1,0 +1,127 @@
+// Host-side driver of the device pose-graph solver (C++ behind the C-ABI of include/pgs.h).
+//
+// Owns the problem (parameter blocks + residual blocks as the reference's ceres::Problem does,
+// reference src/PoseGraphSLAM.cpp:1340-1367,1550-1556,1629-1633,1847-1849), the device buffers and
+// the trust-region Levenberg-Marquardt loop that replaces ceres::Solve (PoseGraphSLAM.cpp:1903).
+// The loop restates Ceres 1.12-1.14's TrustRegionMinimizer + LevenbergMarquardtStrategy semantics
+// (SURVEY §3.4); only scalars cross PCIe per iteration.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/pgs.h"
+
+namespace pgs {
+
+template <class T>
+struct DBuf {
+  T* p = nullptr; size_t n = 0;
+  ~DBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t resize(size_t m, bool zero = false) {
+    if (m <= n && p) { if (zero) return cudaMemset(p, 0, sizeof(T) * (m ? m : 1)); return cudaSuccess; }
+    release();
+    cudaError_t e = cudaMalloc((void**)&p, sizeof(T) * (m ? m : 1));
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    n = m;
+    if (zero) return cudaMemset(p, 0, sizeof(T) * (m ? m : 1));
+    return cudaSuccess;
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
+    cudaError_t e = resize(h.size()); if (e != cudaSuccess) return e;
+    if (h.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s);
+  }
+};
+
+struct SkylineFactor;  // pgs_skyline.cu
+
+class Solver {
+ public:
+  explicit Solver(const pgs_options& o);
+  ~Solver();
+  int init();
+
+  // ---- problem construction (host side; marks the structure dirty)
+  int set_nodes(int n, const double* q, const double* t, bool append);
+  int update_nodes(int first, int n, const double* q, const double* t);
+  int get_poses(int first, int n, double* q, double* t);
+  int set_switches(int first, int n, const double* s);
+  int get_switches(int first, int n, double* s);
+  int add_odom(int m, const int* c1, const int* c2, const double* q, const double* t, const double* w);
+  int add_loop(int m, const int* a, const int* b, const double* q, const double* t, const double* w);
+  int set_regs(int k, const int* node, const double* q, const double* t, const double* w);
+
+  // ---- evaluation / assembly / solve
+  int evaluate(double* cost, double* r_o, double* J_o, double* r_l, double* J_l, double* r_r, double* J_r);
+  int gradient(double* g_pose, double* g_switch);
+  int assemble(double* diag, int* pair_hi, int* pair_lo, double* offdiag, double* loop_v, double* loop_hss);
+  int linear_step(double radius, double* delta_pose, double* delta_switch, double* mcc, int* lin_iters);
+  int solve(pgs_summary* sum, pgs_iteration* iters, int cap);
+  int time_sweep(int mode, int reps, int flush_l2, double* ms, int64_t* launches);
+  int evaluate_from_host(const double* q, const double* t, const double* s, double* cost);
+  int64_t sweep_bytes() const;
+  void sizes(pgs_sizes* s);
+
+  std::string err;
+  pgs_options opt;
+
+ private:
+  int fail(int code, const std::string& msg) { err = msg; return code; }
+  int cuda_fail(cudaError_t e, const char* what);
+  int finalize();                        // sort edges, build incidence/pair/adjacency structures, upload
+  int sync_params_to_device();           // host q,t,sw -> device pose / sw (if dirty)
+  int sync_params_to_host();             // device -> host mirrors (if device is newer)
+  int launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev);
+  int run_assemble();
+  int compute_scaling(bool compute_scale);
+  int build_system(double radius);
+  int solve_linear(int* iters);          // Ad/Ao/b -> y  (PCG or skyline Cholesky)
+  int solve_pcg(int* iters);
+  int solve_skyline();
+  int read_scalars(int n);               // d_scal -> h_scal (pinned), synchronises the stream
+
+  int N = 0;
+  // host problem, caller order
+  std::vector<double> h_q, h_t, h_sw;
+  std::vector<int> o_c1, o_c2; std::vector<double> o_q, o_t, o_w;
+  std::vector<int> l_a, l_b; std::vector<double> l_q, l_t, l_w;
+  std::vector<int> r_node; std::vector<double> r_q, r_t, r_w;
+  bool structure_dirty = true, regs_dirty = true, host_params_newer = true, device_params_newer = false;
+
+  // sorted structure (host)
+  std::vector<int> perm_o, perm_l;       // sorted index -> caller index
+  std::vector<int> inv_perm_l;
+  int n_pairs = 0;
+  std::vector<int> h_pair_hi, h_pair_lo;
+  std::vector<char> h_node_used;
+
+  // device
+  int dev = 0; cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DBuf<double> d_pose, d_cpose, d_sw, d_csw, d_stage_q, d_stage_t, d_stage_s;
+  DBuf<int2> d_oidx, d_lidx, d_pair;
+  DBuf<double> d_oobs, d_lobs, d_ranchor;
+  DBuf<int> d_rnode, d_perm_o, d_perm_l;
+  DBuf<double> d_or, d_oJ, d_lr, d_lJ, d_gr, d_gJ;
+  DBuf<int> d_inc_ptr, d_inc_item, d_pe_ptr, d_pe_item, d_adj_ptr, d_adj_item;
+  DBuf<char> d_node_used;
+  DBuf<double> d_Hd, d_g, d_Ho, d_lv, d_lh, d_lg, d_lvt, d_lw, d_lgt;
+  DBuf<double> d_scale_p, d_scale_s, d_diag_p, d_diag_s;
+  DBuf<double> d_Ad, d_Ao, d_b, d_y, d_dp, d_ds;
+  DBuf<double> d_Minv, d_px, d_pr, d_prn, d_pz, d_pp, d_pAp;
+  DBuf<double> d_partial, d_scal, d_flush;
+  DBuf<unsigned int> d_counter;
+  double* h_scal = nullptr;              // pinned
+  double* h_pin_q = nullptr; double* h_pin_t = nullptr; double* h_pin_s = nullptr; size_t pin_n = 0, pin_s = 0;
+  int sweep_grid = 0;
+  SkylineFactor* sky = nullptr;
+  int64_t factor_nnz = 0;
+
+  // phase timers (ms, accumulated per solve)
+  double ms_sweep = 0, ms_asm = 0, ms_lin = 0;
+  void tic(); double toc();
+};
+
+}  // namespace pgs

@@ -1,0 +1,93 @@
+"""GPU parity: libpgs (CUDA, through the C-ABI) against the CPU oracle on the same seeded inputs.
+Tolerances: residual/Jacobian blocks 1e-12 relative (fp64, closed form vs Jet autodiff);
+final poses 1e-5 m / 1e-4 rad, identical switch states, cost 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from util_graphs import load_oracle, load_pgs, random_graph, rot_angle_between
+
+pytestmark = pytest.mark.gpu
+
+import solve_keyframe_pose_graph_b200 as pgs  # noqa: E402
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max()) if a.size else 0.0
+
+
+@pytest.mark.parametrize("n,fan,nl,seed", [(60, 3, 12, 0), (257, 5, 40, 1), (33, 1, 0, 2), (1000, 3, 300, 3)])
+def test_evaluate_matches_oracle(n, fan, nl, seed):
+    g = random_graph(n, fan, nl, outlier_frac=0.2, seed=seed)
+    sw = np.random.default_rng(seed).uniform(0.0, 1.1, size=nl) if nl else None
+    O = load_oracle(g, sw); S = load_pgs(g, sw)
+    eo = O.evaluate(autodiff=True); es = S.evaluate()
+    assert abs(es["cost"] - eo["cost"]) <= 1e-12 * max(1.0, eo["cost"])
+    for k in ("r_o", "J_o", "r_l", "J_l", "r_r", "J_r"):
+        assert rel_err(es[k], eo[k]) < 1e-12, k
+    gp, gs = S.gradient()
+    assert rel_err(gp, eo["g_p"]) < 1e-11 and rel_err(gs, eo["g_s"]) < 1e-11
+
+
+def test_assemble_matches_jtj():
+    g = random_graph(120, 3, 30, outlier_frac=0.2, seed=5)
+    O = load_oracle(g); S = load_pgs(g)
+    eo = O.evaluate(autodiff=True)
+    N = g["N"]
+    H = np.zeros((6 * N, 6 * N))
+    def add(J, c1, c2):
+        idx = np.r_[6 * c1:6 * c1 + 6, 6 * c2:6 * c2 + 6]
+        H[np.ix_(idx, idx)] += J.T @ J
+    for e in range(len(g["oc1"])):
+        add(eo["J_o"][e], g["oc1"][e], g["oc2"][e])
+    for e in range(len(g["la"])):
+        add(eo["J_l"][e][:, :12], g["lb"][e], g["la"][e])
+    for k in range(len(g["rn"])):
+        i = g["rn"][k]; H[6 * i:6 * i + 6, 6 * i:6 * i + 6] += eo["J_r"][k].T @ eo["J_r"][k]
+    A = S.assemble()
+    for i in range(N):
+        assert np.allclose(A["diag"][i], H[6 * i:6 * i + 6, 6 * i:6 * i + 6], rtol=0, atol=1e-10)
+    seen = np.zeros((N, N), bool)
+    for p in range(len(A["pair_hi"])):
+        hi, lo = A["pair_hi"][p], A["pair_lo"][p]
+        assert hi > lo and not seen[hi, lo]
+        seen[hi, lo] = True
+        assert np.allclose(A["offdiag"][p], H[6 * hi:6 * hi + 6, 6 * lo:6 * lo + 6], rtol=0, atol=1e-10)
+    Hb = np.abs(H).reshape(N, 6, N, 6).max(axis=(1, 3)) > 0
+    assert np.array_equal(np.tril(Hb, -1), seen)          # every structurally non-zero block is present exactly once
+    for e in range(len(g["la"])):
+        J = eo["J_l"][e]
+        assert np.allclose(A["loop_v"][e], J[:, :12].T @ J[:, 12], atol=1e-11)
+        assert np.isclose(A["loop_hss"][e], J[:, 12] @ J[:, 12], atol=1e-12)
+
+
+@pytest.mark.parametrize("solver", [pgs.capi.BLOCK_PCG, pgs.capi.SKYLINE_CHOLESKY])
+def test_linear_step_matches_oracle(solver):
+    g = random_graph(150, 3, 40, outlier_frac=0.1, seed=7)
+    O = load_oracle(g); S = load_pgs(g, linear_solver=solver, pcg_tolerance=1e-13)
+    for radius in (1e4, 3.7e6, 12.0):
+        dpo, dso, mo = O.linear_step(radius)
+        dps, dss, ms, it = S.linear_step(radius)
+        scale = max(1.0, np.abs(dpo).max())
+        assert np.abs(dps - dpo).max() < 1e-7 * scale, (radius, np.abs(dps - dpo).max())
+        assert np.abs(dss - dso).max() < 1e-7
+        assert abs(ms - mo) < 1e-7 * max(1.0, abs(mo))
+
+
+@pytest.mark.parametrize("solver", [pgs.capi.BLOCK_PCG, pgs.capi.SKYLINE_CHOLESKY])
+@pytest.mark.parametrize("n,fan,nl,outl,seed", [(50, 1, 1, 0.0, 11), (200, 3, 40, 0.0, 12), (400, 3, 120, 0.1, 13)])
+def test_solve_matches_oracle(solver, n, fan, nl, outl, seed):
+    g = random_graph(n, fan, nl, outlier_frac=outl, seed=seed)
+    O = load_oracle(g); S = load_pgs(g, linear_solver=solver, pcg_tolerance=1e-12)
+    so = O.solve(); ss = S.solve()
+    assert ss["termination"] == so["termination"]
+    assert len(ss["iterations"]) == len(so["iterations"])
+    for a, b in zip(ss["iterations"], so["iterations"]):       # same accept/reject trajectory
+        assert a["step_is_successful"] == b["step_is_successful"] and a["step_is_valid"] == b["step_is_valid"]
+        assert abs(a["cost"] - b["cost"]) <= 1e-6 * max(1e-12, abs(b["cost"]))
+        assert abs(a["trust_region_radius"] - b["trust_region_radius"]) <= 1e-6 * b["trust_region_radius"]
+    assert abs(ss["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]
+    qo, to = O.poses(); qs, ts = S.poses()
+    assert np.abs(ts - to).max() < 1e-5
+    assert rot_angle_between(qs, qo).max() < 1e-4
+    assert np.array_equal(S.switches() > 0.5, O.switches() > 0.5)
+    assert np.abs(S.switches() - O.switches()).max() < 1e-5
