@@ -146,11 +146,12 @@ int pgs_solve(pgs_handle h, pgs_summary* summary, pgs_iteration* iters, int32_t 
 
 /* ---- measurement hooks used by bench.py ---- */
 /* Runs the residual+Jacobian sweep `reps` times with every input already resident in HBM and
- * returns the mean device time per sweep in milliseconds (CUDA events on the solver's stream).
+ * returns the mean device time in milliseconds, measured per repetition with CUDA events on the
+ * solver's stream: ms_per_sweep = sweep kernel + cost reduction, ms_sweep_kernel = the sweep kernel alone.
  * flush_l2 != 0 writes a >L2-sized scratch buffer between repetitions (outside the timed spans).
  * mode: 0 = residuals + Jacobians (mode J), 1 = cost only. */
 int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush_l2, double* ms_per_sweep,
-                   int64_t* kernel_launches);
+                   double* ms_sweep_kernel, int64_t* kernel_launches);
 /* End-to-end step: host poses/switches (pinned or pageable) -> device, one mode-J sweep, cost back
  * to the host.  q,t,s may be NULL to reuse the current values of that array. */
 int pgs_evaluate_from_host(pgs_handle h, const double* q_xyzw, const double* t, const double* s, double* cost);

@@ -1,0 +1,64 @@
+/* pgs_facade.h — C view of the ROS-free C++ facade (NodeDataManager + PoseGraphSLAM,
+ * solve_keyframe_pose_graph_b200/csrc/host/) so that non-C++ hosts (the Python tests, bench.py) can drive
+ * the same trigger logic the reference node runs: ingest keyframes / loop edges / kidnap signals, call
+ * one wake-up of reinit_ceres_problem_onnewloopedge_optimize6DOF(), read the optimised poses.
+ * Reference: src/NodeDataManager.cpp:23-215 (ingest), src/PoseGraphSLAM.cpp:1251-1950 (trigger),
+ * src/PoseGraphSLAM.cpp:178-224 (getters).  C++ users include the facade headers directly. */
+#ifndef PGS_FACADE_H_
+#define PGS_FACADE_H_
+#include <stdint.h>
+#include "pgs.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgs_facade_s* pgs_facade_handle;
+
+typedef struct pgs_facade_options {
+  int32_t odom_fanout;        /* 5, PoseGraphSLAM.cpp:1577 */
+  int32_t derive_odometry;    /* 1: odometry edges derived from the manager's poses (reference behaviour) */
+  int32_t dry_run;            /* 1: build problem + initial guesses on the host only (no CUDA) */
+  pgs_options solver;
+} pgs_facade_options;
+
+int pgs_facade_default_options(pgs_facade_options* o);
+int pgs_facade_create(const pgs_facade_options* o, pgs_facade_handle* out);
+void pgs_facade_destroy(pgs_facade_handle h);
+const char* pgs_facade_last_error(pgs_facade_handle h);
+
+/* ingest (NodeDataManager) */
+int pgs_facade_add_nodes(pgs_facade_handle h, int32_t n, const int64_t* stamps_ns, const double* q_xyzw, const double* t);
+int pgs_facade_add_loop_edges(pgs_facade_handle h, int32_t m, const int32_t* a, const int32_t* b, const double* q_bTa,
+                              const double* t_bTa, const double* w);          /* by node index */
+int pgs_facade_add_loop_edge_stamped(pgs_facade_handle h, int64_t stamp_a_ns, int64_t stamp_b_ns, const double* q_bTa,
+                                     const double* t_bTa, double w);          /* 1 added, 0 dropped (no such keyframe) */
+int pgs_facade_kidnap_indicator(pgs_facade_handle h, int64_t stamp_ns, int32_t kidnapped);
+int pgs_facade_add_odometry_edge(pgs_facade_handle h, int32_t a, int32_t b, const double* q_aTb, const double* t_aTb, double w);
+
+/* one wake-up of the solver thread: 1 solved, 0 not triggered, <0 error */
+int pgs_facade_solve_once(pgs_facade_handle h, int32_t force);
+int pgs_facade_status(pgs_facade_handle h);
+
+/* results (PoseGraphSLAM getters) */
+int32_t pgs_facade_n_nodes(pgs_facade_handle h);
+int32_t pgs_facade_solved_until(pgs_facade_handle h);
+int pgs_facade_get_poses(pgs_facade_handle h, double* q_xyzw, double* t);     /* all nNodes() */
+int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s);       /* per manager loop edge */
+int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* iters, int32_t cap);
+
+/* introspection of the graph-construction rules (parity tests against the oracle front-end) */
+int32_t pgs_facade_n_odom_terms(pgs_facade_handle h);
+int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w);
+int32_t pgs_facade_n_reg_terms(pgs_facade_handle h);
+int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t* node, double* q, double* t, double* w);
+int32_t pgs_facade_which_world(pgs_facade_handle h, int64_t stamp_ns);
+int32_t pgs_facade_n_worlds(pgs_facade_handle h);
+int32_t pgs_facade_world_setid(pgs_facade_handle h, int32_t world);
+int32_t pgs_facade_world_start(pgs_facade_handle h, int32_t world);
+int32_t pgs_facade_world_end(pgs_facade_handle h, int32_t world);
+int pgs_facade_pose_between_worlds(pgs_facade_handle h, int32_t m, int32_t n, double* m_T_n_rowmajor16); /* 1 ok, 0 unknown */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

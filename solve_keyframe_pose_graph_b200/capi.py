@@ -231,9 +231,10 @@ class PoseGraphSolver:
 
     # ---- measurement hooks
     def time_sweep(self, mode=0, reps=10, flush_l2=False):
-        ms = C.c_double(0); n = C.c_int64(0)
-        self._ck(self.L.pgs_time_sweep(self.h, C.c_int32(mode), C.c_int32(reps), C.c_int32(int(flush_l2)), C.byref(ms), C.byref(n)))
-        return ms.value, n.value
+        """-> (ms per step = sweep kernel + cost reduction, ms of the sweep kernel alone, kernel launches)"""
+        ms = C.c_double(0); msk = C.c_double(0); n = C.c_int64(0)
+        self._ck(self.L.pgs_time_sweep(self.h, C.c_int32(mode), C.c_int32(reps), C.c_int32(int(flush_l2)), C.byref(ms), C.byref(msk), C.byref(n)))
+        return ms.value, msk.value, n.value
 
     def evaluate_from_host_ptr(self, q_ptr, t_ptr, s_ptr):
         """Raw-pointer variant (pinned torch tensors): addresses as ints, 0 for 'reuse'."""

@@ -1,0 +1,79 @@
+// ROS-free node / loop-edge store with the getter surface the solver front-end consumes
+// (reference src/NodeDataManager.h:95-111 node/edge getters, :152-187 kidnap/world queries).
+// ros::Time becomes int64 nanoseconds; the ROS callbacks become plain methods:
+//   camera_pose_callback          (NodeDataManager.cpp:23-103)  -> add_node()
+//   loopclosure_pose_callback     (NodeDataManager.cpp:107-189) -> add_loop_edge() (timestamp lookup, 1 ms tolerance)
+//   rcvd_kidnap_indicator_callback(NodeDataManager.cpp:763-792) -> rcvd_kidnap_indicator()
+// Covariances, JSON and extrinsics are out of scope (never read by the solver).
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "Worlds.h"
+#include "pose_math.h"
+
+namespace pgs {
+
+class NodeDataManager {
+ public:
+  NodeDataManager();
+  ~NodeDataManager();
+
+  // ---- ingest
+  void add_node(int64_t stamp_ns, const Matrix4d& w_T_cam);
+  // Returns false (edge dropped) when either timestamp matches no node, as the reference does (:181-185).
+  bool add_loop_edge(int64_t stamp_a_ns, int64_t stamp_b_ns, const Matrix4d& b_T_a, double weight, const std::string& description = "");
+  bool add_loop_edge_by_index(int a, int b, const Matrix4d& b_T_a, double weight, const std::string& description = "");
+  bool rcvd_kidnap_indicator(int64_t stamp_ns, bool kidnapped);
+
+  // ---- node getters
+  int getNodeLen() const;
+  bool getNodePose(int i, Matrix4d& w_T_cam) const;
+  const Matrix4d& getNodePose(int i) const;
+  bool nodePoseExists(int i) const;
+  int64_t getNodeTimestamp(int i) const;
+  // ---- edge getters
+  int getEdgeLen() const;
+  const Matrix4d& getEdgePose(int i) const;                 // b_T_a
+  const std::pair<int, int>& getEdgeIdxInfo(int i) const;   // (a, b)
+  double getEdgeWeight(int i) const;
+  const std::string getEdgeDescriptionString(int i) const;
+
+  // ---- kidnap / world queries
+  bool curr_kidnap_status() const { return current_kidnap_status; }
+  int n_kidnaps() const;
+  int64_t stamp_of_kidnap_i_started(int i) const;
+  int64_t stamp_of_kidnap_i_ended(int i) const;
+  int nodeidx_of_world_i_started(int i) const;
+  int nodeidx_of_world_i_ended(int i) const;
+  int n_worlds() const;
+  // >= 0: world id; negative: kidnap dead zone -(k+1)   (NodeDataManager.cpp:1127-1198)
+  int which_world_is_this(int64_t stamp_ns) const;
+  Worlds* getWorldsPtr() { return worlds_handle_raw_ptr; }
+  const Worlds* getWorldsConstPtr() const { return worlds_handle_raw_ptr; }
+
+ private:
+  int find_indexof_node(int64_t stamp_ns) const;   // caller holds node_mutex
+  int which_world_nolock(int64_t t) const;
+
+  mutable std::mutex node_mutex;
+  std::vector<Matrix4d> node_pose;
+  std::vector<int64_t> node_timestamps;
+
+  mutable std::mutex edge_mutex;
+  std::vector<std::pair<int, int>> loopclosure_edges;
+  std::vector<double> loopclosure_edges_goodness;
+  std::vector<Matrix4d> loopclosure_p_T_c;
+  std::vector<std::string> loopclosure_description;
+
+  mutable std::mutex mutex_kidnap;
+  std::vector<int64_t> kidnap_starts, kidnap_ends;
+  std::atomic<bool> current_kidnap_status;
+  Worlds* worlds_handle_raw_ptr = nullptr;
+};
+
+}  // namespace pgs

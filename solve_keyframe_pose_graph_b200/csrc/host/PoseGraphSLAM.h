@@ -1,0 +1,117 @@
+// ROS-free drop-in for the reference's PoseGraphSLAM class (reference src/PoseGraphSLAM.h:57-223): same
+// constructor, solver-thread entry point, status codes and thread-safe getters, but the body of
+// reinit_ceres_problem_onnewloopedge_optimize6DOF() builds the problem through the C-ABI of
+// include/pgs.h and solves it on the B200 instead of calling ceres::Solve.
+//
+// Additions named by BASELINE.json's north_star (absent in the reference): addOdometryEdge / addLoopEdge
+// for explicit graphs, and solve_once() = one trigger body without the 0.5 Hz sleep loop.
+#pragma once
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../../include/pgs.h"
+#include "NodeDataManager.h"
+#include "pose_math.h"
+
+namespace pgs {
+
+struct PoseGraphSLAMOptions {
+  int odom_fanout = 5;              // f = 1..5, reference PoseGraphSLAM.cpp:1577
+  double odom_decay = 0.9;          // pow(0.9, f), :1604
+  double odom_yaw_divisor = 6.0;    // exp(-yaw_deg^2 / 6), :1606
+  double min_reg_weight = 1.1;      // max(1.1, log(1 + end - start)/2), :1839
+  bool derive_odometry = true;      // false: only edges given through addOdometryEdge
+  double loop_rate_hz = 0.5;        // ros::Rate loop_rate(0.5), :1257
+  bool dry_run = false;             // build the problem and the initial guesses on the host, skip the device
+  pgs_options solver;               // Ceres-equivalent + device options (pgs_default_options)
+  PoseGraphSLAMOptions() { pgs_default_options(&solver); }
+};
+
+class PoseGraphSLAM {
+ public:
+  explicit PoseGraphSLAM(NodeDataManager* _manager, const PoseGraphSLAMOptions& options = PoseGraphSLAMOptions());
+  ~PoseGraphSLAM();
+
+  // Intended to run on its own thread: polls the manager at loop_rate_hz and solves when new loop edges
+  // arrived (PoseGraphSLAM.cpp:1251-1950).
+  void reinit_ceres_problem_onnewloopedge_optimize6DOF();
+  void reinit_ceres_problem_onnewloopedge_optimize6DOF_enable() { isEnabled = true; }
+  void reinit_ceres_problem_onnewloopedge_optimize6DOF_disable() { isEnabled = false; }
+  // -1 nothing happening, 0 sleeping, 1 setting up, 2 solve in progress, 3 solve finished (PoseGraphSLAM.h:100-105)
+  int get_reinit_ceres_problem_onnewloopedge_optimize6DOF_status() { return status; }
+
+  // One wake-up of the loop above.  Returns true if a solve was triggered.  force = solve even without
+  // new loop edges.  On failure returns false and last_error() is non-empty.
+  bool solve_once(bool force = false);
+  const std::string& last_error() const { return error_; }
+
+  // Explicit-graph API (north_star).  Poses are 4x4: a_T_b for odometry (binds SixDOFError(a, b)),
+  // b_T_a for loop edges (stored in the manager, bound as (b, a, switch)).
+  bool addOdometryEdge(int a, int b, const Matrix4d& a_T_b, double weight);
+  bool addLoopEdge(int a, int b, const Matrix4d& b_T_a, double weight);
+
+  // ---- thread-safe getters (PoseGraphSLAM.cpp:178-224)
+  const Matrix4d getNodePose(int i) const;
+  bool nodePoseExists(int i) const;
+  int nNodes() const;
+  void getAllNodePose(std::vector<Matrix4d>& vec_w_T_ci) const;
+  int solvedUntil() const { std::lock_guard<std::mutex> lk(mutex_opt_vars); return solved_until; }
+  double get_loopedge_switching_variable_val(int i) const;      // i = loop-edge index; NaN for a bad index
+  const std::tuple<int, int, float, std::string>& get_odomedge_residue_info(int i) const;
+  int get_odomedge_residue_info_size() const;
+  const std::tuple<int, int, float, std::string, std::string>& get_loopedge_residue_info(int i) const;
+  int get_loopedge_residue_info_size() const;
+
+  // ---- introspection for tests / bench
+  const pgs_summary& last_summary() const { return summary_; }
+  const std::vector<pgs_iteration>& last_iterations() const { return iterations_; }
+  struct RegTerm { int node; Matrix4d anchor; double weight; };
+  const std::vector<RegTerm>& regularization_terms() const { return reg_terms_; }
+  struct OdomTerm { int u, umf; double q[4], t[3], weight; };
+  const std::vector<OdomTerm>& odometry_terms() const { return odom_terms_; }
+  pgs_handle device_handle() { return handle_; }
+
+ private:
+  bool fail(const std::string& msg) { error_ = msg; status = 0; return false; }
+  void allocate_and_append_new_opt_variable_withpose(const Matrix4d& pose);
+  bool update_opt_variable_with(int i, const Matrix4d& pose);
+  void allocate_and_append_new_edge_switch_var();
+  int n_opt_variables() const;
+  int n_opt_switch() const;
+
+  NodeDataManager* manager;
+  PoseGraphSLAMOptions opt_;
+  std::atomic<bool> isEnabled;
+  std::atomic<int> status;
+  std::string error_;
+
+  mutable std::mutex mutex_opt_vars;
+  std::vector<double> _opt_quat_;    // x,y,z,w per node (PoseGraphSLAM.h:153)
+  std::vector<double> _opt_t_;
+  std::vector<double> _opt_switch_;  // one per loop edge of the manager
+  int solved_until = 0;
+
+  mutable std::mutex mutex_residue_info;
+  std::vector<std::tuple<int, int, float, std::string>> odometry_edges_terms;
+  std::vector<std::tuple<int, int, float, std::string, std::string>> loop_edges_terms;
+
+  // trigger state that persists across wake-ups (locals of the reference's thread function)
+  int prev_loopedge_len = 0, prev_node_len = 0;
+  std::map<int, std::tuple<int, int>> changes_to_setid_on_set_union;
+  std::vector<RegTerm> reg_terms_;
+  std::vector<OdomTerm> odom_terms_;
+  std::vector<OdomTerm> pending_explicit_odom_;
+  std::vector<int> loop_slot_;       // manager loop-edge index -> device loop-edge index (-1: skipped, dead zone)
+  int n_device_nodes_ = 0, n_device_loops_ = 0;
+  int odom_scanned_until_ = 0;       // odometry edges exist for u <= this
+
+  pgs_handle handle_ = nullptr;
+  pgs_summary summary_{};
+  std::vector<pgs_iteration> iterations_;
+};
+
+}  // namespace pgs

@@ -1,0 +1,123 @@
+// C view of the facade (include/pgs_facade.h).
+#include "../../../include/pgs_facade.h"
+
+#include <cstring>
+#include <string>
+
+#include "PoseGraphSLAM.h"
+
+struct pgs_facade_s {
+  pgs::NodeDataManager manager;
+  pgs::PoseGraphSLAM* slam = nullptr;
+  std::string err;
+  ~pgs_facade_s() { delete slam; }
+};
+
+extern "C" {
+
+int pgs_facade_default_options(pgs_facade_options* o) {
+  if (!o) return PGS_ERR_INVALID_ARGUMENT;
+  o->odom_fanout = 5; o->derive_odometry = 1; o->dry_run = 0;
+  return pgs_default_options(&o->solver);
+}
+int pgs_facade_create(const pgs_facade_options* o, pgs_facade_handle* out) {
+  if (!out) return PGS_ERR_INVALID_ARGUMENT;
+  pgs_facade_options d;
+  if (o) d = *o; else pgs_facade_default_options(&d);
+  pgs_facade_s* h = new pgs_facade_s();
+  pgs::PoseGraphSLAMOptions po;
+  po.odom_fanout = d.odom_fanout; po.derive_odometry = d.derive_odometry != 0; po.dry_run = d.dry_run != 0; po.solver = d.solver;
+  h->slam = new pgs::PoseGraphSLAM(&h->manager, po);
+  *out = h;
+  return PGS_OK;
+}
+void pgs_facade_destroy(pgs_facade_handle h) { delete h; }
+const char* pgs_facade_last_error(pgs_facade_handle h) { return h ? (h->err.empty() ? h->slam->last_error().c_str() : h->err.c_str()) : ""; }
+
+int pgs_facade_add_nodes(pgs_facade_handle h, int32_t n, const int64_t* stamps, const double* q, const double* t) {
+  if (!h || n < 0 || (n && (!stamps || !q || !t))) return PGS_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < n; ++i) h->manager.add_node(stamps[i], pgs::raw_xyzw_to_mat(q + 4 * (size_t)i, t + 3 * (size_t)i));
+  return PGS_OK;
+}
+int pgs_facade_add_loop_edges(pgs_facade_handle h, int32_t m, const int32_t* a, const int32_t* b, const double* q, const double* t, const double* w) {
+  if (!h || m < 0 || (m && (!a || !b || !q || !t))) return PGS_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < m; ++i)
+    if (!h->manager.add_loop_edge_by_index(a[i], b[i], pgs::raw_xyzw_to_mat(q + 4 * (size_t)i, t + 3 * (size_t)i), w ? w[i] : 1.0)) {
+      h->err = "loop edge endpoint out of range"; return PGS_ERR_INVALID_ARGUMENT; }
+  return PGS_OK;
+}
+int pgs_facade_add_loop_edge_stamped(pgs_facade_handle h, int64_t sa, int64_t sb, const double* q, const double* t, double w) {
+  if (!h || !q || !t) return PGS_ERR_INVALID_ARGUMENT;
+  return h->manager.add_loop_edge(sa, sb, pgs::raw_xyzw_to_mat(q, t), w) ? 1 : 0;
+}
+int pgs_facade_kidnap_indicator(pgs_facade_handle h, int64_t stamp, int32_t kidnapped) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  return h->manager.rcvd_kidnap_indicator(stamp, kidnapped != 0) ? PGS_OK : PGS_ERR_STATE;
+}
+int pgs_facade_add_odometry_edge(pgs_facade_handle h, int32_t a, int32_t b, const double* q, const double* t, double w) {
+  if (!h || !q || !t) return PGS_ERR_INVALID_ARGUMENT;
+  return h->slam->addOdometryEdge(a, b, pgs::raw_xyzw_to_mat(q, t), w) ? PGS_OK : PGS_ERR_INVALID_ARGUMENT;
+}
+int pgs_facade_solve_once(pgs_facade_handle h, int32_t force) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  const bool ok = h->slam->solve_once(force != 0);
+  if (!ok && !h->slam->last_error().empty()) return PGS_ERR_STATE;
+  return ok ? 1 : 0;
+}
+int pgs_facade_status(pgs_facade_handle h) { return h ? h->slam->get_reinit_ceres_problem_onnewloopedge_optimize6DOF_status() : -1; }
+int32_t pgs_facade_n_nodes(pgs_facade_handle h) { return h ? h->slam->nNodes() : 0; }
+int32_t pgs_facade_solved_until(pgs_facade_handle h) { return h ? h->slam->solvedUntil() : 0; }
+int pgs_facade_get_poses(pgs_facade_handle h, double* q, double* t) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  const int n = h->slam->nNodes();
+  for (int i = 0; i < n; ++i) { double qq[4], tt[3]; pgs::mat_to_raw_xyzw(h->slam->getNodePose(i), qq, tt);
+    if (q) std::memcpy(q + 4 * (size_t)i, qq, 32); if (t) std::memcpy(t + 3 * (size_t)i, tt, 24); }
+  return PGS_OK;
+}
+int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s) {
+  if (!h || !s) return PGS_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < n; ++i) s[i] = h->slam->get_loopedge_switching_variable_val(i);
+  return PGS_OK;
+}
+int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* iters, int32_t cap) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  if (s) *s = h->slam->last_summary();
+  const auto& it = h->slam->last_iterations();
+  for (int i = 0; iters && i < cap && i < (int)it.size(); ++i) iters[i] = it[i];
+  return PGS_OK;
+}
+int32_t pgs_facade_n_odom_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->odometry_terms().size() : 0; }
+int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  const auto& v = h->slam->odometry_terms();
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (u) u[i] = v[i].u; if (umf) umf[i] = v[i].umf; if (w) w[i] = v[i].weight;
+    if (q) std::memcpy(q + 4 * i, v[i].q, 32); if (t) std::memcpy(t + 3 * i, v[i].t, 24);
+  }
+  return PGS_OK;
+}
+int32_t pgs_facade_n_reg_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->regularization_terms().size() : 0; }
+int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t* node, double* q, double* t, double* w) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  const auto& v = h->slam->regularization_terms();
+  for (size_t i = 0; i < v.size(); ++i) {
+    double qq[4], tt[3]; pgs::mat_to_raw_xyzw(v[i].anchor, qq, tt);
+    if (node) node[i] = v[i].node; if (w) w[i] = v[i].weight;
+    if (q) std::memcpy(q + 4 * i, qq, 32); if (t) std::memcpy(t + 3 * i, tt, 24);
+  }
+  return PGS_OK;
+}
+int32_t pgs_facade_which_world(pgs_facade_handle h, int64_t stamp) { return h->manager.which_world_is_this(stamp); }
+int32_t pgs_facade_n_worlds(pgs_facade_handle h) { return h->manager.n_worlds(); }
+int32_t pgs_facade_world_setid(pgs_facade_handle h, int32_t w) { return h->manager.getWorldsPtr()->find_setID_of_world_i(w); }
+int32_t pgs_facade_world_start(pgs_facade_handle h, int32_t w) { return h->manager.nodeidx_of_world_i_started(w); }
+int32_t pgs_facade_world_end(pgs_facade_handle h, int32_t w) { return h->manager.nodeidx_of_world_i_ended(w); }
+int pgs_facade_pose_between_worlds(pgs_facade_handle h, int32_t m, int32_t n, double* M16) {
+  bool ok = true;
+  const pgs::Matrix4d T = h->manager.getWorldsPtr()->getPoseBetweenWorlds(m, n, &ok);
+  if (M16) std::memcpy(M16, T.m, 128);
+  return ok ? 1 : 0;
+}
+
+}  // extern "C"

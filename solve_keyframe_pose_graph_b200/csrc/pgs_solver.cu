@@ -317,7 +317,7 @@ int Solver::read_scalars(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-int Solver::launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev) {
+int Solver::launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev, cudaEvent_t after_kernel) {
   SweepArgs A;
   A.pose = pose; A.sw = sw;
   A.o_idx = d_oidx.p; A.o_obs = d_oobs.p; A.n_odom = (int)o_c1.size();
@@ -328,6 +328,7 @@ int Solver::launch_sweep(int mode, const double* pose, const double* sw, double*
   const int tiles = cdiv(A.n_odom, TILE) + cdiv(A.n_loop, TILE) + cdiv(A.n_reg, TILE);
   const int grid = std::max(1, std::min(sweep_grid, cdiv(tiles, 8)));
   if (mode == 0) sweep_kernel<0><<<grid, 256, 0, stream>>>(A); else sweep_kernel<1><<<grid, 256, 0, stream>>>(A);
+  if (after_kernel) cudaEventRecord(after_kernel, stream);
   reduce_sum_kernel<<<1, 256, 0, stream>>>(d_partial.p, grid, 0.5, cost_out_dev);
   CU(cudaGetLastError());
   return PGS_OK;
@@ -516,30 +517,28 @@ int Solver::linear_step(double radius, double* delta_pose, double* delta_switch,
   return PGS_OK;
 }
 
-int Solver::time_sweep(int mode, int reps, int flush_l2, double* ms, int64_t* launches) {
+int Solver::time_sweep(int mode, int reps, int flush_l2, double* ms, double* ms_kernel, int64_t* launches) {
   CU(cudaSetDevice(dev));
   if (int rc = sync_params_to_device()) return rc;
   if (reps < 1) reps = 1;
   size_t flush_n = 0;
   if (flush_l2) { flush_n = (size_t)48 << 20; CU(d_flush.resize(flush_n)); }   // 384 MiB of doubles > 126 MB L2
-  double total = 0.0;
-  if (!flush_l2) {
+  cudaEvent_t evk; CU(cudaEventCreate(&evk));
+  double total = 0.0, total_k = 0.0;
+  // every repetition is timed on its own: [ev0] sweep kernel [evk] cost reduction [ev1]; the optional L2
+  // flush runs between repetitions, outside the timed span
+  for (int i = 0; i < reps; ++i) {
+    if (flush_l2) flush_kernel<<<1184, 256, 0, stream>>>(d_flush.p, flush_n, (double)i);
     CU(cudaEventRecord(ev0, stream));
-    for (int i = 0; i < reps; ++i) if (int rc = launch_sweep(mode, d_pose.p, d_sw.p, d_scal.p + L_COST)) return rc;
+    if (int rc = launch_sweep(mode, d_pose.p, d_sw.p, d_scal.p + L_COST, evk)) return rc;
     CU(cudaEventRecord(ev1, stream));
     CU(cudaEventSynchronize(ev1));
-    float t = 0; CU(cudaEventElapsedTime(&t, ev0, ev1)); total = t;
-  } else {
-    for (int i = 0; i < reps; ++i) {
-      flush_kernel<<<1184, 256, 0, stream>>>(d_flush.p, flush_n, (double)i);
-      CU(cudaEventRecord(ev0, stream));
-      if (int rc = launch_sweep(mode, d_pose.p, d_sw.p, d_scal.p + L_COST)) return rc;
-      CU(cudaEventRecord(ev1, stream));
-      CU(cudaEventSynchronize(ev1));
-      float t = 0; CU(cudaEventElapsedTime(&t, ev0, ev1)); total += t;
-    }
+    float t = 0, tk = 0; CU(cudaEventElapsedTime(&t, ev0, ev1)); CU(cudaEventElapsedTime(&tk, ev0, evk));
+    total += t; total_k += tk;
   }
+  cudaEventDestroy(evk);
   if (ms) *ms = total / reps;
+  if (ms_kernel) *ms_kernel = total_k / reps;
   if (launches) *launches = 2LL * reps;   // sweep + cost reduction per repetition
   return PGS_OK;
 }

@@ -59,7 +59,7 @@ class Solver {
   int assemble(double* diag, int* pair_hi, int* pair_lo, double* offdiag, double* loop_v, double* loop_hss);
   int linear_step(double radius, double* delta_pose, double* delta_switch, double* mcc, int* lin_iters);
   int solve(pgs_summary* sum, pgs_iteration* iters, int cap);
-  int time_sweep(int mode, int reps, int flush_l2, double* ms, int64_t* launches);
+  int time_sweep(int mode, int reps, int flush_l2, double* ms, double* ms_kernel, int64_t* launches);
   int evaluate_from_host(const double* q, const double* t, const double* s, double* cost);
   int64_t sweep_bytes() const;
   void sizes(pgs_sizes* s);
@@ -73,7 +73,7 @@ class Solver {
   int finalize();                        // sort edges, build incidence/pair/adjacency structures, upload
   int sync_params_to_device();           // host q,t,sw -> device pose / sw (if dirty)
   int sync_params_to_host();             // device -> host mirrors (if device is newer)
-  int launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev);
+  int launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev, cudaEvent_t after_kernel = nullptr);
   int run_assemble();
   int compute_scaling(bool compute_scale);
   int build_system(double radius);

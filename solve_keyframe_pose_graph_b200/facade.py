@@ -1,0 +1,160 @@
+"""ctypes view of include/pgs_facade.h: the ROS-free NodeDataManager + PoseGraphSLAM pair.
+
+`Facade` mirrors how reference src/keyframe_pose_graph_slam_node.cpp drives the two classes: feed
+keyframe poses / loop edges / kidnap signals into the manager, run one wake-up of
+`reinit_ceres_problem_onnewloopedge_optimize6DOF()`, read `getNodePose` back."""
+import ctypes as C
+
+import numpy as np
+
+from .capi import Iteration, Options, PgsError, Summary, TERMINATION, c_dp, c_ip, lib
+
+
+class FacadeOptions(C.Structure):
+    _fields_ = [("odom_fanout", C.c_int32), ("derive_odometry", C.c_int32), ("dry_run", C.c_int32), ("solver", Options)]
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_ip)
+
+
+class Facade:
+    def __init__(self, odom_fanout=5, derive_odometry=True, dry_run=False, **solver_opts):
+        self.L = lib()
+        self.L.pgs_facade_last_error.restype = C.c_char_p
+        self.L.pgs_facade_last_error.argtypes = [C.c_void_p]
+        o = FacadeOptions()
+        self.L.pgs_facade_default_options(C.byref(o))
+        o.odom_fanout = odom_fanout; o.derive_odometry = int(derive_odometry); o.dry_run = int(dry_run)
+        for k, v in solver_opts.items():
+            if not hasattr(o.solver, k):
+                raise AttributeError(k)
+            setattr(o.solver, k, v)
+        self.opt = o
+        self.h = C.c_void_p()
+        if self.L.pgs_facade_create(C.byref(o), C.byref(self.h)) != 0:
+            raise PgsError("pgs_facade_create failed")
+        self.n_loop = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pgs_facade_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise PgsError(f"facade error {rc}: {self.L.pgs_facade_last_error(self.h).decode()}")
+        return rc
+
+    # ---- ingest
+    def add_nodes(self, stamps, q, t):
+        stamps = np.ascontiguousarray(stamps, dtype=np.int64); q, qp = _d(q); t, tp = _d(t)
+        self._ck(self.L.pgs_facade_add_nodes(self.h, C.c_int32(len(stamps)), stamps.ctypes.data_as(C.c_void_p), qp, tp))
+
+    def add_loop_edges(self, a, b, q, t, w):
+        a, ap = _i(a); b, bp = _i(b); q, qp = _d(q); t, tp = _d(t); w, wp = _d(w)
+        self._ck(self.L.pgs_facade_add_loop_edges(self.h, C.c_int32(len(a)), ap, bp, qp, tp, wp)); self.n_loop += len(a)
+
+    def add_loop_edge_stamped(self, sa, sb, q, t, w=1.0):
+        q, qp = _d(q); t, tp = _d(t)
+        r = self._ck(self.L.pgs_facade_add_loop_edge_stamped(self.h, C.c_int64(sa), C.c_int64(sb), qp, tp, C.c_double(w)))
+        self.n_loop += r
+        return bool(r)
+
+    def kidnap_indicator(self, stamp, kidnapped):
+        self._ck(self.L.pgs_facade_kidnap_indicator(self.h, C.c_int64(int(stamp)), C.c_int32(int(kidnapped))))
+
+    def add_odometry_edge(self, a, b, q, t, w):
+        q, qp = _d(q); t, tp = _d(t)
+        self._ck(self.L.pgs_facade_add_odometry_edge(self.h, C.c_int32(a), C.c_int32(b), qp, tp, C.c_double(w)))
+
+    def ingest(self, g):
+        """Feed a generated graph (synth.generate) in time order: nodes, kidnap signals, then loop edges."""
+        ev = sorted([(int(s), 1) for s in g["k0"]] + [(int(s), 0) for s in g["k1"]])
+        pos = 0
+        for stamp, kid in ev:
+            # nodes with stamp <= kidnap-start belong before the signal; un-kidnap precedes the next world's first node
+            cut = int(np.searchsorted(g["stamps"], stamp, side="right"))
+            if cut > pos:
+                self.add_nodes(g["stamps"][pos:cut], g["q"][pos:cut], g["t"][pos:cut]); pos = cut
+            self.kidnap_indicator(stamp, kid)
+        if pos < g["N"]:
+            self.add_nodes(g["stamps"][pos:], g["q"][pos:], g["t"][pos:])
+        if len(g["la"]):
+            self.add_loop_edges(g["la"], g["lb"], g["lq"], g["lt"], g["lw"])
+
+    # ---- solve
+    def solve_once(self, force=False):
+        return self._ck(self.L.pgs_facade_solve_once(self.h, C.c_int32(int(force)))) == 1
+
+    def status(self):
+        return self.L.pgs_facade_status(self.h)
+
+    # ---- results
+    def n_nodes(self):
+        return self.L.pgs_facade_n_nodes(self.h)
+
+    def solved_until(self):
+        return self.L.pgs_facade_solved_until(self.h)
+
+    def poses(self):
+        n = self.n_nodes(); q = np.zeros((n, 4)); t = np.zeros((n, 3))
+        self._ck(self.L.pgs_facade_get_poses(self.h, q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp)))
+        return q, t
+
+    def switches(self):
+        s = np.zeros(max(self.n_loop, 1))
+        self._ck(self.L.pgs_facade_get_switches(self.h, C.c_int32(self.n_loop), s.ctypes.data_as(c_dp)))
+        return s[: self.n_loop]
+
+    def summary(self):
+        s = Summary(); cap = self.opt.solver.max_num_iterations + 8; its = (Iteration * cap)()
+        self._ck(self.L.pgs_facade_get_summary(self.h, C.byref(s), its, C.c_int32(cap)))
+        d = {f: getattr(s, f) for f, _ in Summary._fields_}
+        d["termination"] = TERMINATION.get(s.termination, "?")
+        d["iterations"] = [{f: getattr(its[i], f) for f, _ in Iteration._fields_} for i in range(min(s.num_iterations, cap))]
+        return d
+
+    # ---- introspection
+    def odom_terms(self):
+        n = self.L.pgs_facade_n_odom_terms(self.h)
+        u = np.zeros(n, np.int32); v = np.zeros(n, np.int32); q = np.zeros((n, 4)); t = np.zeros((n, 3)); w = np.zeros(n)
+        self._ck(self.L.pgs_facade_get_odom_terms(self.h, u.ctypes.data_as(c_ip), v.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
+        return dict(u=u, umf=v, q=q, t=t, w=w)
+
+    def reg_terms(self):
+        n = self.L.pgs_facade_n_reg_terms(self.h)
+        node = np.zeros(n, np.int32); q = np.zeros((n, 4)); t = np.zeros((n, 3)); w = np.zeros(n)
+        self._ck(self.L.pgs_facade_get_reg_terms(self.h, node.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
+        return dict(node=node, q=q, t=t, w=w)
+
+    def which_world(self, stamp):
+        return self.L.pgs_facade_which_world(self.h, C.c_int64(int(stamp)))
+
+    def n_worlds(self):
+        return self.L.pgs_facade_n_worlds(self.h)
+
+    def world_setid(self, w):
+        return self.L.pgs_facade_world_setid(self.h, C.c_int32(w))
+
+    def world_start(self, w):
+        return self.L.pgs_facade_world_start(self.h, C.c_int32(w))
+
+    def world_end(self, w):
+        return self.L.pgs_facade_world_end(self.h, C.c_int32(w))
+
+    def pose_between_worlds(self, m, n):
+        M = np.zeros((4, 4))
+        ok = self.L.pgs_facade_pose_between_worlds(self.h, C.c_int32(m), C.c_int32(n), M.ctypes.data_as(c_dp))
+        return M if ok else None
