@@ -7,10 +7,23 @@
 namespace pgs {
 struct SkylineFactor;
 // Symbolic phase (host): envelope of every node row from the pair list (hi > lo), panel partition, row lists.
-SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err);
+// n_border_nodes > 0: the last n_border_nodes nodes are border unknowns of a domain decomposition — they are
+// not eliminated, their rows keep the whole border block, and (N - n_border_nodes) * 6 must be a multiple of
+// skyline_panel_width().
+SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
+                              int n_border_nodes = 0);
 void skyline_destroy(SkylineFactor* f);
 int64_t skyline_nnz(const SkylineFactor* f);
+int skyline_panel_width();
 // Numeric phase (device): scatter Ad[N][36] / Ao[P][36] into the envelope, factor A = L L^T, solve A y = b.
 // Returns PGS_OK, PGS_ERR_LINEAR_SOLVER (non-positive pivot) or a CUDA error code.
 int skyline_factor_solve(SkylineFactor* f, const double* Ad, const double* Ao, const double* b, double* y, std::string* err);
+// The same in pieces (multi-GPU): eliminate the interior panels; read the border Schur complement (packed lower
+// triangle, nb(nb+1)/2) and forward-substituted border rhs; after the border solve put x_border into
+// y[interior_scalars .. n) and back-substitute the interior; check the pivot flag (synchronises).
+int skyline_factor(SkylineFactor* f, const double* Ad, const double* Ao, const double* b, std::string* err);
+int skyline_border_get(SkylineFactor* f, double* S_packed, double* rhs, std::string* err);
+int skyline_backward(SkylineFactor* f, double* y, std::string* err);
+int skyline_check(SkylineFactor* f, std::string* err);
+int skyline_interior_scalars(const SkylineFactor* f);
 }  // namespace pgs
