@@ -144,6 +144,26 @@ int pgs_linear_step(pgs_handle h, double radius, double* delta_pose, double* del
  *      (PoseGraphSLAM.cpp:1903).  iters may be NULL; at most iters_cap rows are written. ---- */
 int pgs_solve(pgs_handle h, pgs_summary* summary, pgs_iteration* iters, int32_t iters_cap);
 
+/* ---- multi-GPU: one process per GPU, node-range sharding.  Every process loads the
+ *      SAME full graph through the calls above, then attaches a communicator; pgs_solve() then sweeps/assembles
+ *      only this rank's residual blocks, eliminates this rank's interior nodes and all-reduces the border Schur
+ *      system once per LM iteration over NCCL.  After the solve every rank holds all optimised poses. ---- */
+typedef struct pgs_dist_stats {
+  int32_t rank, world;
+  int32_t n_interior_nodes, n_border_nodes;         /* this rank's interior; border is global */
+  int32_t n_odom_owned, n_loop_owned, n_reg_owned;
+  int64_t border_buffer_bytes;                      /* size of the per-iteration all-reduce */
+  int64_t n_collectives, bytes_reduced;             /* over the last solve */
+} pgs_dist_stats;
+int pgs_dist_unique_id(void* id128);                /* rank 0: ncclGetUniqueId; distribute the 128 bytes yourself */
+int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128);
+int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out);
+/* The partition rule on its own (host only, no device needed): node_owner[N] = owning rank or -1 for a border
+ * node; *_owner = rank that evaluates each residual block.  Loop edge e couples (a[e], b[e]). */
+int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t* c1, const int32_t* c2, int32_t n_loop,
+                  const int32_t* a, const int32_t* b, int32_t n_reg, const int32_t* reg_node, int32_t* node_owner,
+                  int32_t* odom_owner, int32_t* loop_owner, int32_t* reg_owner, int32_t* n_border);
+
 /* ---- measurement hooks used by bench.py ---- */
 /* Runs the residual+Jacobian sweep `reps` times with every input already resident in HBM and
  * returns the mean device time in milliseconds, measured per repetition with CUDA events on the

@@ -64,6 +64,12 @@ class Sizes(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_odom", C.c_int32), ("n_loop", C.c_int32), ("n_reg", C.c_int32), ("n_pairs", C.c_int32)]
 
 
+class DistStats(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_interior_nodes", C.c_int32), ("n_border_nodes", C.c_int32),
+                ("n_odom_owned", C.c_int32), ("n_loop_owned", C.c_int32), ("n_reg_owned", C.c_int32),
+                ("border_buffer_bytes", C.c_int64), ("n_collectives", C.c_int64), ("bytes_reduced", C.c_int64)]
+
+
 SKYLINE_CHOLESKY, BLOCK_PCG = 0, 1
 TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}
 
@@ -105,6 +111,27 @@ def _d(a):
 def _i(a):
     a = np.ascontiguousarray(a, dtype=np.int32)
     return a, a.ctypes.data_as(c_ip)
+
+
+def dist_unique_id():
+    """128-byte NCCL unique id (call on rank 0, broadcast to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().pgs_dist_unique_id(buf)
+    if rc != 0:
+        raise PgsError(f"pgs_dist_unique_id failed ({rc}): {lib().pgs_last_error(None).decode()}")
+    return bytes(buf.raw)
+
+
+def partition(n_nodes, world, oc1, oc2, la, lb, rn):
+    """Host-only view of the node-range partition rule (include/pgs.h pgs_partition)."""
+    oc1, p1 = _i(oc1); oc2, p2 = _i(oc2); la, pa = _i(la); lb, pb = _i(lb); rn, pr = _i(rn)
+    node_owner = np.zeros(max(n_nodes, 1), np.int32); oo = np.zeros(max(len(oc1), 1), np.int32)
+    lo = np.zeros(max(len(la), 1), np.int32); ro = np.zeros(max(len(rn), 1), np.int32); nb = C.c_int32(0)
+    rc = lib().pgs_partition(C.c_int32(n_nodes), C.c_int32(world), C.c_int32(len(oc1)), p1, p2, C.c_int32(len(la)), pa, pb, C.c_int32(len(rn)), pr,
+                             node_owner.ctypes.data_as(c_ip), oo.ctypes.data_as(c_ip), lo.ctypes.data_as(c_ip), ro.ctypes.data_as(c_ip), C.byref(nb))
+    if rc != 0:
+        raise PgsError(f"pgs_partition failed ({rc})")
+    return dict(node_owner=node_owner[:n_nodes], odom_owner=oo[:len(oc1)], loop_owner=lo[:len(la)], reg_owner=ro[:len(rn)], n_border=nb.value)
 
 
 def default_options(**kw):
@@ -228,6 +255,14 @@ class PoseGraphSolver:
         d = {f: getattr(s, f) for f, _ in Summary._fields_}
         d["termination"] = TERMINATION[s.termination]; d["iterations"] = rows
         return d
+
+    # ---- multi-GPU
+    def dist_init(self, rank, world, unique_id):
+        self._ck(self.L.pgs_dist_init(self.h, C.c_int32(rank), C.c_int32(world), C.c_char_p(unique_id)))
+
+    def dist_stats(self):
+        s = DistStats(); self._ck(self.L.pgs_dist_get_stats(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in DistStats._fields_}
 
     # ---- measurement hooks
     def time_sweep(self, mode=0, reps=10, flush_l2=False):

@@ -2,6 +2,7 @@
 #include <new>
 #include <string>
 #include "pgs_solver.h"
+#include "host/partition.h"
 
 using pgs::Solver;
 static thread_local std::string g_create_error;
@@ -61,5 +62,30 @@ int pgs_solve(pgs_handle h, pgs_summary* sum, pgs_iteration* iters, int32_t cap)
 int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush, double* ms, double* ms_kernel, int64_t* launches) { H(h); return h->s->time_sweep(mode, reps, flush, ms, ms_kernel, launches); }
 int pgs_evaluate_from_host(pgs_handle h, const double* q, const double* t, const double* s, double* cost) { H(h); return h->s->evaluate_from_host(q, t, s, cost); }
 int64_t pgs_sweep_algorithmic_bytes(pgs_handle h) { if (!h || !h->s) return 0; return h->s->sweep_bytes(); }
+
+
+int pgs_dist_unique_id(void* id128) {
+  if (!id128) return PGS_ERR_INVALID_ARGUMENT;
+  return pgs::Comm::unique_id(id128, &g_create_error);
+}
+int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128) { H(h); return h->s->dist_init(rank, world, id128); }
+int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out) { H(h); if (!out) return PGS_ERR_INVALID_ARGUMENT; return h->s->dist_stats(out); }
+int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t* c1, const int32_t* c2, int32_t n_loop, const int32_t* a,
+                  const int32_t* b, int32_t n_reg, const int32_t* reg_node, int32_t* node_owner, int32_t* odom_owner, int32_t* loop_owner,
+                  int32_t* reg_owner, int32_t* n_border) {
+  if (n_nodes < 0 || world < 1 || n_odom < 0 || n_loop < 0 || n_reg < 0) return PGS_ERR_INVALID_ARGUMENT;
+  if ((n_odom && (!c1 || !c2)) || (n_loop && (!a || !b)) || (n_reg && !reg_node)) return PGS_ERR_INVALID_ARGUMENT;
+  for (int e = 0; e < n_odom; ++e) if (c1[e] < 0 || c1[e] >= n_nodes || c2[e] < 0 || c2[e] >= n_nodes) return PGS_ERR_INVALID_ARGUMENT;
+  for (int e = 0; e < n_loop; ++e) if (a[e] < 0 || a[e] >= n_nodes || b[e] < 0 || b[e] >= n_nodes) return PGS_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < n_reg; ++k) if (reg_node[k] < 0 || reg_node[k] >= n_nodes) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::Partition P;
+  pgs::make_partition(n_nodes, world, n_odom, c1, c2, n_loop, a, b, n_reg, reg_node, &P);
+  if (node_owner) for (int i = 0; i < n_nodes; ++i) node_owner[i] = P.node_owner[i];
+  if (odom_owner) for (int e = 0; e < n_odom; ++e) odom_owner[e] = P.odom_owner[e];
+  if (loop_owner) for (int e = 0; e < n_loop; ++e) loop_owner[e] = P.loop_owner[e];
+  if (reg_owner) for (int k = 0; k < n_reg; ++k) reg_owner[k] = P.reg_owner[k];
+  if (n_border) *n_border = (int)P.border.size();
+  return PGS_OK;
+}
 
 }  // extern "C"

@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(128) assemble_switch_kernel(AsmArgs A) {
 // ------------------------------------------------------------------ K3: scaling, LM diagonal, switch elimination
 struct SysArgs {
   int N, n_loop, n_pairs;
+  int first_border;   // nodes >= first_border are border unknowns of a domain decomposition (== N when there are none)
   double inv_radius;
   const int2* __restrict__ l_idx;
   const double* __restrict__ Hd; const double* __restrict__ g; const double* __restrict__ Ho;
@@ -472,8 +473,10 @@ __global__ void __launch_bounds__(128) system_diag_kernel(SysArgs A) {
   double* Ad = A.Ad + 36 * (size_t)i;
   double* rhs = A.b + 6 * (size_t)i;
   if (b0 == b1) {  // node in no residual block: Ceres drops the parameter block; keep the system SPD
+    // (a border node without local blocks contributes nothing to the summed border system)
+    const double one = i >= A.first_border ? 0.0 : 1.0;
 #pragma unroll
-    for (int k = 0; k < 36; ++k) Ad[k] = (k % 7 == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < 36; ++k) Ad[k] = (k % 7 == 0) ? one : 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) rhs[k] = 0.0;
     return;
@@ -607,7 +610,8 @@ __global__ void __launch_bounds__(256) model_cost_kernel(MccArgs A) {
 
 // ------------------------------------------------------------------ K5: retraction + norms
 // cand = Plus(x, sign*d) per used node / switch.  Partials: [0]=sum (x-cand)^2, [1]=sum x^2, [2]=max |x-cand|
-__global__ void __launch_bounds__(256) retract_kernel(int N, int n_loop, const char* __restrict__ node_used, const double* __restrict__ pose,
+// Nodes >= count_until are retracted but left out of the norms (border nodes are counted by one rank only).
+__global__ void __launch_bounds__(256) retract_kernel(int N, int count_until, int n_loop, const char* __restrict__ node_used, const double* __restrict__ pose,
                                                       const double* __restrict__ sw, const double* __restrict__ dp, const double* __restrict__ ds,
                                                       double sign, double* __restrict__ cpose, double* __restrict__ csw,
                                                       double* __restrict__ p_diff2, double* __restrict__ p_x2, double* __restrict__ p_max) {
@@ -627,8 +631,9 @@ __global__ void __launch_bounds__(256) retract_kernel(int N, int n_loop, const c
       o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
     } else { o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3]; }
     o[4] = x[4] + sign * dp[6 * (size_t)i + 3]; o[5] = x[5] + sign * dp[6 * (size_t)i + 4]; o[6] = x[6] + sign * dp[6 * (size_t)i + 5];
+    const bool counted = i < count_until;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) { const double df = x[k] - o[k]; d2 += df * df; x2 += x[k] * x[k]; mx = fmax(mx, fabs(df)); c[k] = o[k]; }
+    for (int k = 0; k < 7; ++k) { const double df = x[k] - o[k]; if (counted) { d2 += df * df; x2 += x[k] * x[k]; mx = fmax(mx, fabs(df)); } c[k] = o[k]; }
     c[7] = 0.0;
   }
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_loop; e += stride) {
@@ -647,15 +652,20 @@ __global__ void scatter_lg_kernel(int n_loop, const double* __restrict__ lg, dou
 
 // Jacobi scaling (once, at iteration 0) and the clamped LM diagonal (whenever !reuse_diagonal):
 //   scale = 1/(1+sqrt(colnorm2)) ; diag = clamp(colnorm2 * scale^2, lo, hi)  with colnorm2 = diag(J^T J)
-__global__ void scaling_kernel(int N, int n_loop, const double* __restrict__ Hd, const double* __restrict__ lh, int compute_scale, int jacobi,
+// Border unknowns of a domain decomposition (i >= 6*first_border) stay unscaled and undamped here: their column
+// norms are only partial sums; scaling and damping are applied to the summed border system.
+__global__ void scaling_kernel(int N, int first_border, int n_loop, const double* __restrict__ Hd, const double* __restrict__ lh, int compute_scale, int jacobi,
                                double lo, double hi, double* __restrict__ scale_p, double* __restrict__ scale_s,
                                double* __restrict__ diag_p, double* __restrict__ diag_s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 6 * N) {
-    const double n2 = Hd[36 * (size_t)(i / 6) + (i % 6) * 7];
-    if (compute_scale) scale_p[i] = jacobi ? 1.0 / (1.0 + sqrt(n2)) : 1.0;
-    const double s = scale_p[i];
-    diag_p[i] = fmin(fmax(n2 * s * s, lo), hi);
+    if (i >= 6 * first_border) { scale_p[i] = 1.0; diag_p[i] = 0.0; }
+    else {
+      const double n2 = Hd[36 * (size_t)(i / 6) + (i % 6) * 7];
+      if (compute_scale) scale_p[i] = jacobi ? 1.0 / (1.0 + sqrt(n2)) : 1.0;
+      const double s = scale_p[i];
+      diag_p[i] = fmin(fmax(n2 * s * s, lo), hi);
+    }
   }
   if (i < n_loop) {
     const double n2 = lh[i];

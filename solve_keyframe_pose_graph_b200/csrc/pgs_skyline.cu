@@ -80,13 +80,13 @@ int64_t skyline_nnz(const SkylineFactor* f) { return f ? f->nnz : 0; }
 int skyline_panel_width() { return PW; }
 
 SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
-                              int n_border_nodes) {
+                              int n_border_nodes, bool dense) {
   SkylineFactor* f = new SkylineFactor();
   for (int i = 0; i < NEV; ++i) { f->ev_trsm[i] = nullptr; f->ev_rest[i] = nullptr; }
   f->N = N; f->n = 6 * N; f->D = (f->n + PW - 1) / PW; f->stream = stream; f->n_pairs = n_pairs;
   const int n = f->n, D = f->D;
-  const int N_int = N - n_border_nodes;                       // interior nodes come first, border nodes last
-  f->D_elim = n_border_nodes > 0 ? (6 * N_int) / PW : D;      // the caller pads the interior to a whole number of panels
+  const int N_int = dense ? 0 : N - n_border_nodes;           // interior nodes come first, border nodes last
+  f->D_elim = (!dense && n_border_nodes > 0) ? (6 * N_int) / PW : D;   // the caller pads the interior to a whole number of panels
   // ---- symbolic: envelope start per node = min neighbour, rounded down to a panel boundary
   std::vector<int> nstart(N);
   for (int i = 0; i < N; ++i) nstart[i] = i;
@@ -580,16 +580,45 @@ static int set_attrs(std::string* err) {
   return PGS_OK;
 }
 
+static int skyline_begin(SkylineFactor* f, std::string* err) {
+  if (int rc = set_attrs(err)) return rc;
+  SK(cudaMemsetAsync(f->val, 0, sizeof(double) * (size_t)f->nnz, f->stream));
+  SK(cudaMemsetAsync(f->xacc, 0, sizeof(double) * (size_t)std::max(f->D, 1) * PW, f->stream));
+  SK(cudaMemsetAsync(f->fail, 0, sizeof(int), f->stream));
+  return PGS_OK;
+}
+
+// dense (border) system given as a packed lower triangle + rhs; every row of a dense factor starts at column 0
+__global__ void sky_load_packed_kernel(int n, const long long* __restrict__ ptr, const double* __restrict__ S, const double* __restrict__ rhs,
+                                       double* __restrict__ val) {
+  const long long tot = (long long)n * (n + 1) / 2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    int i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= e) ++i;
+    while ((long long)i * (i + 1) / 2 > e) --i;
+    const int j = (int)(e - (long long)i * (i + 1) / 2);
+    val[ptr[i] + j] = S[e];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) val[ptr[n] + i] = rhs[i];
+}
+int skyline_load_packed(SkylineFactor* f, const double* S_packed, const double* rhs, std::string* err) {
+  if (int rc = skyline_begin(f, err)) return rc;
+  sky_load_packed_kernel<<<592, 256, 0, f->stream>>>(f->n, f->ptr, S_packed, rhs, f->val);
+  SK(cudaGetLastError());
+  return PGS_OK;
+}
+
 // Numeric factorisation of the first D_elim panels (all of them for a single-GPU solve).
 int skyline_factor(SkylineFactor* f, const double* Ad, const double* Ao, const double* b, std::string* err) {
+  if (int rc = skyline_begin(f, err)) return rc;
+  const int tot = std::max(36 * std::max(f->N, f->n_pairs), f->n);
+  sky_scatter_kernel<<<(tot + 255) / 256, 256, 0, f->stream>>>(f->N, f->n_pairs, Ad, Ao, b, f->pair_hi, f->pair_lo, f->ptr, f->start, f->val);
+  return skyline_factor_numeric(f, err);
+}
+
+int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
   cudaStream_t s0 = f->stream, s1 = f->s1;
   const int n = f->n;
-  if (int rc = set_attrs(err)) return rc;
-  SK(cudaMemsetAsync(f->val, 0, sizeof(double) * (size_t)f->nnz, s0));
-  SK(cudaMemsetAsync(f->xacc, 0, sizeof(double) * (size_t)std::max(f->D, 1) * PW, s0));
-  SK(cudaMemsetAsync(f->fail, 0, sizeof(int), s0));
-  const int tot = std::max(36 * std::max(f->N, f->n_pairs), n);
-  sky_scatter_kernel<<<(tot + 255) / 256, 256, 0, s0>>>(f->N, f->n_pairs, Ad, Ao, b, f->pair_hi, f->pair_lo, f->ptr, f->start, f->val);
   SK(cudaEventRecord(f->ev_fork, s0));
   SK(cudaStreamWaitEvent(s1, f->ev_fork, 0));
   // panel stream s1:  [wait rest(d-1)] next(d) ... diag(d) trsm(d) -> ev_trsm[d]
@@ -667,5 +696,6 @@ int skyline_border_get(SkylineFactor* f, double* S_packed, double* rhs, std::str
   return PGS_OK;
 }
 int skyline_interior_scalars(const SkylineFactor* f) { return f->D_elim * PW; }
+const int* skyline_fail_flag(const SkylineFactor* f) { return f->fail; }
 
 }  // namespace pgs

@@ -10,8 +10,9 @@ struct SkylineFactor;
 // n_border_nodes > 0: the last n_border_nodes nodes are border unknowns of a domain decomposition — they are
 // not eliminated, their rows keep the whole border block, and (N - n_border_nodes) * 6 must be a multiple of
 // skyline_panel_width().
+// dense: every row starts at column 0 and everything is eliminated (the summed border system of the Schur scheme).
 SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
-                              int n_border_nodes = 0);
+                              int n_border_nodes = 0, bool dense = false);
 void skyline_destroy(SkylineFactor* f);
 int64_t skyline_nnz(const SkylineFactor* f);
 int skyline_panel_width();
@@ -26,4 +27,7 @@ int skyline_border_get(SkylineFactor* f, double* S_packed, double* rhs, std::str
 int skyline_backward(SkylineFactor* f, double* y, std::string* err);
 int skyline_check(SkylineFactor* f, std::string* err);
 int skyline_interior_scalars(const SkylineFactor* f);
+int skyline_load_packed(SkylineFactor* f, const double* S_packed, const double* rhs, std::string* err);   // dense factor: zero + load
+int skyline_factor_numeric(SkylineFactor* f, std::string* err);                                            // the panel loop on what is loaded
+const int* skyline_fail_flag(const SkylineFactor* f);                                                      // device int, 1 = non-positive pivot
 }  // namespace pgs

@@ -16,8 +16,6 @@ namespace pgs {
 
 #define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return cuda_fail(e__, #x); } while (0)
 
-static constexpr int MAX_GRID = 2048;
-enum { L_COST = 8, L_MCC = 9, L_DIFF2 = 10, L_X2 = 11, L_MAX = 12, L_CCOST = 13, L_NSCAL = 32 };
 
 // ---- small pack/unpack kernels between the C-ABI's SoA (q[4N], t[3N], s[El] caller order) and the device layout
 __global__ void pack_pose_kernel(int first, int n, const double* __restrict__ q, const double* __restrict__ t, double* __restrict__ pose) {
@@ -53,7 +51,9 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 Solver::Solver(const pgs_options& o) : opt(o) {}
 
 Solver::~Solver() {
+  inner.reset();
   if (sky) skyline_destroy(sky);
+  if (sky_border) skyline_destroy(sky_border);
   if (h_scal) cudaFreeHost(h_scal);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -157,7 +157,7 @@ int Solver::set_regs(int k, const int* node, const double* q, const double* t, c
   return PGS_OK;
 }
 void Solver::sizes(pgs_sizes* s) {
-  if (structure_dirty) finalize();
+  if (structure_dirty && !comm_owned) finalize();   // a multi-GPU handle never builds the full problem on one device
   s->n_nodes = N; s->n_odom = (int)o_c1.size(); s->n_loop = (int)l_a.size(); s->n_reg = (int)r_node.size(); s->n_pairs = n_pairs;
 }
 int64_t Solver::sweep_bytes() const {
@@ -267,6 +267,7 @@ int Solver::finalize() {
   CU(d_Ad.resize((size_t)std::max(N, 1) * 36, true)); CU(d_Ao.resize((size_t)std::max(n_pairs, 1) * 36, true)); CU(d_b.resize((size_t)std::max(N, 1) * 6, true));
   CU(d_y.resize((size_t)std::max(N, 1) * 6, true)); CU(d_dp.resize((size_t)std::max(N, 1) * 6, true)); CU(d_ds.resize(std::max(El, 1), true));
   if (sky) { skyline_destroy(sky); sky = nullptr; }
+  if (sky_border) { skyline_destroy(sky_border); sky_border = nullptr; }
   CU(cudaStreamSynchronize(stream));
   structure_dirty = false; host_params_newer = true; device_params_newer = false;
   return PGS_OK;
@@ -350,7 +351,7 @@ int Solver::run_assemble() {
 int Solver::compute_scaling(bool compute_scale) {
   const int El = (int)l_a.size();
   const int n = std::max(6 * N, El);
-  if (n) scaling_kernel<<<cdiv(n, 256), 256, 0, stream>>>(N, El, d_Hd.p, d_lh.p, compute_scale ? 1 : 0, opt.jacobi_scaling, opt.min_lm_diagonal,
+  if (n) scaling_kernel<<<cdiv(n, 256), 256, 0, stream>>>(N, first_border >= 0 ? first_border : N, El, d_Hd.p, d_lh.p, compute_scale ? 1 : 0, opt.jacobi_scaling, opt.min_lm_diagonal,
                                                          opt.max_lm_diagonal, d_scale_p.p, d_scale_s.p, d_diag_p.p, d_diag_s.p);
   CU(cudaGetLastError());
   return PGS_OK;
@@ -359,6 +360,7 @@ int Solver::compute_scaling(bool compute_scale) {
 int Solver::build_system(double radius) {
   SysArgs A;
   A.N = N; A.n_loop = (int)l_a.size(); A.n_pairs = n_pairs; A.inv_radius = 1.0 / radius;
+  A.first_border = first_border >= 0 ? first_border : N;
   A.l_idx = d_lidx.p; A.Hd = d_Hd.p; A.g = d_g.p; A.Ho = d_Ho.p; A.lv = d_lv.p; A.lh = d_lh.p; A.lg = d_lg.p;
   A.scale_p = d_scale_p.p; A.scale_s = d_scale_s.p; A.diag_p = d_diag_p.p; A.diag_s = d_diag_s.p;
   A.inc_ptr = d_inc_ptr.p; A.inc_item = d_inc_item.p; A.pe_ptr = d_pe_ptr.p; A.pe_item = d_pe_item.p; A.pair = d_pair.p;
@@ -403,13 +405,18 @@ int Solver::solve_pcg(int* iters) {
 }
 
 int Solver::solve_skyline() {
+  const int nb_nodes = first_border >= 0 ? N - first_border : 0;
   if (!sky) {
-    sky = skyline_create(N, n_pairs, h_pair_hi.data(), h_pair_lo.data(), stream, &err);
+    sky = skyline_create(N, n_pairs, h_pair_hi.data(), h_pair_lo.data(), stream, &err, nb_nodes);
     if (!sky) return PGS_ERR_OUT_OF_MEMORY;
     factor_nnz = skyline_nnz(sky);
   }
-  const int rc = skyline_factor_solve(sky, d_Ad.p, d_Ao.p, d_b.p, d_y.p, &err);
-  return rc;
+  if (!comm || nb_nodes == 0) return skyline_factor_solve(sky, d_Ad.p, d_Ao.p, d_b.p, d_y.p, &err);
+  // multi-GPU: eliminate the interior, exchange + solve the border system, back-substitute the interior.
+  // Pivot failures are not checked here: the flag travels with the scalar all-reduce so every rank takes the same branch.
+  if (int rc = skyline_factor(sky, d_Ad.p, d_Ao.p, d_b.p, &err)) return rc;
+  if (int rc = border_solve()) return rc;
+  return skyline_backward(sky, d_y.p, &err);
 }
 
 int Solver::solve_linear(int* iters) {
@@ -570,7 +577,11 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
 // Follows Ceres 1.12-1.14 TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy.
 int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
   CU(cudaSetDevice(dev));
+  if (comm_owned) return solve_dist(sum, iters, cap);   // outer solver of a multi-GPU run
+  if (comm && opt.linear_solver != PGS_SKYLINE_CHOLESKY) return fail(PGS_ERR_INVALID_ARGUMENT, "multi-GPU solve needs the skyline Cholesky solver");
   if (int rc = sync_params_to_device()) return rc;
+  const int count_until = (comm && !count_border && first_border >= 0) ? first_border : N;
+  border_scale_ready = false;
   ms_sweep = ms_asm = ms_lin = 0.0;
   cudaEvent_t t_begin, t_end; CU(cudaEventCreate(&t_begin)); CU(cudaEventCreate(&t_end));
   CU(cudaEventRecord(t_begin, stream));
@@ -594,11 +605,16 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     tic();
     if (int r = run_assemble()) return r;
     if (iteration == 0) if (int r = compute_scaling(true)) return r;
+    if (comm) if (int r = border_gradient_exchange()) return r;   // summed border gradient -> d_gfull, summed cost -> L_COST
     // |Plus(x, -g) - x| in the ambient space (Ceres' projected-gradient norms)
-    retract_kernel<<<rgrid, 256, 0, stream>>>(N, El, d_node_used.p, d_pose.p, d_sw.p, d_g.p, d_lg.p, -1.0, d_cpose.p, d_csw.p, P0, P1, P2);
+    retract_kernel<<<rgrid, 256, 0, stream>>>(N, count_until, El, d_node_used.p, d_pose.p, d_sw.p, comm ? d_gfull.p : d_g.p, d_lg.p, -1.0, d_cpose.p, d_csw.p, P0, P1, P2);
     reduce_sum_kernel<<<1, 256, 0, stream>>>(P0, rgrid, 1.0, d_scal.p + L_DIFF2);
     reduce_max_kernel<<<1, 256, 0, stream>>>(P2, rgrid, d_scal.p + L_MAX);
     if (cudaGetLastError() != cudaSuccess) return cuda_fail(cudaPeekAtLastError(), "eval_grad_jac");
+    if (comm) {
+      if (int r = comm->allreduce_sum(d_scal.p + L_DIFF2, 1, stream, &err)) return r;
+      if (int r = comm->allreduce_max(d_scal.p + L_MAX, 1, stream, &err)) return r;
+    }
     ms_asm += toc();
     if (int r = read_scalars(L_NSCAL)) return r;
     x_cost = h_scal[L_COST]; grad_norm = std::sqrt(h_scal[L_DIFF2]); grad_max = h_scal[L_MAX];
@@ -627,6 +643,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     ms_asm += toc();
     tic();
     int lin_it = 0;
+    cur_radius = radius; cur_reuse_diag = reuse_diagonal;
     const int lrc = solve_linear(&lin_it);
     ms_lin += toc();
     if (lrc != PGS_OK && lrc != PGS_ERR_LINEAR_SOLVER) return lrc;
@@ -643,15 +660,20 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
       model_cost_kernel<<<mg, 256, 0, stream>>>(M);
       reduce_sum_kernel<<<1, 256, 0, stream>>>(P0, mg, -1.0, d_scal.p + L_MCC);
       // candidate point + its cost, queued speculatively so one read-back serves all the tests
-      retract_kernel<<<rgrid, 256, 0, stream>>>(N, El, d_node_used.p, d_pose.p, d_sw.p, d_dp.p, d_ds.p, 1.0, d_cpose.p, d_csw.p, P0, P1, P2);
+      retract_kernel<<<rgrid, 256, 0, stream>>>(N, count_until, El, d_node_used.p, d_pose.p, d_sw.p, d_dp.p, d_ds.p, 1.0, d_cpose.p, d_csw.p, P0, P1, P2);
       reduce_sum_kernel<<<1, 256, 0, stream>>>(P0, rgrid, 1.0, d_scal.p + L_DIFF2);
       reduce_sum_kernel<<<1, 256, 0, stream>>>(P1, rgrid, 1.0, d_scal.p + L_X2);
       tic();
       if ((rc = launch_sweep(1, d_cpose.p, d_csw.p, d_scal.p + L_CCOST))) return rc;
       ms_sweep += toc();
+      if (comm) {   // model change, candidate cost, step norms and the pivot flags, summed over the ranks
+        if ((rc = dist_fail_flag())) return rc;
+        if ((rc = comm->allreduce_sum(d_scal.p + L_MCC, L_FAIL - L_MCC + 1, stream, &err))) return rc;
+      }
       if ((rc = read_scalars(L_NSCAL))) return rc;
       mcc = h_scal[L_MCC]; cand_cost = h_scal[L_CCOST]; diff2 = h_scal[L_DIFF2]; x2 = h_scal[L_X2];
       step_ok = std::isfinite(mcc) && std::isfinite(diff2) && mcc > 0.0;
+      if (comm && h_scal[L_FAIL] != 0.0) step_ok = false;   // some rank hit a non-positive pivot
     }
     it.step_is_valid = step_ok ? 1 : 0;
     if (!step_ok) {

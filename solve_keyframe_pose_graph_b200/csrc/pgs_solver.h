@@ -10,7 +10,9 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <memory>
 #include "../../include/pgs.h"
+#include "pgs_comm.h"
 
 namespace pgs {
 
@@ -36,6 +38,11 @@ struct DBuf {
 };
 
 struct SkylineFactor;  // pgs_skyline.cu
+
+static constexpr int MAX_GRID = 2048;
+// slots of the small device/pinned scalar array.  L_MCC..L_FAIL are contiguous: the multi-GPU loop sums them
+// over the ranks with one small all-reduce
+enum { L_COST = 8, L_MCC = 9, L_DIFF2 = 10, L_X2 = 11, L_CCOST = 12, L_FAIL = 13, L_MAX = 14, L_NSCAL = 32 };
 
 class Solver {
  public:
@@ -64,6 +71,16 @@ class Solver {
   int64_t sweep_bytes() const;
   void sizes(pgs_sizes* s);
 
+  // ---- multi-GPU
+  // On the handle the caller sees: dist_init() attaches a communicator; solve() then partitions the graph by node
+  // range, loads this rank's interior + the border into an inner Solver and runs the sharded LM in it.
+  int dist_init(int rank, int world, const void* nccl_id128);
+  int dist_stats(pgs_dist_stats* out);
+  // On the inner (per-rank) solver: set by the outer one before the first solve.
+  Comm* comm = nullptr;          // not owned; non-null switches solve() to the collective variant
+  int first_border = -1;         // local index of the first border node (they come last); -1 = no border
+  bool count_border = true;      // exactly one rank counts the (replicated) border nodes in norms
+
   std::string err;
   pgs_options opt;
 
@@ -80,6 +97,11 @@ class Solver {
   int solve_linear(int* iters);          // Ad/Ao/b -> y  (PCG or skyline Cholesky)
   int solve_pcg(int* iters);
   int solve_skyline();
+  int solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap);   // outer: partition, inner solve, gather
+  int border_gradient_exchange();        // inner: all-reduce of the border gradient + cost, norms of Plus(x,-g)-x
+  int border_solve();                    // inner: Schur complement exchange + redundant border solve
+  int dist_fail_flag();                  // inner: pivot flags of both factors -> d_scal[L_FAIL]
+  int nb6() const { return first_border >= 0 ? 6 * (N - first_border) : 0; }
   int read_scalars(int n);               // d_scal -> h_scal (pinned), synchronises the stream
 
   int N = 0;
@@ -117,7 +139,15 @@ class Solver {
   double* h_pin_q = nullptr; double* h_pin_t = nullptr; double* h_pin_s = nullptr; size_t pin_n = 0, pin_s = 0;
   int sweep_grid = 0;
   SkylineFactor* sky = nullptr;
+  SkylineFactor* sky_border = nullptr;
   int64_t factor_nnz = 0;
+  // multi-GPU state
+  std::unique_ptr<Comm> comm_owned;      // outer
+  std::unique_ptr<Solver> inner;         // outer: this rank's local problem
+  std::vector<int> loc2glob, loop2glob;  // outer: local node -> global node (-1 = padding), local loop -> global loop
+  pgs_dist_stats dstats{};
+  DBuf<double> d_xbuf, d_gfull, d_sb, d_diagb, d_zb;   // inner: border exchange buffer, summed gradient, border scale / LM diagonal / solution
+  double cur_radius = 0.0; bool cur_reuse_diag = false, border_scale_ready = false;
 
   // phase timers (ms, accumulated per solve)
   double ms_sweep = 0, ms_asm = 0, ms_lin = 0;
