@@ -168,10 +168,15 @@ int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t*
 /* Runs the residual+Jacobian sweep `reps` times with every input already resident in HBM and
  * returns the mean device time in milliseconds, measured per repetition with CUDA events on the
  * solver's stream: ms_per_sweep = sweep kernel + cost reduction, ms_sweep_kernel = the sweep kernel alone.
- * flush_l2 != 0 writes a >L2-sized scratch buffer between repetitions (outside the timed spans).
+ * flush_l2 != 0 writes a 384 MiB scratch buffer (> the 126 MB L2) and then re-reads 256 MiB of it between
+ * repetitions, outside the timed spans: the write evicts the solver's data, the read pass drains the dirty
+ * lines the write left behind so their write-back is not billed to the sweep.
  * mode: 0 = residuals + Jacobians (mode J), 1 = cost only. */
 int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush_l2, double* ms_per_sweep,
                    double* ms_sweep_kernel, int64_t* kernel_launches);
+/* Practical ceiling for a store-dominated kernel of this size: a pure streaming write of `bytes` bytes,
+ * timed exactly like pgs_time_sweep (per repetition, CUDA events, same L2 flush).  Diagnostic only. */
+int pgs_time_stream_write(pgs_handle h, int64_t bytes, int32_t reps, int32_t flush_l2, double* ms_per_write);
 /* End-to-end step: host poses/switches (pinned or pageable) -> device, one mode-J sweep, cost back
  * to the host.  q,t,s may be NULL to reuse the current values of that array. */
 int pgs_evaluate_from_host(pgs_handle h, const double* q_xyzw, const double* t, const double* s, double* cost);

@@ -271,6 +271,12 @@ class PoseGraphSolver:
         self._ck(self.L.pgs_time_sweep(self.h, C.c_int32(mode), C.c_int32(reps), C.c_int32(int(flush_l2)), C.byref(ms), C.byref(msk), C.byref(n)))
         return ms.value, msk.value, n.value
 
+    def time_stream_write(self, nbytes, reps=10, flush_l2=True):
+        """ms of a pure streaming write of `nbytes`, timed like time_sweep (practical ceiling of a store-bound kernel)."""
+        ms = C.c_double(0)
+        self._ck(self.L.pgs_time_stream_write(self.h, C.c_int64(int(nbytes)), C.c_int32(reps), C.c_int32(int(flush_l2)), C.byref(ms)))
+        return ms.value
+
     def evaluate_from_host_ptr(self, q_ptr, t_ptr, s_ptr):
         """Raw-pointer variant (pinned torch tensors): addresses as ints, 0 for 'reuse'."""
         cost = C.c_double(0)

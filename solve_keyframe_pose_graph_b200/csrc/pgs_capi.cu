@@ -59,6 +59,7 @@ int pgs_assemble(pgs_handle h, double* diag, int32_t* phi, int32_t* plo, double*
   H(h); return h->s->assemble(diag, phi, plo, off, lv, lh); }
 int pgs_linear_step(pgs_handle h, double radius, double* dp, double* ds, double* mcc, int32_t* it) { H(h); return h->s->linear_step(radius, dp, ds, mcc, it); }
 int pgs_solve(pgs_handle h, pgs_summary* sum, pgs_iteration* iters, int32_t cap) { H(h); return h->s->solve(sum, iters, cap); }
+int pgs_time_stream_write(pgs_handle h, int64_t bytes, int32_t reps, int32_t flush, double* ms) { H(h); return h->s->time_stream_write(bytes, reps, flush, ms); }
 int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush, double* ms, double* ms_kernel, int64_t* launches) { H(h); return h->s->time_sweep(mode, reps, flush, ms, ms_kernel, launches); }
 int pgs_evaluate_from_host(pgs_handle h, const double* q, const double* t, const double* s, double* cost) { H(h); return h->s->evaluate_from_host(q, t, s, cost); }
 int64_t pgs_sweep_algorithmic_bytes(pgs_handle h) { if (!h || !h->s) return 0; return h->s->sweep_bytes(); }

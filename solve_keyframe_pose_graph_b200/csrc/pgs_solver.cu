@@ -45,6 +45,15 @@ __global__ void scatter_kernel(int n, const int* __restrict__ perm, const double
 __global__ void flush_kernel(double* p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
+// reads n doubles; the store never happens (v is never NaN) but keeps the loads alive
+__global__ void drain_kernel(double* p, size_t n) {
+  double s = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += p[i];
+  if (s != s) p[0] = s;
+}
+__global__ void __launch_bounds__(256) stream_write_kernel(double2* p, size_t n2) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) __stcs(p + i, make_double2(1.0, 2.0));
+}
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
@@ -259,6 +268,8 @@ int Solver::finalize() {
   CU(d_or.resize((size_t)std::max(To, 1) * OD_R * TILE, true)); CU(d_oJ.resize((size_t)std::max(To, 1) * OD_J * TILE, true));
   CU(d_lr.resize((size_t)std::max(Tl, 1) * LP_R * TILE, true)); CU(d_lJ.resize((size_t)std::max(Tl, 1) * LP_J * TILE, true));
   CU(d_gr.resize((size_t)std::max(K, 1) * 6, true)); CU(d_gJ.resize((size_t)std::max(K, 1) * 36, true));
+  CU(d_cost_tile.resize((size_t)To + Tl + cdiv(K, TILE) + 1, true));
+  CU(d_counter.resize(4, true));   // tile scheduler of the sweep: must be zero between launches
   CU(d_Hd.resize((size_t)std::max(N, 1) * 36, true)); CU(d_g.resize((size_t)std::max(N, 1) * 6, true)); CU(d_Ho.resize((size_t)std::max(n_pairs, 1) * 36, true));
   CU(d_lv.resize((size_t)std::max(El, 1) * 12, true)); CU(d_lh.resize(std::max(El, 1), true)); CU(d_lg.resize(std::max(El, 1), true));
   CU(d_lvt.resize((size_t)std::max(El, 1) * 12, true)); CU(d_lw.resize(std::max(El, 1), true)); CU(d_lgt.resize(std::max(El, 1), true));
@@ -325,12 +336,12 @@ int Solver::launch_sweep(int mode, const double* pose, const double* sw, double*
   A.l_idx = d_lidx.p; A.l_obs = d_lobs.p; A.n_loop = (int)l_a.size();
   A.r_node = d_rnode.p; A.r_anchor = d_ranchor.p; A.n_reg = (int)r_node.size();
   A.o_r = d_or.p; A.o_J = d_oJ.p; A.l_r = d_lr.p; A.l_J = d_lJ.p; A.g_r = d_gr.p; A.g_J = d_gJ.p;
-  A.cost_partial = d_partial.p;
+  A.cost_tile = d_cost_tile.p; A.sched = d_counter.p + 2;   // slots 0-1 belong to the PCG kernels
   const int tiles = cdiv(A.n_odom, TILE) + cdiv(A.n_loop, TILE) + cdiv(A.n_reg, TILE);
   const int grid = std::max(1, std::min(sweep_grid, cdiv(tiles, 8)));
   if (mode == 0) sweep_kernel<0><<<grid, 256, 0, stream>>>(A); else sweep_kernel<1><<<grid, 256, 0, stream>>>(A);
   if (after_kernel) cudaEventRecord(after_kernel, stream);
-  reduce_sum_kernel<<<1, 256, 0, stream>>>(d_partial.p, grid, 0.5, cost_out_dev);
+  reduce_sum_kernel<<<1, 1024, 0, stream>>>(d_cost_tile.p, tiles, 0.5, cost_out_dev);
   CU(cudaGetLastError());
   return PGS_OK;
 }
@@ -524,18 +535,26 @@ int Solver::linear_step(double radius, double* delta_pose, double* delta_switch,
   return PGS_OK;
 }
 
+static constexpr size_t FLUSH_DOUBLES = (size_t)48 << 20;   // 384 MiB > 126 MB L2
+
+int Solver::flush_l2_now() {
+  CU(d_flush.resize(FLUSH_DOUBLES));
+  flush_kernel<<<1184, 256, 0, stream>>>(d_flush.p, FLUSH_DOUBLES, 1.0);
+  drain_kernel<<<1184, 256, 0, stream>>>(d_flush.p, (size_t)32 << 20);   // 256 MiB re-read: the dirty tail of the write is evicted
+  CU(cudaGetLastError());
+  return PGS_OK;
+}
+
 int Solver::time_sweep(int mode, int reps, int flush_l2, double* ms, double* ms_kernel, int64_t* launches) {
   CU(cudaSetDevice(dev));
   if (int rc = sync_params_to_device()) return rc;
   if (reps < 1) reps = 1;
-  size_t flush_n = 0;
-  if (flush_l2) { flush_n = (size_t)48 << 20; CU(d_flush.resize(flush_n)); }   // 384 MiB of doubles > 126 MB L2
   cudaEvent_t evk; CU(cudaEventCreate(&evk));
   double total = 0.0, total_k = 0.0;
   // every repetition is timed on its own: [ev0] sweep kernel [evk] cost reduction [ev1]; the optional L2
   // flush runs between repetitions, outside the timed span
   for (int i = 0; i < reps; ++i) {
-    if (flush_l2) flush_kernel<<<1184, 256, 0, stream>>>(d_flush.p, flush_n, (double)i);
+    if (flush_l2) if (int rc = flush_l2_now()) return rc;
     CU(cudaEventRecord(ev0, stream));
     if (int rc = launch_sweep(mode, d_pose.p, d_sw.p, d_scal.p + L_COST, evk)) return rc;
     CU(cudaEventRecord(ev1, stream));
@@ -547,6 +566,26 @@ int Solver::time_sweep(int mode, int reps, int flush_l2, double* ms, double* ms_
   if (ms) *ms = total / reps;
   if (ms_kernel) *ms_kernel = total_k / reps;
   if (launches) *launches = 2LL * reps;   // sweep + cost reduction per repetition
+  return PGS_OK;
+}
+
+int Solver::time_stream_write(int64_t bytes, int reps, int flush_l2, double* ms) {
+  CU(cudaSetDevice(dev));
+  if (bytes <= 0 || (size_t)bytes > FLUSH_DOUBLES * sizeof(double)) return fail(PGS_ERR_INVALID_ARGUMENT, "time_stream_write: bytes must be in (0, 384 MiB]");
+  if (reps < 1) reps = 1;
+  CU(d_flush.resize(FLUSH_DOUBLES));
+  double total = 0.0;
+  for (int i = 0; i < reps; ++i) {
+    if (flush_l2) if (int rc = flush_l2_now()) return rc;
+    CU(cudaEventRecord(ev0, stream));
+    stream_write_kernel<<<sweep_grid, 256, 0, stream>>>(reinterpret_cast<double2*>(d_flush.p), (size_t)bytes / 16);
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaEventSynchronize(ev1));
+    float t = 0; CU(cudaEventElapsedTime(&t, ev0, ev1));
+    total += t;
+  }
+  CU(cudaGetLastError());
+  if (ms) *ms = total / reps;
   return PGS_OK;
 }
 

@@ -67,6 +67,7 @@ class Solver {
   int linear_step(double radius, double* delta_pose, double* delta_switch, double* mcc, int* lin_iters);
   int solve(pgs_summary* sum, pgs_iteration* iters, int cap);
   int time_sweep(int mode, int reps, int flush_l2, double* ms, double* ms_kernel, int64_t* launches);
+  int time_stream_write(int64_t bytes, int reps, int flush_l2, double* ms);
   int evaluate_from_host(const double* q, const double* t, const double* s, double* cost);
   int64_t sweep_bytes() const;
   void sizes(pgs_sizes* s);
@@ -102,6 +103,7 @@ class Solver {
   int border_solve();                    // inner: Schur complement exchange + redundant border solve
   int dist_fail_flag();                  // inner: pivot flags of both factors -> d_scal[L_FAIL]
   int nb6() const { return first_border >= 0 ? 6 * (N - first_border) : 0; }
+  int flush_l2_now();                    // evict everything from L2 and leave no dirty lines behind
   int read_scalars(int n);               // d_scal -> h_scal (pinned), synchronises the stream
 
   int N = 0;
@@ -133,7 +135,7 @@ class Solver {
   DBuf<double> d_scale_p, d_scale_s, d_diag_p, d_diag_s;
   DBuf<double> d_Ad, d_Ao, d_b, d_y, d_dp, d_ds;
   DBuf<double> d_Minv, d_px, d_pr, d_prn, d_pz, d_pp, d_pAp;
-  DBuf<double> d_partial, d_scal, d_flush;
+  DBuf<double> d_partial, d_scal, d_flush, d_cost_tile;
   DBuf<unsigned int> d_counter;
   double* h_scal = nullptr;              // pinned
   double* h_pin_q = nullptr; double* h_pin_t = nullptr; double* h_pin_s = nullptr; size_t pin_n = 0, pin_s = 0;
