@@ -167,7 +167,7 @@ int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t*
 /* ---- measurement hooks used by bench.py ---- */
 /* Runs the residual+Jacobian sweep `reps` times with every input already resident in HBM and
  * returns the mean device time in milliseconds, measured per repetition with CUDA events on the
- * solver's stream: ms_per_sweep = sweep kernel + cost reduction, ms_sweep_kernel = the sweep kernel alone.
+ * solver's stream (ms_per_sweep and ms_sweep_kernel coincide since the cost reduction moved into the sweep kernel).
  * flush_l2 != 0 writes a 384 MiB scratch buffer (> the 126 MB L2) and then re-reads 256 MiB of it between
  * repetitions, outside the timed spans: the write evicts the solver's data, the read pass drains the dirty
  * lines the write left behind so their write-back is not billed to the sweep.

@@ -38,7 +38,8 @@ struct SweepArgs {
   double* __restrict__ l_r; double* __restrict__ l_J;
   double* __restrict__ g_r; double* __restrict__ g_J;      // regulariser [K][6], [K][36] (AoS, a handful)
   double* __restrict__ cost_tile;                          // [tiles] sum of squared residuals per tile of 32 edges
-  unsigned int* __restrict__ sched;                        // [2] {next tile, warps done}; zero between launches
+  unsigned int* __restrict__ sched;                        // [2] {next tile, blocks done}; zero between launches
+  double* __restrict__ cost_out;                           // 0.5 * sum of cost_tile, written by the last block to finish
 };
 
 // ------------------------------------------------------------------ small math
@@ -271,11 +272,34 @@ __global__ void __launch_bounds__(256) sweep_kernel(SweepArgs A) {
     cost = warp_sum(cost);
     if (lane == 0) A.cost_tile[tile] = cost;
   }
-  // the last warp to leave re-arms the scheduler for the next launch
-  if (lane == 0) {
+  // The last block to leave sums the per-tile partials in a fixed order (thread i takes tiles i, i+256, ...; then
+  // the usual shuffle tree) and re-arms the scheduler: no second launch for the cost, and the same bits every run.
+  __shared__ double red[8];
+  __shared__ int is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int nw = gridDim.x * (blockDim.x >> 5);
-    if (atomicAdd(A.sched + 1, 1u) == nw - 1) { A.sched[0] = 0u; A.sched[1] = 0u; }
+    is_last = atomicAdd(A.sched + 1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i0 = threadIdx.x; i0 < T; i0 += 8 * blockDim.x) {   // eight loads in flight, added in index order
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < T ? __ldcg(A.cost_tile + i) : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    *A.cost_out = 0.5 * t;
+    A.sched[0] = 0u; A.sched[1] = 0u;
   }
 }
 

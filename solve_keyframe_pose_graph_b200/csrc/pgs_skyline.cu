@@ -10,14 +10,18 @@
 // every (row, panel) intersection is a full PW-wide, 16-byte aligned segment.  One extra row n carries b^T:
 // factoring it along with the matrix performs the forward substitution for free (row n of L is (L^-1 b)^T).
 //
-// Right-looking by panels of PW columns with one panel of look-ahead on a second stream:
-//   diag    1 CTA    L_dd = chol(A_dd) in shared memory (8-column blocks, 4x4 register tiles), Linv = L_dd^-1 by
-//                    block forward substitution (kept for trsm and the backward solve)
-//   trsm    |R|/32   X = A[R, panel] * Linv^T for the rows R below the panel whose envelope reaches it
-//   update  tiles    A[r, c] -= X[r,:] . X[c,:] for r, c in R, c <= r: 128x64 tiles, 8x4 register micro-tiles,
-//                    K = 96 in three cp.async double-buffered chunks.  "next" = the first two column tiles
-//                    (they hold every column of panel d+1) runs on the panel stream ahead of diag(d+1);
-//                    "rest" runs on the main stream concurrently with diag/trsm of the next panel.
+// Right-looking by panels of PW columns; the panel chain runs one panel ahead of the bulk update on a second,
+// high-priority stream:
+//   chain stream   C(d):     1 CTA.  Applies the one update the bulk has not yet given the diagonal block — the
+//                            rank-96 product of X[d, d-1] from trsm(d-1) — then L_dd = chol(A_dd) and Linv = L_dd^-1,
+//                            every matrix-shaped piece on FP64 tensor cores (DMMA).  Waits for trsm(d-1).
+//   main stream    trsm(d):  X = A[R, panel] * Linv^T for the rows R below the panel whose envelope reaches it.
+//                            Waits for C(d).
+//                  update(d): A[r, c] -= X[r,:] . X[c,:] for r, c in R, c <= r, except the diagonal block of panel
+//                            d+1 (C(d+1) does that one itself, which is what lets it start right after trsm(d)
+//                            instead of after the whole update).  128x64 DMMA tiles, persistent CTAs fed by an
+//                            atomic tile counter, accumulators preloaded with A so the epilogue is a plain store.
+// so C(d+1) overlaps update(d) and the factorisation runs at max(C + trsm, trsm + update) per panel.
 // then a backward sweep (one launch per panel) solves L^T x = y.
 //
 // Partial factorisation (multi-GPU domain decomposition): only the first n_elim panels are
@@ -38,17 +42,18 @@ constexpr int PW = 96;            // panel width in scalars = 16 nodes
 constexpr int PN = PW / 6;
 constexpr int TR = 32;            // trsm rows per CTA
 constexpr int LDP = PW + 2;       // padded leading dimension of PW-wide shared tiles: even (16-B rows), LDP/2 odd
-constexpr int UM_BULK = 128, UM_NEXT = 32, UN = 64;  // update tiles: rows x cols
+constexpr int LDT = PW + 4;       // 100 doubles = 200 words = 8 mod 32: conflict-free DMMA fragment loads (8 rows x 4 k per half-warp pair)
+constexpr int UM = 128, UN = 64;  // update tiles: rows x cols
 constexpr int KC = 32;            // update K chunk
-constexpr int LDK = KC + 2;       // 34: even, LDK/2 odd -> conflict-free 128-bit row reads
-constexpr int NEXT_TILES = 2;     // column tiles of the look-ahead part of the update (2 * UN >= PW)
+constexpr int LDK = KC + 4;       // 36 doubles = 72 words = 8 mod 32: conflict-free DMMA fragment loads, 16-B aligned rows
 constexpr int NEV = 8;            // event ring
 
 struct SkylineFactor {
   int N = 0, n = 0, D = 0;         // nodes, scalars, panels
   int D_elim = 0;                  // panels to eliminate (== D for a full factorisation)
-  cudaStream_t stream = nullptr, s1 = nullptr;
-  cudaEvent_t ev_trsm[NEV], ev_rest[NEV], ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream = nullptr, s1 = nullptr, s2 = nullptr;   // main (rest), chain (C), panel (trsm + next)
+  cudaEvent_t ev_trsm[NEV], ev_rest[NEV], ev_c[NEV], ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  unsigned int* sched = nullptr;   // [2] CTAs-done counter of the backward sweep (self-resetting)
   std::vector<int> h_start;        // per scalar row (n+1 entries, last = rhs row)
   std::vector<long long> h_ptr;    // n+2
   std::vector<int> h_rows_ptr;     // D+1
@@ -68,12 +73,14 @@ struct SkylineFactor {
 void skyline_destroy(SkylineFactor* f) {
   if (!f) return;
   cudaFree(f->val); cudaFree(f->ptr); cudaFree(f->start); cudaFree(f->rows_ptr); cudaFree(f->rows_idx); cudaFree(f->dinv);
-  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo);
+  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched);
   if (f->h_fail) cudaFreeHost(f->h_fail);
-  for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); }
+  for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); if (f->ev_c[i]) cudaEventDestroy(f->ev_c[i]); }
   if (f->ev_fork) cudaEventDestroy(f->ev_fork);
   if (f->ev_join) cudaEventDestroy(f->ev_join);
+  if (f->ev_join2) cudaEventDestroy(f->ev_join2);
   if (f->s1) cudaStreamDestroy(f->s1);
+  if (f->s2) cudaStreamDestroy(f->s2);
   delete f;
 }
 int64_t skyline_nnz(const SkylineFactor* f) { return f ? f->nnz : 0; }
@@ -82,7 +89,7 @@ int skyline_panel_width() { return PW; }
 SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
                               int n_border_nodes, bool dense) {
   SkylineFactor* f = new SkylineFactor();
-  for (int i = 0; i < NEV; ++i) { f->ev_trsm[i] = nullptr; f->ev_rest[i] = nullptr; }
+  for (int i = 0; i < NEV; ++i) { f->ev_trsm[i] = nullptr; f->ev_rest[i] = nullptr; f->ev_c[i] = nullptr; }
   f->N = N; f->n = 6 * N; f->D = (f->n + PW - 1) / PW; f->stream = stream; f->n_pairs = n_pairs;
   const int n = f->n, D = f->D;
   const int N_int = dense ? 0 : N - n_border_nodes;           // interior nodes come first, border nodes last
@@ -126,15 +133,20 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
   if ((e = cudaMalloc((void**)&f->dinv, sizeof(double) * (size_t)std::max(D, 1) * PW * PW)) != cudaSuccess) return bad(e, "dinv");
   if ((e = cudaMalloc((void**)&f->xacc, sizeof(double) * (size_t)std::max(D, 1) * PW)) != cudaSuccess) return bad(e, "xacc");
   if ((e = cudaMalloc((void**)&f->fail, sizeof(int))) != cudaSuccess) return bad(e, "fail");
+  if ((e = cudaMalloc((void**)&f->sched, 4 * sizeof(unsigned int))) != cudaSuccess) return bad(e, "sched");
+  if ((e = cudaMemsetAsync(f->sched, 0, 4 * sizeof(unsigned int), stream)) != cudaSuccess) return bad(e, "sched");
   if ((e = cudaMallocHost((void**)&f->h_fail, sizeof(int))) != cudaSuccess) return bad(e, "h_fail");
   if ((e = cudaMalloc((void**)&f->pair_hi, sizeof(int) * std::max(n_pairs, 1))) != cudaSuccess) return bad(e, "pair_hi");
   if ((e = cudaMalloc((void**)&f->pair_lo, sizeof(int) * std::max(n_pairs, 1))) != cudaSuccess) return bad(e, "pair_lo");
   { int lo_p = 0, hi_p = 0; cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);   // the panel stream carries the critical path
-    if ((e = cudaStreamCreateWithPriority(&f->s1, cudaStreamNonBlocking, hi_p)) != cudaSuccess) return bad(e, "stream"); }
+    if ((e = cudaStreamCreateWithPriority(&f->s1, cudaStreamNonBlocking, hi_p)) != cudaSuccess) return bad(e, "stream");
+    if ((e = cudaStreamCreateWithPriority(&f->s2, cudaStreamNonBlocking, hi_p)) != cudaSuccess) return bad(e, "stream"); }
   for (int i = 0; i < NEV; ++i) {
     if ((e = cudaEventCreateWithFlags(&f->ev_trsm[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
     if ((e = cudaEventCreateWithFlags(&f->ev_rest[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
+    if ((e = cudaEventCreateWithFlags(&f->ev_c[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
   }
+  if ((e = cudaEventCreateWithFlags(&f->ev_join2, cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
   if ((e = cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
   if ((e = cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
   cudaMemcpyAsync(f->ptr, f->h_ptr.data(), sizeof(long long) * (n + 2), cudaMemcpyHostToDevice, stream);
@@ -175,193 +187,264 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NGROUPS>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NGROUPS)); }
 
-// diag: factor the PW x PW diagonal block of panel d in shared memory, store L back, store Linv.
-__global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, const long long* __restrict__ ptr, const int* __restrict__ start,
+// FP64 tensor-core step: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
+// D[l>>2][2*(l&3) + {0,1}].  On B200 DMMA sustains 37 TFLOP/s against 31-34 for DFMA (tools/fp64_lab.cu) and
+// needs one shared-memory load per 2 (128x64 tile) / 1 (32x64 tile) mma instead of 12 per 32 FMAs.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// diag: factor the PW x PW diagonal block of panel d in shared memory, store L back, store X = L^-1.
+// One CTA on the critical path of the whole factorisation, so every matrix-shaped piece runs on DMMA and the
+// inverse is built alongside the factor.  Twelve 8-column steps of two barrier phases each:
+//   phase A  row threads (tid < rows left): re-factor the 8x8 diagonal block in registers (redundantly, no
+//            synchronisation inside) and solve their own row of the block column;
+//            thread 255: the same factor, then W = its inverse -> Dinv[I] and the diagonal block of X;
+//            free warps: finish X row-block I-1 = -W_{I-1} * S (S from the previous phase B).
+//   phase B  8x8 DMMA blocks of the trailing update  A[i,k] -= L[i,I] L[k,I]^T  and of
+//            S = L[I, 0:jb] * X[0:jb, 0:jb] for row-block I, dealt round-robin to the 8 warps.
+// Fragment layout of dmma884: g = lane >> 2, t = lane & 3; A[g][t], B[t][g], C[g][2t..2t+1].
+__device__ __forceinline__ void diag_block_of(int b, int& bi, int& bk) {
+  bi = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+  while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+  while (bi * (bi + 1) / 2 > b) --bi;
+  bk = b - bi * (bi + 1) / 2;
+}
+#ifdef SKY_DIAG_CLOCKS   // tools/diag_lab.cu: cycle stamps of thread 0 after every barrier phase
+__device__ long long g_diag_clk[64];
+#define DIAG_STAMP(i) do { if (threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#endif
+__global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, int prev, const long long* __restrict__ ptr, const int* __restrict__ start,
                                                        double* __restrict__ val, double* __restrict__ dinv, int* __restrict__ fail) {
+  constexpr int NB = PW / 8, LDQ = LDT;
+  DIAG_STAMP(0);
   extern __shared__ __align__(16) double sm_diag[];
-  double* L = sm_diag;                 // [PW][LDP]
-  double* X = sm_diag + PW * LDP;      // [PW][LDP]
-  double* Dinv = X + PW * LDP;         // [PW/8][64] inverses of the 8x8 diagonal blocks
+  double* L = sm_diag;                 // [PW][LDQ]
+  double* X = sm_diag + PW * LDQ;      // [PW][LDQ]  only the lower block triangle is ever written or read
+  double* Dinv = X + PW * LDQ;         // [NB][64] inverses of the 8x8 diagonal factors (full 8x8, upper part zero)
+  double* Sb = Dinv + NB * 64;         // [8][LDQ]  S of the current row-block
   __shared__ long long rbase[PW];
   __shared__ int bad;
   const int c0 = d * PW, w = min(PW, n - c0), tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   if (tid == 0) bad = 0;
-  if (tid < PW) { const int r = c0 + tid; rbase[tid] = tid < w ? ptr[r] + (c0 - start[r]) : 0; }
-  __syncthreads();
-  {
-    // all 36 loads of a thread are issued before the first use (one memory latency instead of 36)
-    double v[PW * PW / 256];
-#pragma unroll
-    for (int q = 0; q < PW * PW / 256; ++q) {
-      const int e = tid + 256 * q, i = e / PW, j = e % PW;
-      v[q] = (i == j && i >= w) ? 1.0 : 0.0;       // identity padding of a short last panel
-      if (i < w && j <= i) v[q] = val[rbase[i] + j];
-    }
-#pragma unroll
-    for (int q = 0; q < PW * PW / 256; ++q) {
-      const int e = tid + 256 * q, i = e / PW, j = e % PW;
-      L[i * LDP + j] = v[q]; X[i * LDP + j] = 0.0;
-    }
+  __shared__ int rprev[PW];            // 1 = the row's envelope reaches panel d-1
+  if (tid < PW) {
+    const int r = c0 + tid;
+    const int st = tid < w ? start[r] : 0;
+    rbase[tid] = tid < w ? ptr[r] + (c0 - st) : 0;
+    rprev[tid] = (prev && tid < w && st <= c0 - PW) ? 1 : 0;
   }
   __syncthreads();
-  // ---- blocked right-looking Cholesky, 8 columns at a time
-  for (int jb = 0; jb < PW; jb += 8) {
-    const int i = jb + tid;
-    double Dg[8][8], arow[8], dinv8[8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) Dg[a][c] = (c <= a) ? L[(jb + a) * LDP + jb + c] : 0.0;
-    if (i < PW) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) arow[c] = L[i * LDP + jb + c];
+  for (int e = tid; e < PW * (PW / 2); e += 256) {            // lower triangle by 16-byte pairs, the rest zero-filled
+    const int i = e / (PW / 2), j2 = e % (PW / 2);
+    const bool ok = i < w && 2 * j2 <= i;
+    cp_async16(&L[i * LDQ + 2 * j2], ok ? (const void*)(val + rbase[i] + 2 * j2) : (const void*)val, ok);
+  }
+  if (prev) {
+    // X[d, d-1] (written by trsm(d-1)) staged in the X buffer, which the factorisation does not touch before step 0
+    for (int e = tid; e < PW * (PW / 2); e += 256) {
+      const int i = e / (PW / 2), j2 = e % (PW / 2);
+      const bool ok = rprev[i] != 0;
+      cp_async16(&X[i * LDQ + 2 * j2], ok ? (const void*)(val + rbase[i] - PW + 2 * j2) : (const void*)val, ok);
     }
-    // every thread re-factors the 8x8 diagonal block in registers (no synchronisation inside)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      double dd = Dg[c][c];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (k < c) dd -= Dg[c][k] * Dg[c][k];
-      if (!(dd > 0.0)) { if (tid == 0) bad = 1; dd = 1.0; }
-      const double inv = rsqrt(dd);      // 1 ulp; the sqrt + divide pair would put ~600 cycles per column on the critical path
-      Dg[c][c] = dd * inv; dinv8[c] = inv;
-#pragma unroll
-      for (int a = 0; a < 8; ++a) if (a > c) {
-        double s = Dg[a][c];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < c) s -= Dg[a][k] * Dg[c][k];
-        Dg[a][c] = s * inv;
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (prev) {
+    // A_dd -= X X^T on the lower block triangle: 78 blocks of 8x8, two per warp in flight, K = 96
+    constexpr int NBLK = NB * (NB + 1) / 2;
+    for (int b = 2 * wid; b < NBLK; b += 16) {
+      int bi0, bk0, bi1, bk1;
+      diag_block_of(b, bi0, bk0);
+      const bool two = b + 1 < NBLK;
+      diag_block_of(two ? b + 1 : b, bi1, bk1);
+      double2* cp0 = reinterpret_cast<double2*>(&L[(8 * bi0 + g) * LDQ + 8 * bk0 + 2 * t]);
+      double2* cp1 = reinterpret_cast<double2*>(&L[(8 * bi1 + g) * LDQ + 8 * bk1 + 2 * t]);
+      double2 u = *cp0, v = *cp1;
+      const double* a0 = &X[(8 * bi0 + g) * LDQ + t]; const double* b0 = &X[(8 * bk0 + g) * LDQ + t];
+      const double* a1 = &X[(8 * bi1 + g) * LDQ + t]; const double* b1 = &X[(8 * bk1 + g) * LDQ + t];
+#pragma unroll 6
+      for (int k = 0; k < PW; k += 4) {
+        dmma884(u.x, u.y, -a0[k], b0[k]);
+        dmma884(v.x, v.y, -a1[k], b1[k]);
       }
+      *cp0 = u;
+      if (two) *cp1 = v;
     }
-    __syncthreads();   // everybody has read the diagonal block / its own row before they are overwritten
-    if (i < PW) {
-      double row[8];
-      if (tid < 8) {
+    __syncthreads();
+  }
+  if (tid >= w && tid < PW) L[tid * LDQ + tid] = 1.0;         // identity padding of a short last panel
+  __syncthreads();
+  DIAG_STAMP(1);
+  double Dg[8][8], dinv8[8];
+  for (int I = 0; I < NB; ++I) {
+    const int jb = 8 * I, nrow = PW - jb;
+    const bool row_thread = tid < nrow, inv_thread = tid == 255;
+    // ---------------- phase A
+    if (row_thread || inv_thread) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) row[c] = 0.0;
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int a = 0; a < 8; ++a) if (a == tid) {
+        for (int c = 0; c < 8; ++c) Dg[a][c] = (c <= a) ? L[(jb + a) * LDQ + jb + c] : 0.0;
+      double arow[8];
+      if (row_thread) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) if (c <= a) row[c] = Dg[a][c];
+        for (int c = 0; c < 8; ++c) arow[c] = L[(jb + tid) * LDQ + jb + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double dd = Dg[c][c];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k < c) dd -= Dg[c][k] * Dg[c][k];
+        if (!(dd > 0.0)) { if (tid == 0) bad = 1; dd = 1.0; }
+        const double inv = rsqrt(dd);      // 1 ulp; the sqrt + divide pair would put ~600 cycles per column on the critical path
+        Dg[c][c] = dd * inv; dinv8[c] = inv;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) if (a > c) {
+          double sacc = Dg[a][c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (k < c) sacc -= Dg[a][k] * Dg[c][k];
+          Dg[a][c] = sacc * inv;
         }
-      } else {
+      }
+      if (row_thread && tid >= 8) {        // rows below the diagonal block: x = arow * Dg^-T
+        double row[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          double s = arow[c];
+          double sacc = arow[c];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) if (k < c) s -= row[k] * Dg[c][k];
-          row[c] = s * dinv8[c];
+          for (int k = 0; k < 8; ++k) if (k < c) sacc -= row[k] * Dg[c][k];
+          row[c] = sacc * dinv8[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(&L[(jb + tid) * LDQ + jb + c]) = make_double2(row[c], row[c + 1]);
+      }
+      if (inv_thread) {                    // W = Dg^-1 (lower triangular) -> Dinv[I] and the diagonal block of X
+        double Xi[8][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+          for (int a = 0; a < 8; ++a) Xi[a][c] = 0.0;
+          Xi[c][c] = dinv8[c];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) if (a > c) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k >= c && k < a) sacc += Dg[a][k] * Xi[k][c];
+            Xi[a][c] = -sacc * dinv8[a];
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            *reinterpret_cast<double2*>(&Dinv[I * 64 + a * 8 + c]) = make_double2(Xi[a][c], Xi[a][c + 1]);
+            *reinterpret_cast<double2*>(&X[(jb + a) * LDQ + jb + c]) = make_double2(Xi[a][c], Xi[a][c + 1]);
+          }
+      }
+    }
+    {
+      // X[I-1, 8J..8J+7] = -W_{I-1} * S[:, 8J..8J+7] on the warps that hold no row thread (warp 7 is the inverse warp)
+      const int first_free = (nrow + 31) >> 5, nfw = 7 - first_free, P = I - 1;
+      if (I >= 1 && wid >= first_free && wid < 7) {
+        const double* Wp = Dinv + P * 64;
+        for (int J = wid - first_free; J < P; J += nfw) {
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int sk = 0; sk < 2; ++sk) dmma884(d0, d1, Wp[g * 8 + 4 * sk + t], Sb[(4 * sk + t) * LDQ + 8 * J + g]);
+          *reinterpret_cast<double2*>(&X[(8 * P + g) * LDQ + 8 * J + 2 * t]) = make_double2(-d0, -d1);
         }
       }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) L[i * LDP + jb + c] = row[c];
     }
     __syncthreads();
-    // trailing update by 4x4 register blocks: A[i][k] -= sum_c L[i][jb+c] L[k][jb+c] on the lower block triangle
-    const int t0 = jb + 8, nb = (PW - t0) / 4;
-    if (tid < nb * (nb + 1) / 2) {
-      int bi = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
-      while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
-      while (bi * (bi + 1) / 2 > tid) --bi;
-      const int bj = tid - bi * (bi + 1) / 2;
-      const int i0 = t0 + 4 * bi, k0 = t0 + 4 * bj;
-      double acc[4][4];
+    DIAG_STAMP(2 + 2 * I);
+    // ---------------- phase B
+    if (tid < 8) {                         // factored diagonal block (nobody reads these rows during phase B)
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 8; ++a) if (a == tid) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        double2 ar[4], bc[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { ar[a] = *reinterpret_cast<const double2*>(&L[(i0 + a) * LDP + jb + c]); bc[a] = *reinterpret_cast<const double2*>(&L[(k0 + a) * LDP + jb + c]); }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] += ar[a].x * bc[b].x + ar[a].y * bc[b].y;
+        for (int c = 0; c < 8; ++c) if (c <= a) L[(jb + a) * LDQ + jb + c] = Dg[a][c];
       }
+    }
+    __syncwarp();
+    {
+      // trailing update, 8x8 blocks (bi >= bk) of the rows below the block column
+      const int t0 = jb + 8, m = (PW - t0) / 8, nblk = m * (m + 1) / 2;
+      for (int b = wid; b < nblk; b += 24) {   // three blocks per round so their loads and DMMAs overlap
+        double2* cp[3]; double2 c[3]; const double* ap[3]; const double* bp[3]; bool on[3];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int u = 0; u < 3; ++u) {
+          const int bb = b + 8 * u;
+          on[u] = bb < nblk;
+          int bi, bk; diag_block_of(on[u] ? bb : b, bi, bk);
+          const int i0 = t0 + 8 * bi, k0 = t0 + 8 * bk;
+          cp[u] = reinterpret_cast<double2*>(&L[(i0 + g) * LDQ + k0 + 2 * t]);
+          ap[u] = &L[(i0 + g) * LDQ + jb + t]; bp[u] = &L[(k0 + g) * LDQ + jb + t];
+          c[u] = *cp[u];
+        }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) L[(i0 + a) * LDP + k0 + b] -= acc[a][b];   // the strict upper part of diagonal blocks is scratch
+        for (int u = 0; u < 3; ++u) { dmma884(c[u].x, c[u].y, -ap[u][0], bp[u][0]); dmma884(c[u].x, c[u].y, -ap[u][4], bp[u][4]); }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) if (on[u]) *cp[u] = c[u];   // diagonal blocks also get their (unused) upper half
+      }
+      // S[:, 8J..8J+7] = sum_{k = 8J}^{jb-1} L[jb+., k] X[k, 8J+.]; two interleaved accumulators per block
+      for (int J = 7 - wid; J < I; J += 8) {
+        double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+        const double* ap = &L[(jb + g) * LDQ + t];
+        const double* bp = &X[t * LDQ + 8 * J + g];
+        int k = 8 * J;
+        for (; k + 8 <= jb; k += 8) {
+          dmma884(e0, e1, ap[k], bp[k * LDQ]);
+          dmma884(f0, f1, ap[k + 4], bp[(k + 4) * LDQ]);
+        }
+        *reinterpret_cast<double2*>(&Sb[g * LDQ + 8 * J + 2 * t]) = make_double2(e0 + f0, e1 + f1);
+      }
     }
     __syncthreads();
+    DIAG_STAMP(3 + 2 * I);
   }
-  // ---- X = L^-1: invert the 8x8 diagonal blocks, then block forward substitution by block distance
-  if (tid < PW / 8) {
-    const int o = 8 * tid;
-    double Xi[8][8], rl[8];
+  {                                        // last row-block: X[NB-1, 0:8(NB-1)] = -W_{NB-1} * S
+    const double* Wp = Dinv + (NB - 1) * 64;
+    for (int J = wid; J < NB - 1; J += 8) {
+      double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) rl[c] = 1.0 / L[(o + c) * LDP + o + c];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-      for (int a = 0; a < 8; ++a) Xi[a][c] = 0.0;
-      Xi[c][c] = rl[c];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) if (a > c) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k >= c && k < a) s += L[(o + a) * LDP + o + k] * Xi[k][c];
-        Xi[a][c] = -s * rl[a];
-      }
+      for (int sk = 0; sk < 2; ++sk) dmma884(d0, d1, Wp[g * 8 + 4 * sk + t], Sb[(4 * sk + t) * LDQ + 8 * J + g]);
+      *reinterpret_cast<double2*>(&X[(8 * (NB - 1) + g) * LDQ + 8 * J + 2 * t]) = make_double2(-d0, -d1);
     }
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { Dinv[tid * 64 + a * 8 + c] = Xi[a][c]; X[(o + a) * LDP + o + c] = Xi[a][c]; }
   }
   __syncthreads();
-  constexpr int NB = PW / 8;
-  for (int t = 1; t < NB; ++t) {
-    const int cnt = (NB - t) * 64;
-    // stage 1: S_IJ = sum_{K=J}^{I-1} L_IK X_KJ, written into the (still unused) X_IJ slot
-    for (int e = tid; e < cnt; e += blockDim.x) {
-      const int J = e / 64, a = (e % 64) / 8, b = e % 8, I = J + t;
-      double s = 0.0;
-      for (int k = 8 * J; k < 8 * I; ++k) s += L[(8 * I + a) * LDP + k] * X[k * LDP + 8 * J + b];
-      X[(8 * I + a) * LDP + 8 * J + b] = s;
+  DIAG_STAMP(2 + 2 * NB);
+  double* dout = dinv + (size_t)d * PW * PW;
+  for (int e = tid; e < PW * (PW / 2); e += 256) {
+    const int i = e / (PW / 2), j = 2 * (e % (PW / 2));
+    const bool in_lo = i < w && j <= i;                      // j even: (j, j+1) both in the lower triangle unless j == i
+    double2 x = make_double2(0.0, 0.0);
+    if (in_lo) {
+      const double2 l = *reinterpret_cast<const double2*>(&L[i * LDQ + j]);
+      x = *reinterpret_cast<const double2*>(&X[i * LDQ + j]);
+      if (j + 1 <= i) *reinterpret_cast<double2*>(val + rbase[i] + j) = l;
+      else { val[rbase[i] + j] = l.x; x.y = 0.0; }
+      if (j + 1 >= w) x.y = 0.0;
     }
-    __syncthreads();
-    // stage 2: X_IJ = -Dinv_I S_IJ (read everything, then write)
-    double out[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int e = tid + q * 256;
-      out[q] = 0.0;
-      if (e < cnt) {
-        const int J = e / 64, a = (e % 64) / 8, b = e % 8, I = J + t;
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) if (c <= a) s += Dinv[I * 64 + a * 8 + c] * X[(8 * I + c) * LDP + 8 * J + b];
-        out[q] = -s;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int e = tid + q * 256;
-      if (e < cnt) { const int J = e / 64, a = (e % 64) / 8, b = e % 8, I = J + t; X[(8 * I + a) * LDP + 8 * J + b] = out[q]; }
-    }
-    __syncthreads();
-  }
-#pragma unroll 12
-  for (int q = 0; q < PW * PW / 256; ++q) {
-    const int e = tid + 256 * q, i = e / PW, j = e % PW;
-    if (i < w && j <= i) val[rbase[i] + j] = L[i * LDP + j];
-    dinv[(size_t)d * PW * PW + e] = (i < w && j < w && j <= i) ? X[i * LDP + j] : 0.0;
+    *reinterpret_cast<double2*>(dout + i * PW + j) = x;
   }
   if (tid == 0 && bad) *fail = 1;
+  DIAG_STAMP(3 + 2 * NB);
 }
 
-// trsm: X[r][j] = sum_k A[r][c0+k] * Linv[j][k] for the rows r in R_d, in place.  32 rows x 96 columns per CTA,
-// 2 x 6 outputs per thread.
+// trsm: X[r][j] = sum_k A[r][c0+k] * Linv[j][k] for the rows r in R_d, in place.  32 rows x 96 columns per CTA;
+// warp (wm, wn) of the 2 x 4 warp grid owns rows 16 wm.., columns 24 wn.. as 2 x 3 DMMA tiles.  Linv is lower
+// triangular, so output columns j0..j0+7 only need k <= j0+7.
 __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const long long* __restrict__ ptr, const int* __restrict__ start,
                                                           const int* __restrict__ rows_ptr, const int* __restrict__ rows_idx,
                                                           const double* __restrict__ dinv, double* __restrict__ val) {
   extern __shared__ __align__(16) double sm[];
-  double* Li = sm;                    // [PW][LDP]  Linv
-  double* A = sm + PW * LDP;          // [TR][LDP]
+  double* Li = sm;                    // [PW][LDT]  Linv
+  double* A = sm + PW * LDT;          // [TR][LDT]
   __shared__ long long rbase[TR];
   const int c0 = d * PW, tid = threadIdx.x;
   const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
@@ -373,209 +456,273 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
   }
   __syncthreads();
   const double* dsrc = dinv + (size_t)d * PW * PW;
-  for (int e = tid; e < PW * (PW / 2); e += blockDim.x) {
-    const int i = e / (PW / 2), j2 = e % (PW / 2);
-    cp_async16(&Li[i * LDP + 2 * j2], dsrc + i * PW + 2 * j2, true);
-  }
   for (int e = tid; e < TR * (PW / 2); e += blockDim.x) {
     const int i = e / (PW / 2), j2 = e % (PW / 2);
     const bool ok = rbase[i] >= 0;
-    cp_async16(&A[i * LDP + 2 * j2], ok ? (const void*)(val + rbase[i] + 2 * j2) : (const void*)val, ok);
+    cp_async16(&A[i * LDT + 2 * j2], ok ? (const void*)(val + rbase[i] + 2 * j2) : (const void*)val, ok);
+  }
+  for (int e = tid; e < PW * (PW / 2); e += blockDim.x) {
+    const int i = e / (PW / 2), j2 = e % (PW / 2);
+    cp_async16(&Li[i * LDT + 2 * j2], dsrc + i * PW + 2 * j2, true);
   }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
-  const int tx = tid & 15, ty = tid >> 4;
-  double acc[2][6];
+  const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = wid & 1, wn = wid >> 1;
+  double acc[2][3][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < PW; k += 2) {
-    const double2 a0 = *reinterpret_cast<const double2*>(&A[(2 * ty) * LDP + k]);
-    const double2 a1 = *reinterpret_cast<const double2*>(&A[(2 * ty + 1) * LDP + k]);
+    for (int j = 0; j < 3; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  const double* a_s = A + (16 * wm + g) * LDT + t;
+  const double* b_s = Li + (24 * wn + g) * LDT + t;
+  const int kmax = 24 * wn + 24;      // columns of this warp need k < kmax
+  for (int k = 0; k < kmax; k += 4) {
+    double a[2], b[3];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const double2 b = *reinterpret_cast<const double2*>(&Li[(tx + 16 * j) * LDP + k]);
-      acc[0][j] += a0.x * b.x + a0.y * b.y;
-      acc[1][j] += a1.x * b.x + a1.y * b.y;
-    }
+    for (int i = 0; i < 2; ++i) a[i] = a_s[(8 * i) * LDT + k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) b[j] = b_s[(8 * j) * LDT + k];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const long long b = rbase[2 * ty + i];
+    const long long b = rbase[16 * wm + 8 * i + g];
     if (b < 0) continue;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) val[b + tx + 16 * j] = acc[i][j];
+    for (int j = 0; j < 3; ++j) *reinterpret_cast<double2*>(val + b + 24 * wn + 8 * j + 2 * t) = make_double2(acc[i][j][0], acc[i][j][1]);
   }
 }
 
-// update: A[r][c] -= X[r,:] . X[c,:] over the tiles (ti, tj) of R_d x R_d that intersect the lower triangle,
-// column tiles tj in [tj0, tj0 + gridDim.x).
-template <int UM>   // 128: throughput tiles (8x4 per thread) for the bulk; 32: latency tiles (2x4) for the look-ahead columns
-__global__ void __launch_bounds__(256, 2) sky_update_kernel(int d, int n, int tj0, const long long* __restrict__ ptr, const int* __restrict__ start,
+// update: A[r][c] -= X[r,:] . X[c,:] over the tiles (ti, tj) of R_d x R_d that intersect the lower triangle, except
+// the elements with r < skip_below (the diagonal block of panel d+1, which C(d+1) updates itself).
+// Row tile ti owns the column tiles tj = 0 .. 2 ti + 1 (UM == 2 UN).  Two launches per panel:
+//   part 0 ("next")  the column tiles tj < 2 — they hold every column of panel d+1, which trsm(d+1) is waiting for;
+//                    tile index T = 2 ti + tj;
+//   part 1 ("rest")  tj >= 2, T = ti (ti - 1) + (tj - 2), on the low-priority stream.
+// A CTA is two independent 256-thread groups (own shared-memory half, own named barrier), one tile each; it needs
+// 216 KB of shared memory, so exactly one fits per SM and the chain kernel C(d+1) (167 KB) always finds a free SM
+// as soon as any CTA retires, instead of waiting for two co-resident CTAs to retire together.
+// Per group 8 warps as 4 x 2, every warp a grid of 4 x 4 8x8 DMMA tiles, K = 96 in three cp.async chunks.
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+template <int PART>
+__global__ void __launch_bounds__(512, 1) sky_update_kernel(int d, int n, int skip_below, int Tr, int Tc,
+                                                            const long long* __restrict__ ptr, const int* __restrict__ start,
                                                             const int* __restrict__ rows_ptr, const int* __restrict__ rows_idx, double* __restrict__ val) {
-  constexpr int MI = UM / 16;
-  const int ti = blockIdx.y, tj = tj0 + blockIdx.x;
-  if (tj * UN >= (ti + 1) * UM) return;     // tile entirely above the diagonal
+  constexpr int WARPS_M = 4, WARPS_N = 2;
+  constexpr int WTM = UM / WARPS_M, WTN = UN / WARPS_N, FM = WTM / 8, FN = WTN / 8;
+  static_assert(UM == 2 * UN, "triangular tile enumeration assumes UM == 2 UN");
   extern __shared__ __align__(16) double sm[];
-  double* As = sm;                           // [2][UM][LDK]
-  double* Bs = sm + 2 * UM * LDK;            // [2][UN][LDK]
-  __shared__ long long s_abase[UM], s_bbase[UN];   // element offset of (row, c0) in val, -1 = no such row
-  __shared__ int s_arow[UM], s_bcol[UN];
-  const int c0 = d * PW, tid = threadIdx.x;
+  const int grp = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  double* As = sm + grp * (2 * (UM + UN) * LDK);   // [2][UM][LDK]
+  double* Bs = As + 2 * UM * LDK;                  // [2][UN][LDK]
+  __shared__ long long sh_abase[2][UM], sh_bbase[2][UN];   // element offset of (row, c0) in val, -1 = no such row
+  __shared__ int sh_arow[2][UM], sh_bcol[2][UN];
+  long long* s_abase = sh_abase[grp]; long long* s_bbase = sh_bbase[grp];
+  int* s_arow = sh_arow[grp]; int* s_bcol = sh_bcol[grp];
+  const int c0 = d * PW;
   const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
-  if (tid < UM) {
-    const int ir = ti * UM + tid;
-    const int r = ir < nr ? rows_idx[rb + ir] : -1;
-    s_arow[tid] = r; s_abase[tid] = r >= 0 ? ptr[r] + (c0 - start[r]) : -1;
-  } else if (tid < UM + UN) {
-    const int t = tid - UM, ic = tj * UN + t;
-    int c = ic < nr ? rows_idx[rb + ic] : -1;
-    if (c >= n) c = -1;                      // the rhs row is never a column
-    s_bcol[t] = c; s_bbase[t] = c >= 0 ? ptr[c] + (c0 - start[c]) : -1;
-  }
-  __syncthreads();
-  auto issue = [&](int chunk, int stage) {
-    const int k0 = chunk * KC;
-    double* a_dst = As + stage * UM * LDK; double* b_dst = Bs + stage * UN * LDK;
-#pragma unroll
-    for (int e = tid; e < (UM + UN) * (KC / 2); e += 256) {
-      const int row = e / (KC / 2), seg = e % (KC / 2);
-      if (row < UM) { const long long b = s_abase[row]; cp_async16(&a_dst[row * LDK + 2 * seg], b >= 0 ? (const void*)(val + b + k0 + 2 * seg) : (const void*)val, b >= 0); }
-      else { const int rr = row - UM; const long long b = s_bbase[rr]; cp_async16(&b_dst[rr * LDK + 2 * seg], b >= 0 ? (const void*)(val + b + k0 + 2 * seg) : (const void*)val, b >= 0); }
-    }
-    cp_async_commit();
-  };
-  // lane layout inside a warp: 8 (tx) x 4 (ty); warp w covers ty 4*(w>>1).., tx 8*(w&1)..
-  const int lane = tid & 31, wid = tid >> 5;
-  const int tx = (wid & 1) * 8 + (lane & 7), ty = (wid >> 1) * 4 + (lane >> 3);   // tx 0..15 -> cols tx+16j, ty 0..15 -> rows ty+16i
-  // 64-bit shared loads: a warp reads 4 distinct a addresses and 8 distinct b addresses per instruction, all in
-  // different banks (row stride 68 words), so every load is a single broadcast wavefront
-  double acc[MI][4];
-#pragma unroll
-  for (int i = 0; i < MI; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = wid % WARPS_M, wn = wid / WARPS_M;
   constexpr int NCH = PW / KC;
-  issue(0, 0);
-  issue(1, 1);
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (ch + 1 < NCH) cp_async_wait<1>(); else cp_async_wait<0>();
-    __syncthreads();
-    const double* a_s = As + (ch & 1) * UM * LDK + ty * LDK;
-    const double* b_s = Bs + (ch & 1) * UN * LDK + tx * LDK;
-#pragma unroll 8
-    for (int k = 0; k < KC; ++k) {
-      double a[MI], b[4];
-#pragma unroll
-      for (int i = 0; i < MI; ++i) a[i] = a_s[(16 * i) * LDK + k];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = b_s[(16 * j) * LDK + k];
-#pragma unroll
-      for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
-    if (ch + 2 < NCH) { __syncthreads(); issue(ch + 2, ch & 1); }
-  }
-  // epilogue: read-modify-write in groups of up to 4 rows so up to 16 loads are in flight per thread
-  int cidx[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) cidx[j] = s_bcol[tx + 16 * j];
-  constexpr int HR = MI < 4 ? MI : 4;
-#pragma unroll
-  for (int h = 0; h < MI / HR; ++h) {
-    double old[HR][4]; long long base[HR]; int rr[HR];
-#pragma unroll
-    for (int i = 0; i < HR; ++i) {
-      rr[i] = s_arow[ty + 16 * (HR * h + i)];
-      base[i] = rr[i] >= 0 ? s_abase[ty + 16 * (HR * h + i)] - c0 : 0;   // offset of (row, column 0)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const int c = cidx[j]; old[i][j] = (rr[i] >= 0 && c >= 0 && c <= rr[i]) ? val[base[i] + c] : 0.0; }
-    }
-#pragma unroll
-    for (int i = 0; i < HR; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const int c = cidx[j]; if (rr[i] >= 0 && c >= 0 && c <= rr[i]) val[base[i] + c] = old[i][j] - acc[HR * h + i][j]; }
-  }
-}
-
-// backward sweep for panel d (processed D-1 .. 0):  x_d = Linv^T (y_d + acc_d)  [or x_d given, for border panels],
-// then push  acc[c] -= sum_{r in panel} L[r][c] x_r  for every column c in [lo, c0) inside the rows' envelopes.
-// 256 threads = 32 columns x 8 row groups.
-__global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo, int x_given, const long long* __restrict__ ptr, const int* __restrict__ start,
-                                                           const double* __restrict__ val, const double* __restrict__ dinv,
-                                                           double* __restrict__ acc, double* __restrict__ x) {
-  extern __shared__ __align__(16) double sm[];
-  double* Li = sm;                      // [PW][PW+1]
-  __shared__ double xs[PW], rhs[PW], red[8][33];
-  __shared__ long long rbase[PW];       // ptr[r] - start[r]
-  __shared__ int rstart[PW];
-  const int c0 = d * PW, w = min(PW, n - c0), tid = threadIdx.x;
-  if (tid < PW) {
-    const int r = c0 + tid;
-    rbase[tid] = tid < w ? ptr[r] - start[r] : 0; rstart[tid] = tid < w ? start[r] : 0x7fffffff;
-    rhs[tid] = tid < w ? val[ptr[n] + c0 + tid] + acc[c0 + tid] : 0.0;
-  }
-  if (!x_given) {
-    const double* dsrc = dinv + (size_t)d * PW * PW;
-    for (int e = tid; e < PW * PW; e += blockDim.x) Li[(e / PW) * (PW + 1) + (e % PW)] = dsrc[e];
-  }
-  __syncthreads();
-  if (tid < PW) {
-    double s;
-    if (x_given) s = tid < w ? x[c0 + tid] : 0.0;
+  {
+    const int T = 2 * blockIdx.x + grp;
+    int ti, tj;
+    if (PART == 0) { ti = T >> 1; tj = T & 1; }
     else {
-      double s0 = 0.0, s1 = 0.0;   // x_j = sum_{i>=j} Linv[i][j] rhs_i
-      int i = tid;
-      for (; i + 1 < w; i += 2) { s0 += Li[i * (PW + 1) + tid] * rhs[i]; s1 += Li[(i + 1) * (PW + 1) + tid] * rhs[i + 1]; }
-      if (i < w) s0 += Li[i * (PW + 1) + tid] * rhs[i];
-      s = s0 + s1;
-      if (blockIdx.x == 0 && tid < w) x[c0 + tid] = s;
+      ti = (int)((1.0f + sqrtf(1.0f + 4.0f * (float)T)) * 0.5f);
+      while (ti * (ti - 1) > T) --ti;
+      while ((ti + 1) * ti <= T) ++ti;
+      tj = 2 + (T - ti * (ti - 1));
     }
-    xs[tid] = s;
-  }
-  __syncthreads();
-  const int cx = tid & 31, g = tid >> 5;
-  for (int cb = lo + blockIdx.x * 32; cb < c0; cb += gridDim.x * 32) {
-    const int c = cb + cx;
-    double s = 0.0;
-    if (c < c0) {
+    if (ti >= Tr || tj >= Tc) return;        // whole group: no tile (odd tile count, or the last row tile ran past Tc)
+    if (tid < UM) {
+      const int ir = ti * UM + tid;
+      const int r = ir < nr ? rows_idx[rb + ir] : -1;
+      s_arow[tid] = r; s_abase[tid] = r >= 0 ? ptr[r] + (c0 - start[r]) : -1;
+    } else if (tid < UM + UN) {
+      const int q = tid - UM, ic = tj * UN + q;
+      int c = ic < nr ? rows_idx[rb + ic] : -1;
+      if (c >= n) c = -1;                    // the rhs row is never a column
+      s_bcol[q] = c; s_bbase[q] = c >= 0 ? ptr[c] + (c0 - start[c]) : -1;
+    }
+    group_sync(grp);
+    auto issue = [&](int chunk, int stage) {
+      const int k0 = chunk * KC;
+      double* a_dst = As + stage * UM * LDK; double* b_dst = Bs + stage * UN * LDK;
 #pragma unroll
-      for (int q = 0; q < PW / 8; ++q) {
-        const int i = g * (PW / 8) + q;
-        if (c >= rstart[i]) s += val[rbase[i] + c] * xs[i];
+      for (int e = tid; e < (UM + UN) * (KC / 2); e += 256) {
+        const int row = e / (KC / 2), seg = e % (KC / 2);
+        if (row < UM) { const long long bo = s_abase[row]; cp_async16(&a_dst[row * LDK + 2 * seg], bo >= 0 ? (const void*)(val + bo + k0 + 2 * seg) : (const void*)val, bo >= 0); }
+        else { const int rr = row - UM; const long long bo = s_bbase[rr]; cp_async16(&b_dst[rr * LDK + 2 * seg], bo >= 0 ? (const void*)(val + bo + k0 + 2 * seg) : (const void*)val, bo >= 0); }
+      }
+      cp_async_commit();
+    };
+    issue(0, 0);
+    issue(1, 1);
+    // The accumulators start at A_old and the A fragments are negated, so the tile leaves the loop as
+    // A_old - X X^T and the epilogue is a plain store: the read half of the read-modify-write is in flight together
+    // with the first operand chunk (loaded straight into the accumulator registers) instead of stalling the
+    // epilogue.  A lane owns two adjacent list positions (even, odd) of a row; list positions of a node's six
+    // scalars are consecutive and start even, so the pair is always (c, c + 1), 16-byte aligned; on the diagonal
+    // (c == r) only the first of the two exists.
+    double acc[FM][FN][2];
+    int cidx[FN];
+#pragma unroll
+    for (int j = 0; j < FN; ++j) cidx[j] = s_bcol[wn * WTN + 8 * j + 2 * t];
+#pragma unroll
+    for (int i = 0; i < FM; ++i) {
+      const int rl = wm * WTM + 8 * i + g;
+      const int r = s_arow[rl];
+      const long long base = r >= 0 ? s_abase[rl] - c0 : 0;   // offset of (row, column 0)
+      const bool live = r >= skip_below;                       // also false for r = -1
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        const int c = cidx[j];
+        double2 o = make_double2(0.0, 0.0);
+        if (live && c >= 0) {
+          if (c + 1 <= r) o = *reinterpret_cast<const double2*>(val + base + c);
+          else if (c == r) o.x = val[base + c];
+        }
+        acc[i][j][0] = o.x; acc[i][j][1] = o.y;
       }
     }
-    red[g][cx] = s;
-    __syncthreads();
-    if (g == 0 && c < c0) {
-      double t = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) t += red[q][cx];
-      acc[c] -= t;
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (ch + 1 < NCH) cp_async_wait<1>(); else cp_async_wait<0>();
+      group_sync(grp);
+      const double* a_s = As + (ch & 1) * UM * LDK + (wm * WTM + g) * LDK + t;
+      const double* b_s = Bs + (ch & 1) * UN * LDK + (wn * WTN + g) * LDK + t;
+#pragma unroll
+      for (int k = 0; k < KC; k += 4) {
+        double a[FM], bf[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) a[i] = -a_s[(8 * i) * LDK + k];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) bf[j] = b_s[(8 * j) * LDK + k];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+      }
+      if (ch + 2 < NCH) { group_sync(grp); issue(ch + 2, ch & 1); }
     }
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < FM; ++i) {
+      const int rl = wm * WTM + 8 * i + g;
+      const int r = s_arow[rl];
+      const long long base = r >= 0 ? s_abase[rl] - c0 : 0;
+      const bool live = r >= skip_below;
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        const int c = cidx[j];
+        if (live && c >= 0) {
+          if (c + 1 <= r) *reinterpret_cast<double2*>(val + base + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+          else if (c == r) val[base + c] = acc[i][j][0];
+        }
+      }
+    }
   }
 }
 
-static const size_t SM_TRSM = sizeof(double) * (PW * LDP + TR * LDP);
-static const size_t SM_UPD = sizeof(double) * (2 * (UM_BULK + UN) * LDK);
-static const size_t SM_UPD_NEXT = sizeof(double) * (2 * (UM_NEXT + UN) * LDK);
-static const size_t SM_DIAG = sizeof(double) * (2 * PW * LDP + (PW / 8) * 64);
-static const size_t SM_BACK = sizeof(double) * (PW * (PW + 1));
+// backward sweep, one launch per panel d = D-1 .. 0 (plus one leading launch that only computes x of the last panel):
+//   push      acc[c] -= sum_{r in panel d} L[r][c] x_r  for every column c in [lo, c0) inside the rows' envelopes
+//             (256 threads = 32 columns x 8 row groups per CTA);
+//   next x    the last CTA to finish then solves the next panel, x_{d-1} = Linv_{d-1}^T (y_{d-1} + acc_{d-1}) — its
+//             accumulator is complete at that point — so Linv is read once per panel, not once per CTA.
+// Border panels of a partial factorisation (d >= D_elim) take x as given: they push, nobody computes them.
+__global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo, int do_push, int next_d, const long long* __restrict__ ptr,
+                                                           const int* __restrict__ start, const double* __restrict__ val, const double* __restrict__ dinv,
+                                                           double* __restrict__ acc, double* __restrict__ x, unsigned int* __restrict__ cnt) {
+  __shared__ double xs[PW], red[8][33];
+  __shared__ long long rbase[PW];       // ptr[r] - start[r]
+  __shared__ int rstart[PW];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  if (do_push) {
+    const int c0 = d * PW, w = min(PW, n - c0);
+    if (tid < PW) {
+      const int r = c0 + tid;
+      rbase[tid] = tid < w ? ptr[r] - start[r] : 0; rstart[tid] = tid < w ? start[r] : 0x7fffffff;
+      xs[tid] = tid < w ? x[c0 + tid] : 0.0;
+    }
+    __syncthreads();
+    const int cx = tid & 31, g = tid >> 5;
+    for (int cb = lo + blockIdx.x * 32; cb < c0; cb += gridDim.x * 32) {
+      const int c = cb + cx;
+      double s = 0.0;
+      if (c < c0) {
+#pragma unroll
+        for (int q = 0; q < PW / 8; ++q) {
+          const int i = g * (PW / 8) + q;
+          if (c >= rstart[i]) s += val[rbase[i] + c] * xs[i];
+        }
+      }
+      red[g][cx] = s;
+      __syncthreads();
+      if (g == 0 && c < c0) {
+        double tt = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tt += red[q][cx];
+        acc[c] -= tt;
+      }
+      __syncthreads();
+    }
+  }
+  if (next_d < 0) return;
+  if (tid == 0) {
+    __threadfence();
+    const bool last = atomicAdd(cnt, 1u) == gridDim.x - 1;
+    if (last) *cnt = 0u;
+    is_last = last ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    const int c0 = next_d * PW, w = min(PW, n - c0);
+    double* rhs = xs;                     // reuse
+    if (tid < PW) rhs[tid] = tid < w ? val[ptr[n] + c0 + tid] + __ldcg(acc + c0 + tid) : 0.0;
+    __syncthreads();
+    const double* Li = dinv + (size_t)next_d * PW * PW;
+    // x_j = sum_{i>=j} Linv[i][j] rhs_i: warp wq takes rows i = wq, wq+8, ..., a lane three columns; all 36 loads of
+    // a lane are independent, so the whole product costs one L2 round trip.  Linv is stored with explicit zeros
+    // above the diagonal, so no triangle test is needed.
+    const int ln = tid & 31, wq = tid >> 5;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < PW / 8; ++q) {
+      const int i = wq + 8 * q;
+      const double ri = rhs[i];
+      p0 += Li[i * PW + ln] * ri; p1 += Li[i * PW + 32 + ln] * ri; p2 += Li[i * PW + 64 + ln] * ri;
+    }
+    __shared__ double part[8][PW];
+    part[wq][ln] = p0; part[wq][32 + ln] = p1; part[wq][64 + ln] = p2;
+    __syncthreads();
+    if (tid < w) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sacc += part[q][tid];
+      x[c0 + tid] = sacc;
+    }
+  }
+}
+
+static const size_t SM_TRSM = sizeof(double) * (PW * LDT + TR * LDT);
+static const size_t SM_UPD = sizeof(double) * (2 * 2 * (UM + UN) * LDK);   // two groups x two stages: 216 KB, one CTA per SM
+static const size_t SM_DIAG = sizeof(double) * (2 * PW * LDT + (PW / 8) * 64 + 8 * LDT);
 
 static int set_attrs(std::string* err) {
   static bool attr_set = false;
   if (attr_set) return PGS_OK;
   SK(cudaFuncSetAttribute(sky_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
   SK(cudaFuncSetAttribute(sky_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TRSM));
-  SK(cudaFuncSetAttribute(sky_update_kernel<UM_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
-  SK(cudaFuncSetAttribute(sky_update_kernel<UM_NEXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD_NEXT));
-  SK(cudaFuncSetAttribute(sky_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BACK));
+  SK(cudaFuncSetAttribute(sky_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
+  SK(cudaFuncSetAttribute(sky_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
   attr_set = true;
   return PGS_OK;
 }
@@ -617,31 +764,39 @@ int skyline_factor(SkylineFactor* f, const double* Ad, const double* Ao, const d
 }
 
 int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
-  cudaStream_t s0 = f->stream, s1 = f->s1;
+  cudaStream_t s0 = f->stream, s1 = f->s1, s2 = f->s2;
   const int n = f->n;
   SK(cudaEventRecord(f->ev_fork, s0));
   SK(cudaStreamWaitEvent(s1, f->ev_fork, 0));
-  // panel stream s1:  [wait rest(d-1)] next(d) ... diag(d) trsm(d) -> ev_trsm[d]
-  // main  stream s0:  [wait ev_trsm[d]] rest(d) -> ev_rest[d]
+  SK(cudaStreamWaitEvent(s2, f->ev_fork, 0));
+  // chain stream s1:  [wait trsm(d-1), rest(d-2)] C(d)    -> ev_c[d]
+  // panel stream s2:  [wait C(d)]                 trsm(d) -> ev_trsm[d]   [wait rest(d-1)] next(d)
+  // main  stream s0:  [wait trsm(d)]              rest(d) -> ev_rest[d]
+  // next(d-1) precedes trsm(d) on s2, rest(d-1) precedes rest(d) on s0.
   for (int d = 0; d < f->D_elim; ++d) {
     const int nr = f->h_rows_ptr[d + 1] - f->h_rows_ptr[d];
-    const int Tr = (nr + UM_BULK - 1) / UM_BULK, Trn = (nr + UM_NEXT - 1) / UM_NEXT, Tc = (nr + UN - 1) / UN;
-    sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, f->ptr, f->start, f->val, f->dinv, f->fail);
-    sky_trsm_kernel<<<(nr + TR - 1) / TR, 256, SM_TRSM, s1>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val);
-    SK(cudaEventRecord(f->ev_trsm[d % NEV], s1));
-    // rest(d) on the main stream, concurrent with next(d) / diag(d+1) / trsm(d+1)
-    if (Tc > NEXT_TILES) {
-      SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
-      sky_update_kernel<UM_BULK><<<dim3(Tc - NEXT_TILES, Tr), 256, SM_UPD, s0>>>(d, n, NEXT_TILES, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
-    }
+    const int Tr = (nr + UM - 1) / UM, Tc = (nr + UN - 1) / UN;
+    if (d > 0) SK(cudaStreamWaitEvent(s1, f->ev_trsm[(d - 1) % NEV], 0));
+    if (d > 1) SK(cudaStreamWaitEvent(s1, f->ev_rest[(d - 2) % NEV], 0));   // rest(d-2) holds part of panel d-2's update of A_dd
+    sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
+    SK(cudaEventRecord(f->ev_c[d % NEV], s1));
+    SK(cudaStreamWaitEvent(s2, f->ev_c[d % NEV], 0));
+    sky_trsm_kernel<<<(nr + TR - 1) / TR, 256, SM_TRSM, s2>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val);
+    SK(cudaEventRecord(f->ev_trsm[d % NEV], s2));
+    // C(d+1) applies panel d's update to its own diagonal block; past the eliminated part nobody does, so next(d) keeps it.
+    // The rhs row (index n) is always live, also when the last panel is short.
+    const int skip_below = (d + 1 < f->D_elim) ? std::min((d + 2) * PW, n) : 0;
+    if (d > 0) SK(cudaStreamWaitEvent(s2, f->ev_rest[(d - 1) % NEV], 0));
+    sky_update_kernel<0><<<Tr, 512, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
+    SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
+    if (Tr > 1) sky_update_kernel<1><<<(Tr * (Tr - 1) + 1) / 2, 512, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     SK(cudaEventRecord(f->ev_rest[d % NEV], s0));
-    // next(d): columns of panel d+1 (and a little beyond); must follow rest(d-1), which may touch the same columns
-    if (d > 0) SK(cudaStreamWaitEvent(s1, f->ev_rest[(d - 1) % NEV], 0));
-    sky_update_kernel<UM_NEXT><<<dim3(std::min(Tc, NEXT_TILES), Trn), 256, SM_UPD_NEXT, s1>>>(d, n, 0, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
   }
-  // join: the main stream continues after both streams are done
+  // join: the main stream continues after all three are done
   SK(cudaEventRecord(f->ev_join, s1));
   SK(cudaStreamWaitEvent(s0, f->ev_join, 0));
+  SK(cudaEventRecord(f->ev_join2, s2));
+  SK(cudaStreamWaitEvent(s0, f->ev_join2, 0));
   SK(cudaGetLastError());
   return PGS_OK;
 }
@@ -649,12 +804,17 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
 // Backward substitution L^T x = y.  Panels >= D_elim (border, multi-GPU) take x as given in y[] beforehand.
 int skyline_backward(SkylineFactor* f, double* y, std::string* err) {
   cudaStream_t st = f->stream;
-  const int n = f->n;
-  for (int d = f->D - 1; d >= 0; --d) {
+  const int n = f->n, D = f->D;
+  if (D == 0) return PGS_OK;
+  unsigned int* cnt = f->sched + 2;
+  // x of the last panel (unless it is a given border panel)
+  if (D - 1 < f->D_elim) sky_backward_kernel<<<1, 256, 0, st>>>(D, n, 0, 0, D - 1, f->ptr, f->start, f->val, f->dinv, f->xacc, y, cnt);
+  for (int d = D - 1; d >= 0; --d) {
     const int cols = d * PW - f->h_lo[d];
+    const int next_d = (d - 1 >= 0 && d - 1 < f->D_elim) ? d - 1 : -1;
+    if (cols <= 0 && next_d < 0) continue;
     const int grid = std::max(1, std::min(592, (cols + 31) / 32));
-    const int given = d >= f->D_elim ? 1 : 0;
-    sky_backward_kernel<<<grid, 256, SM_BACK, st>>>(d, n, f->h_lo[d], given, f->ptr, f->start, f->val, f->dinv, f->xacc, y);
+    sky_backward_kernel<<<grid, 256, 0, st>>>(d, n, f->h_lo[d], cols > 0 ? 1 : 0, next_d, f->ptr, f->start, f->val, f->dinv, f->xacc, y, cnt);
   }
   SK(cudaGetLastError());
   return PGS_OK;
