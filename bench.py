@@ -246,7 +246,8 @@ def main():
             "metric": METRIC, "value": E_total / (ms_step_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, full, world), "edges_per_gpu": E_local, "l2": "flushed between timed steps (384 MiB scratch write, then 256 MiB re-read so no dirty lines are left to write back)",
-                       "step": "sweep_kernel<J>: residuals, Jacobian blocks and cost in one launch", "parallelism": f"node-range x{world}"},
+                       "step": "sweep_kernel<J>: residuals, Jacobian blocks and cost in one launch", "parallelism": f"node-range x{world}",
+                       "nodes_per_gpu": int(shard["N"]), "halo_nodes_rank0": int(shard.get("n_halo", 0))},
             "e2e": {"value": E_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                     "h2d_bytes_per_step": int(56 * shard["N"] + 8 * len(shard["la"])), "d2h_bytes_per_step": 8,
                     "api": "pgs_evaluate_from_host (pinned q,t,switches -> device, mode-J sweep, cost -> host)"},

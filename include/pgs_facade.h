@@ -46,6 +46,15 @@ int pgs_facade_get_poses(pgs_facade_handle h, double* q_xyzw, double* t);     /*
 int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s);       /* per manager loop edge */
 int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* iters, int32_t cap);
 
+/* Composer (reference src/Composer.cpp:10-292): one pass of pose_assember_thread's loop body on the device
+ * (include/pgs_compose.h).  out_T [n][16] row-major assembled pose per keyframe (global_lmb), out_world [n] its
+ * world id (the key of global_jmb); either may be NULL.  Returns the number of keyframes, < 0 on error. */
+int pgs_facade_compose(pgs_facade_handle h, double* out_T, int32_t* out_world);
+int32_t pgs_facade_n_keyframes(pgs_facade_handle h);                          /* manager->getNodeLen() */
+/* get_last_known_camerapose (Composer.cpp:264-276): index of the last keyframe or -1; T16 / stamp may be NULL */
+int pgs_facade_last_known_camerapose(pgs_facade_handle h, double* T16, int64_t* stamp_ns);
+int pgs_facade_compose_timing(pgs_facade_handle h, double* ms_kernel, double* ms_total);
+
 /* introspection of the graph-construction rules (parity tests against the oracle front-end) */
 int32_t pgs_facade_n_odom_terms(pgs_facade_handle h);
 int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w);

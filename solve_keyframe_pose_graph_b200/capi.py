@@ -134,6 +134,38 @@ def partition(n_nodes, world, oc1, oc2, la, lb, rn):
     return dict(node_owner=node_owner[:n_nodes], odom_owner=oo[:len(oc1)], loop_owner=lo[:len(la)], reg_owner=ro[:len(rn)], n_border=nb.value)
 
 
+class ComposeInput(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("mgr_T", c_dp), ("world_id", c_ip), ("n_slam", C.c_int32), ("slam_q", c_dp), ("slam_t", c_dp),
+                ("solved_until", C.c_int32), ("solved_until_world", C.c_int32), ("n_worlds", C.c_int32), ("world_end", c_ip),
+                ("world_setid", c_ip), ("ws_exists", C.POINTER(C.c_uint8)), ("ws_T_w", c_dp)]
+
+
+def compose_poses(mgr_T, world_id, slam_q, slam_t, solved_until, solved_until_world, world_end, world_setid, ws_exists, ws_T_w, device=0):
+    """include/pgs_compose.h in one call: the Composer pose assembly (reference src/Composer.cpp:24-209) on the device.
+    Returns (T [n,4,4], kernel ms, total ms)."""
+    L = lib()
+    L.pgs_compose_last_error.restype = C.c_char_p; L.pgs_compose_last_error.argtypes = [C.c_void_p]
+    h = C.c_void_p()
+    if L.pgs_compose_create(C.c_int32(device), C.byref(h)) != 0:
+        raise PgsError("pgs_compose_create failed: no usable CUDA device (there is no CPU fallback)")
+    try:
+        mgr_T, pm = _d(np.asarray(mgr_T).reshape(-1, 16)); wid, pw = _i(world_id)
+        sq, pq = _d(np.asarray(slam_q).reshape(-1, 4)); st, pt = _d(np.asarray(slam_t).reshape(-1, 3))
+        we, pe = _i(world_end); ws, ps = _i(world_setid)
+        ex = np.ascontiguousarray(ws_exists, dtype=np.uint8); wt, pwt = _d(np.asarray(ws_T_w).reshape(-1, 16))
+        inp = ComposeInput(len(wid), pm, pw, len(sq), pq, pt, int(solved_until), int(solved_until_world), len(we), pe, ps,
+                           ex.ctypes.data_as(C.POINTER(C.c_uint8)), pwt)
+        out = np.zeros((max(len(wid), 1), 4, 4))
+        rc = L.pgs_compose_run(h, C.byref(inp), out.ctypes.data_as(c_dp))
+        if rc != 0:
+            raise PgsError(f"pgs_compose_run failed ({rc}): {L.pgs_compose_last_error(h).decode()}")
+        a = C.c_double(0); b = C.c_double(0)
+        L.pgs_compose_last_timing(h, C.byref(a), C.byref(b))
+        return out[: len(wid)], a.value, b.value
+    finally:
+        L.pgs_compose_destroy(h)
+
+
 def default_options(**kw):
     o = Options()
     lib().pgs_default_options(C.byref(o))

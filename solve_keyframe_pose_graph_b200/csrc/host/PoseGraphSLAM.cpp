@@ -22,6 +22,7 @@ void PoseGraphSLAM::getAllNodePose(std::vector<Matrix4d>& w_T_ci) const {
   const int n = nNodes();
   for (int i = 0; i < n; ++i) w_T_ci.push_back(getNodePose(i));
 }
+void PoseGraphSLAM::getAllNodeRaw(std::vector<double>& q, std::vector<double>& t) const { std::lock_guard<std::mutex> lk(mutex_opt_vars); q = _opt_quat_; t = _opt_t_; }
 int PoseGraphSLAM::nNodes() const { std::lock_guard<std::mutex> lk(mutex_opt_vars); return (int)(_opt_t_.size() / 3); }
 const Matrix4d PoseGraphSLAM::getNodePose(int i) const {
   std::lock_guard<std::mutex> lk(mutex_opt_vars);

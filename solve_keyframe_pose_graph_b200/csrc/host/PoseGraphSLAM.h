@@ -59,6 +59,7 @@ class PoseGraphSLAM {
   bool nodePoseExists(int i) const;
   int nNodes() const;
   void getAllNodePose(std::vector<Matrix4d>& vec_w_T_ci) const;
+  void getAllNodeRaw(std::vector<double>& quat_xyzw, std::vector<double>& t) const;   // the optimiser's own storage, one lock (used by Composer)
   int solvedUntil() const { std::lock_guard<std::mutex> lk(mutex_opt_vars); return solved_until; }
   double get_loopedge_switching_variable_val(int i) const;      // i = loop-edge index; NaN for a bad index
   const std::tuple<int, int, float, std::string>& get_odomedge_residue_info(int i) const;

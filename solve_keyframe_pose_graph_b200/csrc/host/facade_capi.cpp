@@ -4,13 +4,16 @@
 #include <cstring>
 #include <string>
 
+#include "Composer.h"
 #include "PoseGraphSLAM.h"
 
 struct pgs_facade_s {
   pgs::NodeDataManager manager;
   pgs::PoseGraphSLAM* slam = nullptr;
+  pgs::Composer* composer = nullptr;
+  int device = 0;
   std::string err;
-  ~pgs_facade_s() { delete slam; }
+  ~pgs_facade_s() { delete composer; delete slam; }
 };
 
 extern "C" {
@@ -28,6 +31,7 @@ int pgs_facade_create(const pgs_facade_options* o, pgs_facade_handle* out) {
   pgs::PoseGraphSLAMOptions po;
   po.odom_fanout = d.odom_fanout; po.derive_odometry = d.derive_odometry != 0; po.dry_run = d.dry_run != 0; po.solver = d.solver;
   h->slam = new pgs::PoseGraphSLAM(&h->manager, po);
+  h->device = d.solver.device;
   *out = h;
   return PGS_OK;
 }
@@ -85,6 +89,33 @@ int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* i
   if (s) *s = h->slam->last_summary();
   const auto& it = h->slam->last_iterations();
   for (int i = 0; iters && i < cap && i < (int)it.size(); ++i) iters[i] = it[i];
+  return PGS_OK;
+}
+int pgs_facade_compose(pgs_facade_handle h, double* out_T, int32_t* out_world) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  if (!h->composer) h->composer = new pgs::Composer(&h->manager, h->slam, h->device);
+  if (!h->composer->pose_assember_once()) { h->err = h->composer->last_error(); return PGS_ERR_CUDA; }
+  const std::vector<pgs::Matrix4d> lmb = h->composer->get_global_lmb();
+  const int n = (int)lmb.size();
+  for (int i = 0; i < n; ++i) {
+    if (out_T) std::memcpy(out_T + 16 * (size_t)i, lmb[i].m, 128);
+    if (out_world) out_world[i] = h->manager.which_world_is_this(h->manager.getNodeTimestamp(i));
+  }
+  return n;
+}
+int32_t pgs_facade_n_keyframes(pgs_facade_handle h) { return h ? h->manager.getNodeLen() : 0; }
+int pgs_facade_last_known_camerapose(pgs_facade_handle h, double* T16, int64_t* stamp_ns) {
+  if (!h || !h->composer) return -1;
+  pgs::Matrix4d T; int64_t st = 0;
+  const int r = h->composer->get_last_known_camerapose(T, st);
+  if (r >= 0) { if (T16) std::memcpy(T16, T.m, 128); if (stamp_ns) *stamp_ns = st; }
+  return r;
+}
+int pgs_facade_compose_timing(pgs_facade_handle h, double* ms_kernel, double* ms_total) {
+  if (!h || !h->composer) return PGS_ERR_STATE;
+  if (ms_kernel) *ms_kernel = h->composer->last_kernel_ms();
+  if (ms_total) *ms_total = h->composer->last_total_ms();
   return PGS_OK;
 }
 int32_t pgs_facade_n_odom_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->odometry_terms().size() : 0; }

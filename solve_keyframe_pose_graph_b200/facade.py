@@ -126,6 +126,27 @@ class Facade:
         d["iterations"] = [{f: getattr(its[i], f) for f, _ in Iteration._fields_} for i in range(min(s.num_iterations, cap))]
         return d
 
+    # ---- Composer (reference src/Composer.cpp:10-292)
+    def n_keyframes(self):
+        return self.L.pgs_facade_n_keyframes(self.h)
+
+    def compose(self):
+        """One pass of Composer::pose_assember_thread on the device -> (T [n,4,4] assembled poses, world id [n])."""
+        n = self.n_keyframes()
+        T = np.zeros((max(n, 1), 4, 4)); w = np.zeros(max(n, 1), np.int32)
+        r = self._ck(self.L.pgs_facade_compose(self.h, T.ctypes.data_as(c_dp), w.ctypes.data_as(c_ip)))
+        return T[:r], w[:r]
+
+    def last_known_camerapose(self):
+        T = np.zeros((4, 4)); st = C.c_int64(0)
+        r = self.L.pgs_facade_last_known_camerapose(self.h, T.ctypes.data_as(c_dp), C.byref(st))
+        return r, T, st.value
+
+    def compose_timing(self):
+        a = C.c_double(0); b = C.c_double(0)
+        self._ck(self.L.pgs_facade_compose_timing(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- introspection
     def odom_terms(self):
         n = self.L.pgs_facade_n_odom_terms(self.h)

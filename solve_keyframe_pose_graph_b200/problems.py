@@ -32,8 +32,10 @@ def build_problem(config=3, fanout=None, **spec_overrides):
 
 def shard_problem(p, rank, world):
     """Node-range sharding: rank k owns nodes [kN/P, (k+1)N/P); an edge belongs to the shard of
-    its lower-index endpoint; poses are replicated (56 B/node), so remote endpoints need no exchange for
-    the sweep.  Returns a problem with only this rank's residual blocks."""
+    its lower-index endpoint.  The shard keeps only the poses its blocks touch — its own range plus the halo of
+    remote endpoints (at most the loop-gap bound above the range) — re-indexed locally in ascending global
+    order (`nodes` maps local -> global), so a rank uploads and reads ~N/P poses, not N.  The sweep needs no
+    exchange.  Returns a problem with only this rank's residual blocks."""
     if world == 1:
         return p
     N = p["N"]
@@ -48,6 +50,13 @@ def shard_problem(p, rank, world):
     rk = (p["rn"] >= lo) & (p["rn"] < hi)
     for k in ("rn", "rq", "rt", "rw"):
         s[k] = p[k][rk]
+    nodes = np.unique(np.concatenate([s["oc1"], s["oc2"], s["la"], s["lb"], s["rn"], np.arange(lo, hi)])).astype(np.int64)
+    g2l = np.full(N, -1, np.int64); g2l[nodes] = np.arange(len(nodes))
+    for k in ("oc1", "oc2", "la", "lb", "rn"):
+        s[k] = g2l[s[k]].astype(np.int32)
+    for k in ("q", "t", "gt_q", "gt_t"):
+        s[k] = np.ascontiguousarray(p[k][nodes])
+    s["N"] = len(nodes); s["nodes"] = nodes; s["n_halo"] = int(len(nodes) - (hi - lo))
     s["shard"] = (rank, world, lo, hi)
     return s
 
