@@ -43,6 +43,41 @@ template <int NACC> __global__ void __launch_bounds__(256) dmma_kernel(double* o
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// dependent-issue latency: one warp, NCH independent accumulator chains, clock64 around a long dependent sequence
+template <int NCH> __global__ void dmma_latency_kernel(double* out, long long* cyc, int iters, double x, double y) {
+  double c0[NCH], c1[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) { c0[i] = threadIdx.x + i; c1[i] = i; }
+  const double a = x + threadIdx.x * 1e-9, b = y;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) dmma(c0[i], c1[i], a, b);
+  }
+  const long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += c0[i] + c1[i];
+  out[threadIdx.x] = s;
+  if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void dfma_latency_kernel(double* out, long long* cyc, int iters, double x, double y) {
+  double acc = threadIdx.x;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) acc = fma(acc, x, y);
+  const long long t1 = clock64();
+  out[threadIdx.x] = acc;
+  if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void rsqrt_latency_kernel(double* out, long long* cyc, int iters, double x) {
+  double acc = x + threadIdx.x;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) acc = rsqrt(acc) + 1.5;
+  const long long t1 = clock64();
+  out[threadIdx.x] = acc;
+  if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+
 template <typename F> static double time_ms(F f, int reps) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   f(); CK(cudaDeviceSynchronize());
@@ -59,6 +94,23 @@ int main() {
   int nsm = 148; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
   double* out; CK(cudaMalloc((void**)&out, sizeof(double) * nsm * 8 * 256));
   const int iters = 4096;
+  {
+    long long* cyc; CK(cudaMalloc((void**)&cyc, 8)); long long h = 0;
+    dmma_latency_kernel<1><<<1, 32>>>(out, cyc, 2048, 0.999, 1e-3); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("DMMA dependent chain, 1 warp: %.1f cycles per mma\n", (double)h / 2048);
+    dmma_latency_kernel<2><<<1, 32>>>(out, cyc, 2048, 0.999, 1e-3); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("DMMA 2 chains, 1 warp: %.1f cycles per mma\n", (double)h / 4096);
+    dmma_latency_kernel<4><<<1, 32>>>(out, cyc, 2048, 0.999, 1e-3); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("DMMA 4 chains, 1 warp: %.1f cycles per mma\n", (double)h / 8192);
+    dmma_latency_kernel<8><<<1, 32>>>(out, cyc, 2048, 0.999, 1e-3); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("DMMA 8 chains, 1 warp: %.1f cycles per mma\n", (double)h / 16384);
+    dmma_latency_kernel<4><<<1, 256>>>(out, cyc, 2048, 0.999, 1e-3); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("DMMA 4 chains, 8 warps (one CTA): %.1f cycles per mma per warp\n", (double)h / 8192);
+    dfma_latency_kernel<<<1, 32>>>(out, cyc, 4096, 0.999, 1e-3); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("DFMA dependent chain: %.1f cycles per fma\n", (double)h / 4096);
+    rsqrt_latency_kernel<<<1, 32>>>(out, cyc, 4096, 2.0); CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("rsqrt(double)+add dependent chain: %.1f cycles per iteration\n", (double)h / 4096);
+  }
   for (int ctas : {1, 2, 4, 8}) {
     {
       const double ms = time_ms([&] { dfma_kernel<16><<<nsm * ctas, 256>>>(out, iters, 0.999, 1e-3); }, 5);
