@@ -185,7 +185,7 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier(); sampler.start()
     ms_step, ms_kernel, launches = S.time_sweep(mode=0, reps=args.steps, flush_l2=True)
-    barrier(); clocks = sampler.stop()
+    barrier()
     ms_warm, ms_kernel_warm, _ = S.time_sweep(mode=0, reps=args.steps, flush_l2=False)
     # practical ceiling: a pure streaming write of the same number of bytes, timed the same way
     ms_write = S.time_stream_write(min(bytes_local, 384 << 20), reps=args.steps, flush_l2=True)
@@ -201,7 +201,7 @@ def main():
     for _ in range(args.steps):
         cost = S.evaluate_from_host_ptr(q_pin.data_ptr(), t_pin.data_ptr(), sp)
     torch.cuda.synchronize(); e2e_s = (time.perf_counter() - t0) / args.steps
-    barrier()
+    barrier(); clocks = sampler.stop()   # sampled across both timed regions (device-resident steps and end-to-end steps)
 
     # ---- max over ranks
     tt = torch.tensor([ms_step, ms_kernel, e2e_s * 1e3, ms_warm], dtype=torch.float64, device="cuda")

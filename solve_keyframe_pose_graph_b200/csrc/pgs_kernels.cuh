@@ -131,17 +131,23 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 // store-bound kernel, and a static round-robin leaves the last partial round on a quarter of the SMs (measured
 // 7 % slower, tools/sweep_lab.cu).  Every tile writes its own cost partial, so the summation order — and with it
 // the cost, bit for bit — does not depend on which warp happened to take which tile.
+#ifndef PGS_SWEEP_MINB
+#define PGS_SWEEP_MINB 2
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256) sweep_kernel(SweepArgs A) {
+__global__ void __launch_bounds__(256, PGS_SWEEP_MINB) sweep_kernel(SweepArgs A) {
   const int lane = threadIdx.x & 31;
   const int To = (A.n_odom + TILE - 1) / TILE, Tl = (A.n_loop + TILE - 1) / TILE, Tr = (A.n_reg + TILE - 1) / TILE;
   const int T = To + Tl + Tr;
 
+  // the ticket for the NEXT tile is drawn before the current one is processed, so the atomic's round trip to L2
+  // overlaps the tile's loads and stores instead of preceding them
+  int ticket = 0;
+  if (lane == 0) ticket = (int)atomicAdd(A.sched, 1u);
   for (;;) {
-    int tile = 0;
-    if (lane == 0) tile = (int)atomicAdd(A.sched, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
+    const int tile = __shfl_sync(0xffffffffu, ticket, 0);
     if (tile >= T) break;
+    if (lane == 0) ticket = (int)atomicAdd(A.sched, 1u);
     double cost = 0.0;
     if (tile < To) {
       // ---- odometry edges: r = w e, J = w Je
