@@ -91,3 +91,25 @@ def test_solve_matches_oracle(solver, n, fan, nl, outl, seed):
     assert rot_angle_between(qs, qo).max() < 1e-4
     assert np.array_equal(S.switches() > 0.5, O.switches() > 0.5)
     assert np.abs(S.switches() - O.switches()).max() < 1e-5
+
+
+def test_evaluate_from_host_is_bit_identical_to_the_resident_path():
+    """pgs_evaluate_from_host (the end-to-end step bench.py times: host poses / switches in, cost out) must give the
+    same bits as loading the same values through set_nodes / set_switches, and leave complete r / J behind.
+    (Streaming the poses in node-range chunks to overlap the copy with the sweep was measured on two boxes and gains
+    nothing: the step is the 6 MB host-to-device copy, 300-550 us against a 50 us sweep.)"""
+    from solve_keyframe_pose_graph_b200 import problems
+    p = problems.build_problem(2, n_nodes=40000, n_loop=6000)
+    S = problems.load_into_solver(p)
+    c0 = S.evaluate(jac=False, residuals=False)["cost"]
+    s0 = np.full(len(p["la"]), 0.99)
+    assert S.evaluate_from_host(p["q"], p["t"], s0) == c0
+    rng = np.random.default_rng(0)
+    t2 = p["t"] + 1e-3 * rng.normal(size=p["t"].shape); s2 = s0 - 0.01 * rng.random(len(s0))
+    c2 = S.evaluate_from_host(p["q"], t2, s2)
+    T = problems.load_into_solver(dict(p, t=t2)); T.set_switches(s2)
+    e = T.evaluate()
+    assert c2 == e["cost"] and c2 != c0
+    r = S.evaluate()
+    assert np.array_equal(r["r_o"], e["r_o"]) and np.array_equal(r["J_l"], e["J_l"]) and np.array_equal(r["r_r"], e["r_r"])
+    S.close(); T.close()
