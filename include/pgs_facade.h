@@ -55,6 +55,22 @@ int32_t pgs_facade_n_keyframes(pgs_facade_handle h);                          /*
 int pgs_facade_last_known_camerapose(pgs_facade_handle h, double* T16, int64_t* stamp_ns);
 int pgs_facade_compose_timing(pgs_facade_handle h, double* ms_kernel, double* ms_total);
 
+/* On-disk formats of the reference (csrc/host/GraphIO.h): writes dir/log_posegraph.json
+ * (NodeDataManager::saveAsJSON, src/NodeDataManager.cpp:503-628), dir/log_optimized_poses.json
+ * (PoseGraphSLAM::saveAsJSON, src/PoseGraphSLAM.cpp:1111-1207) and, when pgs_facade_compose has run,
+ * dir/solved_posegraph.json (Composer::saveStateToDisk, src/Composer.cpp:990-1031, SolvedPoseGraph + KidnapTimestamps).
+ * Returns a bit mask of the files written (1 | 2 | 4) or < 0. */
+int pgs_facade_save_json(pgs_facade_handle h, const char* dir);
+/* NodeDataManager::loadFromJSON (src/NodeDataManager.cpp:631-754) into an empty facade, kidnap signals replayed. */
+int pgs_facade_load_posegraph_json(pgs_facade_handle h, const char* dir);
+/* format helpers (golden-vector tests): prettyprintMatrix4d (src/utils/PoseManipUtils.cpp:206-215) and the matrix
+ * string parsers (PoseManipUtils.cpp:272-295, RawFileIO.cpp:372-409).  Return the string length / 1 on success. */
+int pgs_io_prettyprint(const double* T16, char* out, int32_t cap);
+int pgs_io_mat_to_string(const double* T16, int32_t solved_posegraph_layout, char* out, int32_t cap);
+int pgs_io_string_to_mat(const char* s, double* T16);
+/* loads a solved_posegraph.json: n = number of keyframes (call with NULL outputs to size), poses [n][16], stamps, ids */
+int pgs_io_load_solved_posegraph(const char* json_file, double* T, int64_t* stamp_ns, int32_t* world_id, int32_t* set_id, int32_t cap);
+
 /* introspection of the graph-construction rules (parity tests against the oracle front-end) */
 int32_t pgs_facade_n_odom_terms(pgs_facade_handle h);
 int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w);

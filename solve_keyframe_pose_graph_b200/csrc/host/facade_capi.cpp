@@ -1,10 +1,12 @@
 // C view of the facade (include/pgs_facade.h).
 #include "../../../include/pgs_facade.h"
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 
 #include "Composer.h"
+#include "GraphIO.h"
 #include "PoseGraphSLAM.h"
 
 struct pgs_facade_s {
@@ -117,6 +119,59 @@ int pgs_facade_compose_timing(pgs_facade_handle h, double* ms_kernel, double* ms
   if (ms_kernel) *ms_kernel = h->composer->last_kernel_ms();
   if (ms_total) *ms_total = h->composer->last_total_ms();
   return PGS_OK;
+}
+int pgs_facade_save_json(pgs_facade_handle h, const char* dir) {
+  if (!h || !dir) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  int mask = 0;
+  if (!pgs::saveAsJSON(h->manager, dir, &h->err)) return PGS_ERR_STATE;
+  mask |= 1;
+  if (!pgs::saveAsJSON(*h->slam, h->manager, dir, &h->err)) return PGS_ERR_STATE;
+  mask |= 2;
+  if (h->composer && !h->composer->get_global_lmb().empty()) {
+    if (!pgs::saveSolvedPoseGraph(*h->composer, h->manager, dir, &h->err)) return PGS_ERR_STATE;
+    mask |= 4;
+  }
+  return mask;
+}
+int pgs_facade_load_posegraph_json(pgs_facade_handle h, const char* dir) {
+  if (!h || !dir) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  return pgs::loadFromJSON(h->manager, dir, {}, true, &h->err) ? PGS_OK : PGS_ERR_STATE;
+}
+static int copy_out(const std::string& s, char* out, int32_t cap) {
+  if (out && cap > 0) { const size_t n = std::min((size_t)cap - 1, s.size()); std::memcpy(out, s.data(), n); out[n] = 0; }
+  return (int)s.size();
+}
+int pgs_io_prettyprint(const double* T16, char* out, int32_t cap) {
+  if (!T16) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::Matrix4d T; std::memcpy(T.m, T16, 128);
+  return copy_out(pgs::prettyprintMatrix4d(T), out, cap);
+}
+int pgs_io_mat_to_string(const double* T16, int32_t solved_layout, char* out, int32_t cap) {
+  if (!T16) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::Matrix4d T; std::memcpy(T.m, T16, 128);
+  return copy_out(solved_layout ? pgs::mat_to_string(T, ", ", "\n") : pgs::mat_to_string(T), out, cap);
+}
+int pgs_io_string_to_mat(const char* s, double* T16) {
+  if (!s || !T16) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::Matrix4d T;
+  if (!pgs::string_to_mat(s, T)) return 0;
+  std::memcpy(T16, T.m, 128);
+  return 1;
+}
+int pgs_io_load_solved_posegraph(const char* file, double* T, int64_t* stamp_ns, int32_t* world_id, int32_t* set_id, int32_t cap) {
+  if (!file) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::SolvedPoseGraph g; std::string err;
+  if (!pgs::loadSolvedPoseGraph(file, &g, &err)) return PGS_ERR_STATE;
+  const int n = (int)g.w_T_c.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (T) std::memcpy(T + 16 * (size_t)i, g.w_T_c[i].m, 128);
+    if (stamp_ns) stamp_ns[i] = g.stamp_ns[i];
+    if (world_id) world_id[i] = g.world_id[i];
+    if (set_id) set_id[i] = g.set_id[i];
+  }
+  return n;
 }
 int32_t pgs_facade_n_odom_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->odometry_terms().size() : 0; }
 int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w) {

@@ -147,6 +147,13 @@ class Facade:
         self._ck(self.L.pgs_facade_compose_timing(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    # ---- on-disk formats (reference log_posegraph.json / log_optimized_poses.json / solved_posegraph.json)
+    def save_json(self, directory):
+        return self._ck(self.L.pgs_facade_save_json(self.h, str(directory).encode()))
+
+    def load_posegraph_json(self, directory):
+        self._ck(self.L.pgs_facade_load_posegraph_json(self.h, str(directory).encode()))
+
     # ---- introspection
     def odom_terms(self):
         n = self.L.pgs_facade_n_odom_terms(self.h)
@@ -179,3 +186,29 @@ class Facade:
         M = np.zeros((4, 4))
         ok = self.L.pgs_facade_pose_between_worlds(self.h, C.c_int32(m), C.c_int32(n), M.ctypes.data_as(c_dp))
         return M if ok else None
+
+
+def io_prettyprint(T):
+    T = np.ascontiguousarray(T, dtype=np.float64); buf = C.create_string_buffer(256)
+    lib().pgs_io_prettyprint(T.ctypes.data_as(c_dp), buf, C.c_int32(256))
+    return buf.value.decode()
+
+
+def io_mat_to_string(T, solved_layout=False):
+    T = np.ascontiguousarray(T, dtype=np.float64); buf = C.create_string_buffer(1024)
+    lib().pgs_io_mat_to_string(T.ctypes.data_as(c_dp), C.c_int32(int(solved_layout)), buf, C.c_int32(1024))
+    return buf.value.decode()
+
+
+def io_string_to_mat(s):
+    T = np.zeros((4, 4))
+    return T if lib().pgs_io_string_to_mat(s.encode(), T.ctypes.data_as(c_dp)) == 1 else None
+
+
+def io_load_solved_posegraph(path):
+    L = lib(); n = L.pgs_io_load_solved_posegraph(str(path).encode(), None, None, None, None, C.c_int32(0))
+    if n < 0:
+        raise PgsError(f"cannot load {path}")
+    T = np.zeros((max(n, 1), 4, 4)); st = np.zeros(max(n, 1), np.int64); w = np.zeros(max(n, 1), np.int32); sid = np.zeros(max(n, 1), np.int32)
+    L.pgs_io_load_solved_posegraph(str(path).encode(), T.ctypes.data_as(c_dp), st.ctypes.data_as(C.c_void_p), w.ctypes.data_as(c_ip), sid.ctypes.data_as(c_ip), C.c_int32(n))
+    return T[:n], st[:n], w[:n], sid[:n]

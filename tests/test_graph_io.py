@@ -1,0 +1,75 @@
+"""On-disk formats of the reference (csrc/host/GraphIO.{h,cpp}).  CPU only (dry-run facade).
+Golden vector: the sample of solved_posegraph.json that the reference quotes in its own source
+(src/NodeDataManager.cpp:892-908, 955-995) — real output of the reference — pins the matrix string format, the parser,
+prettyprintMatrix4d / R2ypr and the layout.  Round trips pin the writers against the readers."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frontend, pgo
+from solve_keyframe_pose_graph_b200 import facade, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_solved_posegraph_sample.json")
+
+
+def test_reference_sample_parses_prints_and_reprints_identically():
+    ref = json.load(open(GOLD))
+    T, st, w, sid = facade.io_load_solved_posegraph(GOLD)
+    assert len(T) == 3 and list(st) == [n["stampNSec"] for n in ref["SolvedPoseGraph"]] and list(w) == [0, 0, 0] and list(sid) == [0, 0, 0]
+    for i, node in enumerate(ref["SolvedPoseGraph"]):
+        M = np.array([[float(x) for x in row.split(",")] for row in node["w_T_c"]["data"].split("\n")])
+        assert np.array_equal(T[i], M)                                                    # parser (RawFileIO.cpp:372-409)
+        assert facade.io_prettyprint(T[i]) == node["w_T_c"]["data_pretty"]               # R2ypr + %4.3f (PoseManipUtils.cpp:143-158,206-215)
+        assert facade.io_mat_to_string(T[i], solved_layout=True) == node["w_T_c"]["data"]   # Eigen FullPrecision = 16 significant digits
+        assert np.array_equal(facade.io_string_to_mat(facade.io_mat_to_string(T[i])), M)    # the ',' / ';' layout of the log files
+        # the oracle's R2ypr agrees with the reference's printed angles
+        ypr = pgo.r2ypr_deg(M)
+        assert node["w_T_c"]["data_pretty"].startswith(":YPR(deg)=(%4.3f,%4.3f,%4.3f)" % tuple(ypr))
+    assert facade.io_string_to_mat("1,2,3;4,5,6") is None
+
+
+def test_log_posegraph_round_trip_reproduces_the_session(tmp_path):
+    g = synth.generate_config(4, n_nodes=60, n_interworld=12)
+    F = facade.Facade(odom_fanout=3, dry_run=True); F.ingest(g)
+    assert F.solve_once()
+    assert F.save_json(tmp_path) == 3                                                   # no composer pass in a dry run
+    J = json.load(open(tmp_path / "log_posegraph.json"))
+    assert J["meta_data"]["getNodeLen"] == g["N"] == len(J["nodes"]) and J["meta_data"]["getEdgeLen"] == len(g["la"]) == len(J["loopedges"])
+    assert [n["world_id"] for n in J["nodes"]] == [F.which_world(s) for s in g["stamps"]]
+    assert len(J["kidnap_info"]) == 3 and [w["nodeidx_of_world_i_ended"] for w in J["world_info"]] == [F.world_end(w) for w in range(4)]
+    e0 = J["loopedges"][0]
+    assert (e0["idx0"], e0["idx1"]) == (int(g["la"][0]), int(g["lb"][0])) and e0["code"] in (1, 2) and e0["weight"] == g["lw"][0]
+    assert sorted(J["nodes"][0].keys()) == ["cov", "idx", "timestamp", "wTc", "wTc_pretty", "world_id"]        # the reference's keys (:517-536)
+    O = json.load(open(tmp_path / "log_optimized_poses.json"))
+    assert O["meta_data"]["nNodes"] == g["N"] and len(O["PoseGraphSLAM_loopedgeinfo"]) == len(g["la"])
+    assert "switching_var_after_opt" in O["PoseGraphSLAM_loopedgeinfo"][0]
+    # a fresh facade loaded from the file behaves like the original one
+    G = facade.Facade(odom_fanout=3, dry_run=True); G.load_posegraph_json(tmp_path)
+    assert G.n_keyframes() == g["N"] and G.n_worlds() == 4
+    assert [G.which_world(s) for s in g["stamps"]] == [F.which_world(s) for s in g["stamps"]]
+    G.n_loop = len(g["la"])
+    assert G.solve_once()
+    assert [G.world_setid(w) for w in range(4)] == [F.world_setid(w) for w in range(4)]
+    a, b = F.odom_terms(), G.odom_terms()
+    assert np.array_equal(a["u"], b["u"]) and np.array_equal(a["umf"], b["umf"]) and np.allclose(a["w"], b["w"], rtol=1e-12)
+    assert np.allclose(a["t"], b["t"], atol=1e-12)                                      # 16 significant digits survive the text round trip
+    qa, ta = F.poses(); qb, tb = G.poses()
+    assert np.allclose(ta, tb, atol=1e-9)
+    F.close(); G.close()
+
+
+@pytest.mark.gpu
+def test_solved_posegraph_written_after_a_device_compose(tmp_path):
+    g = synth.generate_config(4, n_nodes=80, n_worlds=3, n_interworld=10)
+    F = facade.Facade(odom_fanout=3); F.ingest(g)
+    assert F.solve_once()
+    T, wid = F.compose()
+    assert F.save_json(tmp_path) == 7
+    T2, st, w2, sid = facade.io_load_solved_posegraph(tmp_path / "solved_posegraph.json")
+    assert np.allclose(T2, T, rtol=0, atol=1e-12 * max(1.0, np.abs(T).max())) and np.array_equal(w2, wid) and np.array_equal(st, g["stamps"])
+    J = json.load(open(tmp_path / "solved_posegraph.json"))
+    assert sorted(J["SolvedPoseGraph"][0].keys()) == ["seq", "setID_of_worldID", "stampNSec", "w_T_c", "worldID"]
+    assert len(J["KidnapTimestamps"]["kidnap_starts"]) == 2 == len(J["KidnapTimestamps"]["kidnap_ends"])
+    F.close()
