@@ -1,0 +1,96 @@
+"""GPU parity on the inputs the reference's code can actually produce at the edges of the path: no loop edges at
+all, keyframes that appear in no residual block (dead-zone nodes: Ceres drops their parameter blocks), several
+residual blocks on the same node pair (two loop closures between the same keyframes; a loop closure on top of an
+odometry pair), loop edges given in both index orders, a graph shorter than one factor panel, and bad arguments
+through the C-ABI.  Checker: the oracle, same tolerances as test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import solve_keyframe_pose_graph_b200 as pgs
+from util_graphs import load_oracle, load_pgs, random_graph, rot_angle_between
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve_both(g, **opt):
+    O = load_oracle(g); S = load_pgs(g, **opt)
+    so = O.solve(); ss = S.solve()
+    assert ss["termination"] == so["termination"] and len(ss["iterations"]) == len(so["iterations"])
+    for a, b in zip(ss["iterations"], so["iterations"]):
+        assert a["step_is_successful"] == b["step_is_successful"]
+    assert abs(ss["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"] + 1e-18   # the floor: exactly consistent graphs end at rounding-level cost
+    (qo, to), (qs, ts) = O.poses(), S.poses()
+    assert np.abs(ts - to).max() < 1e-5 and rot_angle_between(qs, qo).max() < 1e-4
+    if len(g["la"]):
+        assert np.array_equal(S.switches() > 0.5, O.switches() > 0.5)
+    return S, O
+
+
+@pytest.mark.parametrize("solver", [pgs.capi.SKYLINE_CHOLESKY, pgs.capi.BLOCK_PCG])
+def test_odometry_only_graph(solver):
+    g = random_graph(120, 3, 0, seed=21)
+    g["t"] = g["t"] + 0.05 * np.random.default_rng(21).normal(size=g["t"].shape)   # start away from the (exactly consistent) odometry solution
+    S, _ = _solve_both(g, linear_solver=solver, pcg_tolerance=1e-12)
+    S.close()
+
+
+def test_graph_shorter_than_one_panel_and_single_edge():
+    for n, nl in ((5, 0), (2, 0), (12, 1)):                       # 96-scalar panels = 16 nodes
+        g = random_graph(max(n, 12) if nl else n, 1, nl, seed=22) if n >= 12 else random_graph(12, 1, 0, seed=22)
+        if n < 12:                                                 # cut the walk down to n nodes
+            keep = (g["oc1"] < n) & (g["oc2"] < n)
+            g = dict(g, N=n, q=g["q"][:n], t=g["t"][:n], **{k: g[k][keep] for k in ("oc1", "oc2", "oq", "ot", "ow")})
+        S, _ = _solve_both(g)
+        S.close()
+
+
+def test_nodes_in_no_residual_block_keep_their_values():
+    g = random_graph(90, 3, 10, seed=23)
+    dead = np.arange(40, 45)                                       # a dead zone: no odometry, no loop edge touches these
+    ko = ~(np.isin(g["oc1"], dead) | np.isin(g["oc2"], dead)); kl = ~(np.isin(g["la"], dead) | np.isin(g["lb"], dead))
+    g = dict(g, **{k: g[k][ko] for k in ("oc1", "oc2", "oq", "ot", "ow")}, **{k: g[k][kl] for k in ("la", "lb", "lq", "lt", "lw", "lout")})
+    # the second component needs its own anchor, as the reference gives every set root (PoseGraphSLAM.cpp:1828-1849)
+    g["rn"] = np.array([0, 45], np.int32); g["rq"] = g["q"][[0, 45]].copy(); g["rt"] = g["t"][[0, 45]].copy(); g["rw"] = np.array([1.9, 1.9])
+    S, O = _solve_both(g)
+    q, t = S.poses()
+    assert np.array_equal(q[dead], g["q"][dead]) and np.array_equal(t[dead], g["t"][dead])     # untouched, bit for bit
+    S.close()
+
+
+def test_parallel_blocks_on_one_node_pair_and_both_loop_orientations():
+    g = random_graph(80, 2, 8, seed=24)
+    # duplicate two loop edges (same pair, slightly different observation), add a loop closure on an odometry pair,
+    # and give one loop edge with a < b (the reference accepts either order, NodeDataManager.cpp:168-170)
+    la = list(g["la"]) + [g["la"][0], g["la"][1], 30, 10]
+    lb = list(g["lb"]) + [g["lb"][0], g["lb"][1], 29, 50]
+    rng = np.random.default_rng(5)
+    def rel(a, b):   # b_T_a from the ground truth
+        from util_graphs import _compose, _inv
+        return _compose(*_inv(g["gt_q"][b], g["gt_t"][b]), g["gt_q"][a], g["gt_t"][a])
+    extra = [rel(la[i], lb[i]) for i in range(len(g["la"]), len(la))]
+    g = dict(g, la=np.array(la, np.int32), lb=np.array(lb, np.int32),
+             lq=np.vstack([g["lq"]] + [np.array(e[0])[None] for e in extra]), lt=np.vstack([g["lt"]] + [(np.array(e[1]) + 1e-3 * rng.normal(size=3))[None] for e in extra]),
+             lw=np.concatenate([g["lw"], np.ones(4)]), lout=np.concatenate([g["lout"], np.zeros(4, bool)]))
+    S, O = _solve_both(g)
+    A = S.assemble()
+    pairs = set(zip(A["pair_hi"].tolist(), A["pair_lo"].tolist()))
+    assert len(pairs) == len(A["pair_hi"])                          # one Hessian block per distinct pair, however many blocks share it
+    assert (50, 10) in pairs and (30, 29) in pairs
+    S.close()
+
+
+def test_c_abi_rejects_bad_arguments_without_crashing():
+    S = pgs.PoseGraphSolver()
+    q = np.tile([0, 0, 0, 1.0], (4, 1)); t = np.zeros((4, 3))
+    S.set_nodes(q, t)
+    with pytest.raises(pgs.PgsError):
+        S.add_odom_edges([0], [7], q[:1], t[:1], [1.0])             # node index out of range
+    with pytest.raises(pgs.PgsError):
+        S.add_loop_edges([2], [2], q[:1], t[:1], [1.0])             # a == b
+    with pytest.raises(pgs.PgsError):
+        S.set_regularizers([9], q[:1], t[:1], [1.0])
+    s = S.solve()                                                   # no residual blocks at all: cost 0, converges at iteration 0
+    assert s["initial_cost"] == 0.0 and s["termination"] == "CONVERGENCE" and len(s["iterations"]) == 1
+    qq, tt = S.poses()
+    assert np.array_equal(qq, q) and np.array_equal(tt, t)
+    S.close()
