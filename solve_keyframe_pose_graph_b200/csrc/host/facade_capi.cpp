@@ -8,6 +8,7 @@
 #include "Composer.h"
 #include "GraphIO.h"
 #include "PoseGraphSLAM.h"
+#include "RosShim.h"
 
 struct pgs_facade_s {
   pgs::NodeDataManager manager;
@@ -63,6 +64,29 @@ int pgs_facade_kidnap_indicator(pgs_facade_handle h, int64_t stamp, int32_t kidn
 int pgs_facade_add_odometry_edge(pgs_facade_handle h, int32_t a, int32_t b, const double* q, const double* t, double w) {
   if (!h || !q || !t) return PGS_ERR_INVALID_ARGUMENT;
   return h->slam->addOdometryEdge(a, b, pgs::raw_xyzw_to_mat(q, t), w) ? PGS_OK : PGS_ERR_INVALID_ARGUMENT;
+}
+static pgs::ros_shim::Pose make_pose(const double* p, const double* q) {
+  pgs::ros_shim::Pose P; P.position.x = p[0]; P.position.y = p[1]; P.position.z = p[2];
+  P.orientation.x = q[0]; P.orientation.y = q[1]; P.orientation.z = q[2]; P.orientation.w = q[3];
+  return P;
+}
+int pgs_facade_camera_pose_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const double* p, const double* q) {
+  if (!h || !p || !q) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::ros_shim::Odometry msg; msg.header.stamp.sec = sec; msg.header.stamp.nsec = nsec; msg.pose.pose = make_pose(p, q);
+  pgs::ros_shim::camera_pose_callback(h->manager, msg);
+  return PGS_OK;
+}
+int pgs_facade_loopclosure_pose_callback(pgs_facade_handle h, uint32_t sec0, uint32_t nsec0, uint32_t sec1, uint32_t nsec1, const double* p, const double* q, float weight,
+                                         const char* description) {
+  if (!h || !p || !q) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::ros_shim::LoopEdge msg; msg.timestamp0.sec = sec0; msg.timestamp0.nsec = nsec0; msg.timestamp1.sec = sec1; msg.timestamp1.nsec = nsec1;
+  msg.pose_1T0 = make_pose(p, q); msg.weight = weight; msg.description = description ? description : "";
+  return pgs::ros_shim::loopclosure_pose_callback(h->manager, msg) ? 1 : 0;
+}
+int pgs_facade_rcvd_kidnap_indicator_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const char* frame_id) {
+  if (!h || !frame_id) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::ros_shim::Header hd; hd.stamp.sec = sec; hd.stamp.nsec = nsec; hd.frame_id = frame_id;
+  return pgs::ros_shim::rcvd_kidnap_indicator_callback(h->manager, hd) ? PGS_OK : PGS_ERR_STATE;
 }
 int pgs_facade_solve_once(pgs_facade_handle h, int32_t force) {
   if (!h) return PGS_ERR_INVALID_ARGUMENT;

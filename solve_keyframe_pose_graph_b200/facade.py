@@ -79,6 +79,21 @@ class Facade:
         q, qp = _d(q); t, tp = _d(t)
         self._ck(self.L.pgs_facade_add_odometry_edge(self.h, C.c_int32(a), C.c_int32(b), qp, tp, C.c_double(w)))
 
+    # ---- ROS-message entry points (reference callback names, csrc/host/RosShim.h)
+    def camera_pose_callback(self, stamp_ns, position, orientation_xyzw):
+        p, pp = _d(position); q, qp = _d(orientation_xyzw)
+        self._ck(self.L.pgs_facade_camera_pose_callback(self.h, C.c_uint32(int(stamp_ns) // 10**9), C.c_uint32(int(stamp_ns) % 10**9), pp, qp))
+
+    def loopclosure_pose_callback(self, stamp0_ns, stamp1_ns, position, orientation_xyzw, weight=1.0, description=""):
+        p, pp = _d(position); q, qp = _d(orientation_xyzw)
+        r = self._ck(self.L.pgs_facade_loopclosure_pose_callback(self.h, C.c_uint32(int(stamp0_ns) // 10**9), C.c_uint32(int(stamp0_ns) % 10**9),
+                                                                  C.c_uint32(int(stamp1_ns) // 10**9), C.c_uint32(int(stamp1_ns) % 10**9), pp, qp, C.c_float(weight), description.encode()))
+        self.n_loop += r
+        return bool(r)
+
+    def rcvd_kidnap_indicator_callback(self, stamp_ns, frame_id):
+        return self.L.pgs_facade_rcvd_kidnap_indicator_callback(self.h, C.c_uint32(int(stamp_ns) // 10**9), C.c_uint32(int(stamp_ns) % 10**9), frame_id.encode()) == 0
+
     def ingest(self, g):
         """Feed a generated graph (synth.generate) in time order: nodes, kidnap signals, then loop edges."""
         ev = sorted([(int(s), 1) for s in g["k0"]] + [(int(s), 0) for s in g["k1"]])

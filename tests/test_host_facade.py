@@ -169,3 +169,27 @@ def test_generator_is_deterministic_and_matches_baseline_counts():
     # odometry drift is small per step: consecutive relative translation ~ 1 m
     step = np.linalg.norm(np.diff(g["t"], axis=0), axis=1)
     assert abs(step.mean() - 1.0) < 0.01
+
+
+def test_ros_message_callbacks_build_the_same_session_as_the_plain_ingest():
+    # nav_msgs/Odometry, LoopEdge.msg and the kidnap Header routed through the reference's callback names
+    g = synth.generate_config(4, n_nodes=40, n_worlds=3, n_interworld=8)
+    A = facade.Facade(odom_fanout=3, dry_run=True); A.ingest(g)
+    B = facade.Facade(odom_fanout=3, dry_run=True)
+    ev = sorted([(int(s), "kidnapped") for s in g["k0"]] + [(int(s), "unkidnapped") for s in g["k1"]])
+    k = 0
+    for i in range(g["N"]):
+        while k < len(ev) and ev[k][0] < g["stamps"][i]:
+            assert B.rcvd_kidnap_indicator_callback(*ev[k]); k += 1
+        B.camera_pose_callback(g["stamps"][i], g["t"][i], g["q"][i])
+    assert not B.rcvd_kidnap_indicator_callback(g["stamps"][-1] + 5, "lost")          # the reference exits on anything else (:789-791)
+    for e in range(len(g["la"])):                                                       # timestamp0 -> a, timestamp1 -> b, pose_1T0 = b_T_a
+        assert B.loopclosure_pose_callback(g["stamps"][g["la"][e]], g["stamps"][g["lb"][e]], g["lt"][e], g["lq"][e], float(g["lw"][e]), "t")
+    assert not B.loopclosure_pose_callback(g["stamps"][3] + 5 * 10**6, g["stamps"][1], g["lt"][0], g["lq"][0])   # no keyframe within 1 ms: dropped
+    assert [A.which_world(s) for s in g["stamps"]] == [B.which_world(s) for s in g["stamps"]]
+    assert A.solve_once() and B.solve_once()
+    a, b = A.odom_terms(), B.odom_terms()
+    assert np.array_equal(a["u"], b["u"]) and np.allclose(a["t"], b["t"], atol=1e-12) and np.allclose(a["w"], b["w"], rtol=1e-6)
+    (qa, ta), (qb, tb) = A.poses(), B.poses()
+    assert np.allclose(ta, tb, atol=1e-9) and [A.world_setid(w) for w in range(3)] == [B.world_setid(w) for w in range(3)]
+    A.close(); B.close()
