@@ -64,9 +64,9 @@ int pgs_facade_compose_timing(pgs_facade_handle h, double* ms_kernel, double* ms
 
 /* On-disk formats of the reference (csrc/host/GraphIO.h): writes dir/log_posegraph.json
  * (NodeDataManager::saveAsJSON, src/NodeDataManager.cpp:503-628), dir/log_optimized_poses.json
- * (PoseGraphSLAM::saveAsJSON, src/PoseGraphSLAM.cpp:1111-1207) and, when pgs_facade_compose has run,
- * dir/solved_posegraph.json (Composer::saveStateToDisk, src/Composer.cpp:990-1031, SolvedPoseGraph + KidnapTimestamps).
- * Returns a bit mask of the files written (1 | 2 | 4) or < 0. */
+ * (PoseGraphSLAM::saveAsJSON, src/PoseGraphSLAM.cpp:1111-1207) and dir/solved_posegraph.json (Composer::saveStateToDisk,
+ * src/Composer.cpp:990-1031: SolvedPoseGraph — empty until pgs_facade_compose has run — KidnapTimestamps, WorldsData).
+ * Returns 1 | 2, plus 4 when SolvedPoseGraph holds the assembled poses, or < 0. */
 int pgs_facade_save_json(pgs_facade_handle h, const char* dir);
 /* NodeDataManager::loadFromJSON (src/NodeDataManager.cpp:631-754) into an empty facade, kidnap signals replayed. */
 int pgs_facade_load_posegraph_json(pgs_facade_handle h, const char* dir);
@@ -75,6 +75,9 @@ int pgs_facade_load_posegraph_json(pgs_facade_handle h, const char* dir);
 int pgs_io_prettyprint(const double* T16, char* out, int32_t cap);
 int pgs_io_mat_to_string(const double* T16, int32_t solved_posegraph_layout, char* out, int32_t cap);
 int pgs_io_string_to_mat(const char* s, double* T16);
+/* Worlds::loadStateFromDisk (src/Worlds.cpp:499-640) from the "WorldsData" object of a solved_posegraph.json into an
+ * EMPTY facade (before any keyframe): relative poses, world stamps, union-find op-log replayed. */
+int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* solved_posegraph_json);
 /* loads a solved_posegraph.json: n = number of keyframes (call with NULL outputs to size), poses [n][16], stamps, ids */
 int pgs_io_load_solved_posegraph(const char* json_file, double* T, int64_t* stamp_ns, int32_t* world_id, int32_t* set_id, int32_t cap);
 

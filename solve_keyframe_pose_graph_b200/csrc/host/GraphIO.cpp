@@ -181,8 +181,8 @@ bool saveAsJSON(const PoseGraphSLAM& slam, const NodeDataManager& m, const std::
 }
 
 // ------------------------------------------------------------------ solved_posegraph.json (Composer.cpp:990-1031)
-bool saveSolvedPoseGraph(const Composer& composer, const NodeDataManager& m, const std::string& dir, std::string* err) {
-  const std::vector<Matrix4d> lmb = composer.get_global_lmb();
+bool saveSolvedPoseGraph(const Composer* composer, const NodeDataManager& m, const std::string& dir, std::string* err) {
+  const std::vector<Matrix4d> lmb = composer ? composer->get_global_lmb() : std::vector<Matrix4d>();   // no pass yet: empty list, as global_lmb is
   Json obj;
   obj["SolvedPoseGraph"] = Json::array();
   for (size_t i = 0; i < lmb.size(); ++i) {
@@ -202,6 +202,7 @@ bool saveSolvedPoseGraph(const Composer& composer, const NodeDataManager& m, con
   for (int i = 0; i < nk_started; ++i) { Json a; a["stampNSec"] = Json((int64_t)m.stamp_of_kidnap_i_started(i)); ks.push_back(a); }
   for (int i = 0; i < m.n_kidnaps(); ++i) { Json b; b["stampNSec"] = Json((int64_t)m.stamp_of_kidnap_i_ended(i)); ke.push_back(b); }
   obj["KidnapTimestamps"]["kidnap_starts"] = ks; obj["KidnapTimestamps"]["kidnap_ends"] = ke;
+  obj["WorldsData"] = m.getWorldsConstPtr()->saveStateToDisk();                   // Composer.cpp:1031
   return write_file(dir + "/solved_posegraph.json", obj.dump(4), err);
 }
 

@@ -2,9 +2,8 @@
 // replayed through this solver and results written here can be read by the reference's tooling:
 //   log_posegraph.json        NodeDataManager::saveAsJSON / loadFromJSON   (src/NodeDataManager.cpp:503-754)
 //   log_optimized_poses.json  PoseGraphSLAM::saveAsJSON                     (src/PoseGraphSLAM.cpp:1111-1207)
-//   solved_posegraph.json     Composer::saveStateToDisk, the SolvedPoseGraph and KidnapTimestamps sections
-//                             (src/Composer.cpp:952-1106, src/NodeDataManager.cpp:854-888); the WorldsData section
-//                             (Worlds::saveStateToDisk) is not written.
+//   solved_posegraph.json     Composer::saveStateToDisk: SolvedPoseGraph, KidnapTimestamps and WorldsData
+//                             (src/Composer.cpp:952-1106, src/NodeDataManager.cpp:854-888, src/Worlds.cpp:442-497)
 // Matrices are strings: "a,b,c,d;e,f,g,h;..." (Eigen IOFormat(FullPrecision, DontAlignCols, ",", ";")) in the two
 // log files, "a, b, c, d\n..." inside {"rows","cols","data"} in solved_posegraph.json (src/utils/RawFileIO.h:95-106).
 #pragma once
@@ -33,7 +32,7 @@ bool saveAsJSON(const NodeDataManager& manager, const std::string& base_path, st
 bool loadFromJSON(NodeDataManager& manager, const std::string& base_path, const std::vector<bool>& edge_mask = {}, bool restore_kidnaps = true,
                   std::string* err = nullptr);
 bool saveAsJSON(const PoseGraphSLAM& slam, const NodeDataManager& manager, const std::string& base_path, std::string* err = nullptr);   // -> log_optimized_poses.json
-bool saveSolvedPoseGraph(const Composer& composer, const NodeDataManager& manager, const std::string& save_dir_path, std::string* err = nullptr);   // -> solved_posegraph.json
+bool saveSolvedPoseGraph(const Composer* composer, const NodeDataManager& manager, const std::string& save_dir_path, std::string* err = nullptr);   // -> solved_posegraph.json (composer may be null)
 struct SolvedPoseGraph { std::vector<Matrix4d> w_T_c; std::vector<int64_t> stamp_ns; std::vector<int> world_id, set_id; std::vector<int64_t> kidnap_starts, kidnap_ends; };
 bool loadSolvedPoseGraph(const std::string& json_file, SolvedPoseGraph* out, std::string* err = nullptr);
 

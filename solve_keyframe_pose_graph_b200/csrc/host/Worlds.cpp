@@ -1,6 +1,7 @@
 #include "Worlds.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <deque>
 
 namespace pgs {
@@ -110,5 +111,83 @@ int Worlds::find_setID_of_world_i(int i) const {
 int Worlds::n_worlds() const { std::lock_guard<std::mutex> lk(mutex_world); return disjoint_set.element_count(); }
 int Worlds::n_sets() const { std::lock_guard<std::mutex> lk(mutex_world); return disjoint_set.set_count(); }
 std::string Worlds::disjoint_set_log() const { std::lock_guard<std::mutex> lk(mutex_world); return log_; }
+
+// ---------------------------------------------------------------- state file (Worlds.cpp:442-640)
+static std::string mat_rows_string(const Matrix4d& M) {   // RawFileIO::eigen_matrix_to_json: ", " between coefficients, "\n" between rows
+  std::string out; char b[40];
+  for (int r = 0; r < 4; ++r) { for (int c = 0; c < 4; ++c) { snprintf(b, sizeof(b), "%.16g", M(r, c)); out += b; if (c < 3) out += ", "; } if (r < 3) out += "\n"; }
+  return out;
+}
+static bool parse_mat_rows(const std::string& s, Matrix4d& M) {
+  std::vector<double> v; std::string tok;
+  auto flush = [&]() -> bool { if (tok.empty()) return true; try { v.push_back(std::stod(tok)); } catch (...) { return false; } tok.clear(); return true; };
+  for (char c : s) { if (c == ',' || c == ';' || c == '\n') { if (!flush()) return false; } else if (c != ' ' && c != '\t' && c != '\r') tok.push_back(c); }
+  if (!flush() || v.size() != 16) return false;
+  for (int i = 0; i < 16; ++i) M.m[i] = v[i];
+  return true;
+}
+
+Json Worlds::saveStateToDisk() const {
+  std::lock_guard<std::mutex> lk(mutex_world);
+  Json obb;
+  obb["rel_pose_between_worlds__wb_T_wa"] = Json::array();
+  for (const auto& kv : rel_pose) {
+    Json item;
+    item["node_b"] = Json(kv.first.first); item["node_a"] = Json(kv.first.second);
+    item["wb_T_wa"]["rows"] = Json(4); item["wb_T_wa"]["cols"] = Json(4);
+    item["wb_T_wa"]["data"] = Json(mat_rows_string(kv.second));
+    double ypr[3]; R2ypr(kv.second, ypr); char b[200];
+    snprintf(b, sizeof(b), ":YPR(deg)=(%4.3f,%4.3f,%4.3f)  :TxTyTz=(%4.3f,%4.3f,%4.3f)", ypr[0], ypr[1], ypr[2], kv.second(0, 3), kv.second(1, 3), kv.second(2, 3));
+    item["wb_T_wa"]["data_pretty"] = Json(std::string(b));
+    auto info = rel_pose_info.find(kv.first);
+    item["info_wb_T_wa"] = Json(info == rel_pose_info.end() ? std::string() : info->second);
+    obb["rel_pose_between_worlds__wb_T_wa"].push_back(item);
+  }
+  Json A = Json::array(), B = Json::array();
+  for (int64_t t : vec_world_starts) { Json a; a["stampNSec"] = Json(t); A.push_back(a); }
+  for (int64_t t : vec_world_ends) { Json b; b["stampNSec"] = Json(t); B.push_back(b); }
+  obb["vec_world_starts"] = A; obb["vec_world_ends"] = B;
+  obb["disjoint_set"]["debug_string"] = Json(std::string());
+  obb["disjoint_set"]["log_string"] = Json(log_);
+  return obb;
+}
+
+bool Worlds::loadStateFromDisk(const Json& o, std::string* err) {
+  auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
+  std::lock_guard<std::mutex> lk(mutex_world);
+  if (disjoint_set.element_count() != 0 || !rel_pose.empty()) return fail("Worlds::loadStateFromDisk: not empty");
+  const Json& rp = o.at("rel_pose_between_worlds__wb_T_wa");
+  for (size_t i = 0; i < rp.size(); ++i) {
+    Matrix4d T;
+    if (!parse_mat_rows(rp[i].at("wb_T_wa").at("data").as_string(), T)) return fail("Worlds::loadStateFromDisk: bad wb_T_wa");
+    const std::pair<int, int> p((int)rp[i].at("node_b").as_int(), (int)rp[i].at("node_a").as_int());
+    rel_pose[p] = T; rel_pose_info[p] = rp[i].at("info_wb_T_wa").as_string();
+  }
+  // replay the union-find op-log: "add_element:0;add_element:1;union_sets:1,0;" (Worlds.cpp:549-620)
+  const std::string log = o.at("disjoint_set").at("log_string").as_string();
+  size_t p0 = 0;
+  while (p0 < log.size()) {
+    size_t p1 = log.find(';', p0); if (p1 == std::string::npos) p1 = log.size();
+    const std::string cmd = log.substr(p0, p1 - p0); p0 = p1 + 1;
+    if (cmd.size() < 4) break;
+    const size_t colon = cmd.find(':');
+    if (colon == std::string::npos) return fail("Worlds::loadStateFromDisk: bad op-log entry '" + cmd + "'");
+    const std::string op = cmd.substr(0, colon), arg = cmd.substr(colon + 1);
+    try {
+      if (op == "add_element") disjoint_set.add_element(std::stoi(arg));
+      else if (op == "union_sets") {
+        const size_t comma = arg.find(',');
+        if (comma == std::string::npos) return fail("Worlds::loadStateFromDisk: bad union_sets operands");
+        const int x = std::stoi(arg.substr(0, comma)), y = std::stoi(arg.substr(comma + 1));
+        disjoint_set.union_sets(std::max(x, y), std::min(x, y));
+      } else return fail("Worlds::loadStateFromDisk: unknown op '" + op + "'");
+    } catch (...) { return fail("Worlds::loadStateFromDisk: bad number in op-log"); }
+  }
+  log_ = log;
+  const Json& ws = o.at("vec_world_starts"); const Json& we = o.at("vec_world_ends");
+  for (size_t i = 0; i < ws.size(); ++i) vec_world_starts.push_back(ws[i].at("stampNSec").as_int());
+  for (size_t i = 0; i < we.size(); ++i) vec_world_ends.push_back(we[i].at("stampNSec").as_int());
+  return true;
+}
 
 }  // namespace pgs

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "DisjointSet.h"
+#include "Json.h"
 #include "pose_math.h"
 
 namespace pgs {
@@ -30,6 +31,10 @@ class Worlds {
   int n_worlds() const;
   int n_sets() const;
   std::string disjoint_set_log() const;   // "add_element:0;union_sets:1,0;" op-log (Worlds.cpp:164-170,230-240)
+  // The "WorldsData" object of solved_posegraph.json (Worlds.cpp:442-497): relative poses with their info strings,
+  // world start / end stamps and the union-find op-log, which loadStateFromDisk replays (Worlds.cpp:499-640).
+  Json saveStateToDisk() const;
+  bool loadStateFromDisk(const Json& obj, std::string* err = nullptr);   // into an empty Worlds
 
  private:
   mutable std::mutex mutex_world;

@@ -2,6 +2,7 @@
 #include "../../../include/pgs_facade.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -152,16 +153,26 @@ int pgs_facade_save_json(pgs_facade_handle h, const char* dir) {
   mask |= 1;
   if (!pgs::saveAsJSON(*h->slam, h->manager, dir, &h->err)) return PGS_ERR_STATE;
   mask |= 2;
-  if (h->composer && !h->composer->get_global_lmb().empty()) {
-    if (!pgs::saveSolvedPoseGraph(*h->composer, h->manager, dir, &h->err)) return PGS_ERR_STATE;
-    mask |= 4;
-  }
+  if (!pgs::saveSolvedPoseGraph(h->composer, h->manager, dir, &h->err)) return PGS_ERR_STATE;   // always written: KidnapTimestamps + WorldsData
+  if (h->composer && !h->composer->get_global_lmb().empty()) mask |= 4;                          // ... with the assembled poses when a pass has run
   return mask;
 }
 int pgs_facade_load_posegraph_json(pgs_facade_handle h, const char* dir) {
   if (!h || !dir) return PGS_ERR_INVALID_ARGUMENT;
   h->err.clear();
   return pgs::loadFromJSON(h->manager, dir, {}, true, &h->err) ? PGS_OK : PGS_ERR_STATE;
+}
+int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* file) {
+  if (!h || !file) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  FILE* f = fopen(file, "rb");
+  if (!f) { h->err = std::string("cannot open ") + file; return PGS_ERR_STATE; }
+  std::string text; char buf[65536]; size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+  fclose(f);
+  pgs::Json obj; std::string perr;
+  if (!pgs::Json::parse(text, &obj, &perr)) { h->err = perr; return PGS_ERR_STATE; }
+  return h->manager.getWorldsPtr()->loadStateFromDisk(obj.at("WorldsData"), &h->err) ? PGS_OK : PGS_ERR_STATE;
 }
 static int copy_out(const std::string& s, char* out, int32_t cap) {
   if (out && cap > 0) { const size_t n = std::min((size_t)cap - 1, s.size()); std::memcpy(out, s.data(), n); out[n] = 0; }

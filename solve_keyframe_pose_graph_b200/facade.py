@@ -166,6 +166,9 @@ class Facade:
     def save_json(self, directory):
         return self._ck(self.L.pgs_facade_save_json(self.h, str(directory).encode()))
 
+    def load_worlds_state(self, solved_posegraph_json):
+        self._ck(self.L.pgs_facade_load_worlds_state(self.h, str(solved_posegraph_json).encode()))
+
     def load_posegraph_json(self, directory):
         self._ck(self.L.pgs_facade_load_posegraph_json(self.h, str(directory).encode()))
 

@@ -57,7 +57,17 @@ def test_log_posegraph_round_trip_reproduces_the_session(tmp_path):
     assert np.allclose(a["t"], b["t"], atol=1e-12)                                      # 16 significant digits survive the text round trip
     qa, ta = F.poses(); qb, tb = G.poses()
     assert np.allclose(ta, tb, atol=1e-9)
-    F.close(); G.close()
+    # WorldsData of solved_posegraph.json (Worlds.cpp:442-497): relative poses, world stamps and the union-find op-log,
+    # replayed by an empty facade (Worlds::loadStateFromDisk, :499-640)
+    W = json.load(open(tmp_path / "solved_posegraph.json"))["WorldsData"]
+    assert W["disjoint_set"]["log_string"].startswith("add_element:0;add_element:1;add_element:2;add_element:3;") and "union_sets:" in W["disjoint_set"]["log_string"]
+    assert len(W["vec_world_starts"]) == 4 and len(W["vec_world_ends"]) == 3 and len(W["rel_pose_between_worlds__wb_T_wa"]) >= 3
+    H = facade.Facade(dry_run=True); H.load_worlds_state(tmp_path / "solved_posegraph.json")
+    assert [H.world_setid(w) for w in range(5)] == [F.world_setid(w) for w in range(4)] + [-1]   # four worlds known to the union-find, same roots
+    for m_ in range(4):
+        for n_ in range(4):
+            assert np.allclose(H.pose_between_worlds(m_, n_), F.pose_between_worlds(m_, n_), atol=1e-9)
+    F.close(); G.close(); H.close()
 
 
 @pytest.mark.gpu
@@ -72,4 +82,13 @@ def test_solved_posegraph_written_after_a_device_compose(tmp_path):
     J = json.load(open(tmp_path / "solved_posegraph.json"))
     assert sorted(J["SolvedPoseGraph"][0].keys()) == ["seq", "setID_of_worldID", "stampNSec", "w_T_c", "worldID"]
     assert len(J["KidnapTimestamps"]["kidnap_starts"]) == 2 == len(J["KidnapTimestamps"]["kidnap_ends"])
-    F.close()
+    # WorldsData (Worlds.cpp:442-497): relative poses, world stamps and the union-find op-log, replayed by a fresh facade
+    W = J["WorldsData"]
+    assert W["disjoint_set"]["log_string"].startswith("add_element:0;add_element:1;add_element:2;") and "union_sets:" in W["disjoint_set"]["log_string"]
+    assert len(W["vec_world_starts"]) == 3 and len(W["vec_world_ends"]) == 2 and len(W["rel_pose_between_worlds__wb_T_wa"]) >= 2
+    G = facade.Facade(dry_run=True); G.load_worlds_state(tmp_path / "solved_posegraph.json")
+    assert G.n_worlds() == 3 and [G.world_setid(w) for w in range(3)] == [F.world_setid(w) for w in range(3)]
+    for m_ in range(3):
+        for n_ in range(3):
+            assert np.allclose(G.pose_between_worlds(m_, n_), F.pose_between_worlds(m_, n_), atol=1e-9)
+    F.close(); G.close()
