@@ -518,10 +518,11 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
 //   part 0 ("next")  the column tiles tj < 2 — they hold every column of panel d+1, which trsm(d+1) is waiting for;
 //                    tile index T = 2 ti + tj;
 //   part 1 ("rest")  tj >= 2, T = ti (ti - 1) + (tj - 2), on the low-priority stream.
-// A CTA is two independent 256-thread groups (own shared-memory half, own named barrier), one tile each; it needs
-// 216 KB of shared memory, so exactly one fits per SM and the chain kernel C(d+1) (167 KB) always finds a free SM
-// as soon as any CTA retires, instead of waiting for two co-resident CTAs to retire together.
-// Per group 8 warps as 4 x 2, every warp a grid of 4 x 4 8x8 DMMA tiles, K = 96 in three cp.async chunks.
+// One 128x64 tile per 256-thread CTA (108 KB of shared memory, two CTAs per SM): a tile is ~5k cycles of loads
+// (L2 -> SM bandwidth bound) followed by ~12k cycles of DMMA that one CTA can keep saturated, and two CTAs scheduled
+// independently drift out of phase so that one loads while the other multiplies.  (512-thread CTAs of two tiles in
+// lock-step were measured 20 % slower, tools/upd_lab.cu.)
+// 8 warps as 4 x 2, every warp a grid of 4 x 4 8x8 DMMA tiles, K = 96 in three cp.async chunks.
 // predicated 128/64-bit global accesses: no branch, so a thread's sixteen tile loads are all in flight at once
 __device__ __forceinline__ void ldg128_if(double& x, double& y, const double* p, bool pred) {
   asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n @q ld.global.v2.f64 {%0,%1}, [%2];\n}" : "+d"(x), "+d"(y) : "l"(p), "r"((int)pred) : "memory");
@@ -535,35 +536,32 @@ __device__ __forceinline__ void stg128_if(double* p, double x, double y, bool pr
 __device__ __forceinline__ void stg64_if(double* p, double x, bool pred) {
   asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n @q st.global.f64 [%1], %0;\n}" ::"d"(x), "l"(p), "r"((int)pred) : "memory");
 }
-__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 #ifdef SKY_UPD_CLOCKS   // tools/upd_lab.cu: cycle stamps of group 0 / thread 0 of the first CTAs of panel SKY_UPD_CLOCKS
 __device__ long long g_upd_clk[2][64][10];
 #define UPD_STAMP(i) do { if (d == SKY_UPD_CLOCKS && threadIdx.x == 0 && blockIdx.x < 64) g_upd_clk[PART][blockIdx.x][i] = clock64(); } while (0)
 #else
 #define UPD_STAMP(i) do { } while (0)
 #endif
-template <int PART, int GROUPS>
-__global__ void __launch_bounds__(256 * GROUPS, 3 - GROUPS) sky_update_kernel(int d, int n, int skip_below, int Tr, int Tc,
+template <int PART>
+__global__ void __launch_bounds__(256, 2) sky_update_kernel(int d, int n, int skip_below, int Tr, int Tc,
                                                             const long long* __restrict__ ptr, const int* __restrict__ start,
                                                             const int* __restrict__ rows_ptr, const int* __restrict__ rows_idx, double* __restrict__ val) {
   constexpr int WARPS_M = 4, WARPS_N = 2;
   constexpr int WTM = UM / WARPS_M, WTN = UN / WARPS_N, FM = WTM / 8, FN = WTN / 8;
   static_assert(UM == 2 * UN, "triangular tile enumeration assumes UM == 2 UN");
   extern __shared__ __align__(16) double sm[];
-  const int grp = threadIdx.x >> 8, tid = threadIdx.x & 255;
-  double* As = sm + grp * (2 * (UM + UN) * LDK);   // [2][UM][LDK]
+  const int tid = threadIdx.x;
+  double* As = sm;                                 // [2][UM][LDK]
   double* Bs = As + 2 * UM * LDK;                  // [2][UN][LDK]
-  __shared__ long long sh_abase[2][UM], sh_bbase[2][UN];   // element offset of (row, c0) in val, -1 = no such row
-  __shared__ int sh_arow[2][UM], sh_bcol[2][UN];
-  long long* s_abase = sh_abase[grp]; long long* s_bbase = sh_bbase[grp];
-  int* s_arow = sh_arow[grp]; int* s_bcol = sh_bcol[grp];
+  __shared__ long long s_abase[UM], s_bbase[UN];   // element offset of (row, c0) in val, -1 = no such row
+  __shared__ int s_arow[UM], s_bcol[UN];
   const int c0 = d * PW;
   const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
   const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int wm = wid % WARPS_M, wn = wid / WARPS_M;
   constexpr int NCH = PW / KC;
   {
-    const int T = GROUPS * blockIdx.x + grp;
+    const int T = blockIdx.x;
     int ti, tj;
     if (PART == 0) { ti = T >> 1; tj = T & 1; }
     else {
@@ -572,14 +570,7 @@ __global__ void __launch_bounds__(256 * GROUPS, 3 - GROUPS) sky_update_kernel(in
       while ((ti + 1) * ti <= T) ++ti;
       tj = 2 + (T - ti * (ti - 1));
     }
-    if (ti >= Tr || tj >= Tc) return;        // whole group: no tile (odd tile count, or the last row tile ran past Tc)
-#ifndef SKY_UPD_STAGGER
-#define SKY_UPD_STAGGER 6000
-#endif
-    // Stagger the two groups: a tile is ~5k cycles of loads (L2 -> SM bandwidth bound) followed by ~12k cycles of
-    // DMMA that one group alone can keep saturated.  Started together the groups load together and then share the
-    // tensor pipe; started a load phase apart, one loads while the other multiplies (tools/upd_lab.cu).
-    if (GROUPS == 2 && grp == 1 && SKY_UPD_STAGGER > 0) { const long long t_go = clock64() + SKY_UPD_STAGGER; while (clock64() < t_go) { } }
+    if (ti >= Tr || tj >= Tc) return;        // the last row tile can run past the last column tile
     UPD_STAMP(0);
     if (tid < UM) {
       const int ir = ti * UM + tid;
@@ -591,7 +582,7 @@ __global__ void __launch_bounds__(256 * GROUPS, 3 - GROUPS) sky_update_kernel(in
       if (c >= n) c = -1;                    // the rhs row is never a column
       s_bcol[q] = c; s_bbase[q] = c >= 0 ? ptr[c] + (c0 - start[c]) : -1;
     }
-    group_sync(grp);
+    __syncthreads();
     UPD_STAMP(1);
     auto issue = [&](int chunk, int stage) {
       const int k0 = chunk * KC;
@@ -639,7 +630,7 @@ __global__ void __launch_bounds__(256 * GROUPS, 3 - GROUPS) sky_update_kernel(in
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       if (ch + 1 < NCH) cp_async_wait<1>(); else cp_async_wait<0>();
-      group_sync(grp);
+      __syncthreads();
       UPD_STAMP(3 + 2 * ch);
       const double* a_s = As + (ch & 1) * UM * LDK + (wm * WTM + g) * LDK + t;
       const double* b_s = Bs + (ch & 1) * UN * LDK + (wn * WTN + g) * LDK + t;
@@ -656,7 +647,7 @@ __global__ void __launch_bounds__(256 * GROUPS, 3 - GROUPS) sky_update_kernel(in
           for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
       }
       UPD_STAMP(4 + 2 * ch);
-      if (ch + 2 < NCH) { group_sync(grp); issue(ch + 2, ch & 1); }
+      if (ch + 2 < NCH) { __syncthreads(); issue(ch + 2, ch & 1); }
     }
     // epilogue: indices re-read from shared memory so that nothing but the accumulators lives across the MMA loop
 #pragma unroll
@@ -762,8 +753,7 @@ __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo,
 }
 
 static const size_t SM_TRSM = sizeof(double) * (PW * LDT + TR * LDT);
-static const size_t SM_UPD = sizeof(double) * (2 * 2 * (UM + UN) * LDK);   // two groups x two stages: 216 KB, one CTA per SM
-static const size_t SM_UPD1 = sizeof(double) * (2 * (UM + UN) * LDK);      // one group: 108 KB, two CTAs per SM
+static const size_t SM_UPD = sizeof(double) * (2 * (UM + UN) * LDK);   // two stages: 108 KB, two CTAs per SM
 static const size_t SM_DIAG = sizeof(double) * (2 * PW * LDT + (PW / 8) * 64 + 8 * LDT);
 
 static int set_attrs(std::string* err) {
@@ -771,10 +761,8 @@ static int set_attrs(std::string* err) {
   if (attr_set) return PGS_OK;
   SK(cudaFuncSetAttribute(sky_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
   SK(cudaFuncSetAttribute(sky_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TRSM));
-  SK(cudaFuncSetAttribute(sky_update_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
-  SK(cudaFuncSetAttribute(sky_update_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
-  SK(cudaFuncSetAttribute(sky_update_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD1));
-  SK(cudaFuncSetAttribute(sky_update_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD1));
+  SK(cudaFuncSetAttribute(sky_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
+  SK(cudaFuncSetAttribute(sky_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
   attr_set = true;
   return PGS_OK;
 }
@@ -826,7 +814,8 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
   // chain stream s1:  [wait trsm(d-1), rest(d-2)] C(d)    -> ev_c[d]
   // panel stream s2:  [wait C(d)]                 trsm(d) -> ev_trsm[d]   [wait rest(d-1)] next(d)
   // main  stream s0:  [wait trsm(d)]              rest(d) -> ev_rest[d]
-  // next(d-1) precedes trsm(d) on s2, rest(d-1) precedes rest(d) on s0.
+  // next(d-1) precedes trsm(d) on s2, rest(d-1) precedes rest(d) on s0.  (trsm on the chain stream, back to back
+  // with C, saves the two event hops but was measured no faster on c3 and slower on heavier fronts.)
   for (int d = 0; d < f->D_elim; ++d) {
     const int nr = f->h_rows_ptr[d + 1] - f->h_rows_ptr[d];
     const int Tr = (nr + UM - 1) / UM, Tc = (nr + UN - 1) / UN;
@@ -841,19 +830,9 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
     // The rhs row (index n) is always live, also when the last panel is short.
     const int skip_below = (d + 1 < f->D_elim) ? std::min((d + 2) * PW, n) : 0;
     if (d > 0) SK(cudaStreamWaitEvent(s2, f->ev_rest[(d - 1) % NEV], 0));
-#ifndef SKY_NEXT_GROUPS
-#define SKY_NEXT_GROUPS 1
-#endif
-#ifndef SKY_REST_GROUPS
-#define SKY_REST_GROUPS 1
-#endif
-    if (SKY_NEXT_GROUPS == 2) sky_update_kernel<0, 2><<<Tr, 512, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
-    else sky_update_kernel<0, 1><<<2 * Tr, 256, SM_UPD1, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
+    sky_update_kernel<0><<<2 * Tr, 256, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
-    if (Tr > 1) {
-      if (SKY_REST_GROUPS == 2) sky_update_kernel<1, 2><<<(Tr * (Tr - 1) + 1) / 2, 512, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
-      else sky_update_kernel<1, 1><<<Tr * (Tr - 1), 256, SM_UPD1, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
-    }
+    if (Tr > 1) sky_update_kernel<1><<<Tr * (Tr - 1), 256, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     SK(cudaEventRecord(f->ev_rest[d % NEV], s0));
   }
   // join: the main stream continues after all three are done
