@@ -113,3 +113,19 @@ def test_evaluate_from_host_is_bit_identical_to_the_resident_path():
     r = S.evaluate()
     assert np.array_equal(r["r_o"], e["r_o"]) and np.array_equal(r["J_l"], e["J_l"]) and np.array_equal(r["r_r"], e["r_r"])
     S.close(); T.close()
+
+
+def test_tight_options_reach_the_same_minimiser_as_the_oracle():
+    """BASELINE.md parity protocol (ii): with max_num_iterations=100 and function_tolerance=1e-12 both solvers must end
+    at the same stationary point, not merely follow each other for ten iterations."""
+    g = random_graph(200, 3, 40, outlier_frac=0.1, seed=31)
+    from oracle import pgo
+    O = load_oracle(g); S = load_pgs(g, max_num_iterations=100, function_tolerance=1e-12)
+    so = O.solve(pgo.default_options(max_num_iterations=100, function_tolerance=1e-12)); ss = S.solve()
+    assert ss["termination"] == so["termination"] == "CONVERGENCE"
+    assert abs(ss["final_cost"] - so["final_cost"]) <= 1e-9 * so["final_cost"]
+    qo, to = O.poses(); qs, ts = S.poses()
+    assert np.abs(ts - to).max() < 1e-6 and rot_angle_between(qs, qo).max() < 1e-6
+    assert np.array_equal(S.switches() > 0.5, O.switches() > 0.5) and np.abs(S.switches() - O.switches()).max() < 1e-6
+    gp, gs = S.gradient()
+    assert np.abs(gp).max() < 1e-5 * max(1.0, ss["initial_cost"]) and len(ss["iterations"]) < 100    # a stationary point, reached before the cap
