@@ -672,30 +672,34 @@ __global__ void __launch_bounds__(256, 2) sky_update_kernel(int d, int n, int sk
 // backward sweep, one launch per panel d = D-1 .. 0 (plus one leading launch that only computes x of the last panel):
 //   push      acc[c] -= sum_{r in panel d} L[r][c] x_r  for every column c in [lo, c0) inside the rows' envelopes
 //             (256 threads = 32 columns x 8 row groups per CTA);
-//   next x    the last CTA to finish then solves the next panel, x_{d-1} = Linv_{d-1}^T (y_{d-1} + acc_{d-1}) — its
-//             accumulator is complete at that point — so Linv is read once per panel, not once per CTA.
+//   next x    CTA 0 owns the 96 columns of panel d-1: it pushes into them first — which completes that panel's
+//             accumulator, every later panel having pushed in earlier launches — and goes straight on to
+//             x_{d-1} = Linv_{d-1}^T (y_{d-1} + acc_{d-1}) while the other CTAs push into the columns further left.
+//             No counter, no fence: every accumulator entry is touched by one CTA per launch.
 // Border panels of a partial factorisation (d >= D_elim) take x as given: they push, nobody computes them.
-__global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo, int do_push, int next_d, const long long* __restrict__ ptr,
+__global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo, int do_push, int next_d, long long rhs_off, const long long* __restrict__ ptr,
                                                            const int* __restrict__ start, const double* __restrict__ val, const double* __restrict__ dinv,
-                                                           double* __restrict__ acc, double* __restrict__ x, unsigned int* __restrict__ cnt) {
+                                                           double* __restrict__ acc, double* __restrict__ x) {
   __shared__ double xs[PW], red[8][33];
   __shared__ long long rbase[PW];       // ptr[r] - start[r]
   __shared__ int rstart[PW];
-  __shared__ int is_last;
   const int tid = threadIdx.x;
-  if (do_push) {
-    const int c0 = d * PW, w = min(PW, n - c0);
-    if (tid < PW) {
-      const int r = c0 + tid;
-      rbase[tid] = tid < w ? ptr[r] - start[r] : 0; rstart[tid] = tid < w ? start[r] : 0x7fffffff;
-      xs[tid] = tid < w ? x[c0 + tid] : 0.0;
-    }
+  const int c0 = d * PW;
+  const int w = do_push ? min(PW, n - c0) : 0;
+  if (do_push && tid < PW) {
+    const int r = c0 + tid;
+    rbase[tid] = tid < w ? ptr[r] - start[r] : 0; rstart[tid] = tid < w ? start[r] : 0x7fffffff;
+    xs[tid] = tid < w ? x[c0 + tid] : 0.0;
+  }
+  if (blockIdx.x != 0) {
+    // ---- CTAs 1..: the columns left of panel d-1
     __syncthreads();
     const int cx = tid & 31, g = tid >> 5;
-    for (int cb = lo + blockIdx.x * 32; cb < c0; cb += gridDim.x * 32) {
+    const int cend = max(lo, c0 - PW);
+    for (int cb = lo + (blockIdx.x - 1) * 32; cb < cend; cb += (gridDim.x - 1) * 32) {
       const int c = cb + cx;
       double s = 0.0;
-      if (c < c0) {
+      if (c < cend) {
 #pragma unroll
         for (int q = 0; q < PW / 8; ++q) {
           const int i = g * (PW / 8) + q;
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo,
       }
       red[g][cx] = s;
       __syncthreads();
-      if (g == 0 && c < c0) {
+      if (g == 0 && c < cend) {
         double tt = 0.0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) tt += red[q][cx];
@@ -712,43 +716,55 @@ __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo,
       }
       __syncthreads();
     }
+    return;
   }
-  if (next_d < 0) return;
-  if (tid == 0) {
-    __threadfence();
-    const bool last = atomicAdd(cnt, 1u) == gridDim.x - 1;
-    if (last) *cnt = 0u;
-    is_last = last ? 1 : 0;
+  // ---- CTA 0: finish panel d-1.  Everything that does not depend on this launch's push is fetched first: the
+  // right-hand side, the accumulator as the earlier launches left it, and this thread's share of Linv_{d-1}.
+  __shared__ double half[2][PW], part[8][PW];
+  const int cn0 = next_d * PW, wn = next_d >= 0 ? min(PW, n - cn0) : 0;
+  const int ln = tid & 31, wq = tid >> 5;
+  double rhs_pref = 0.0, li[PW / 8][3];
+  if (next_d >= 0) {
+    if (tid < wn) rhs_pref = val[rhs_off + cn0 + tid] + acc[cn0 + tid];
+    const double* Li = dinv + (size_t)next_d * PW * PW;
+#pragma unroll
+    for (int q = 0; q < PW / 8; ++q) { const int i = wq + 8 * q; li[q][0] = Li[i * PW + ln]; li[q][1] = Li[i * PW + 32 + ln]; li[q][2] = Li[i * PW + 64 + ln]; }
   }
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  {
-    const int c0 = next_d * PW, w = min(PW, n - c0);
-    double* rhs = xs;                     // reuse
-    if (tid < PW) rhs[tid] = tid < w ? val[ptr[n] + c0 + tid] + __ldcg(acc + c0 + tid) : 0.0;
-    __syncthreads();
-    const double* Li = dinv + (size_t)next_d * PW * PW;
-    // x_j = sum_{i>=j} Linv[i][j] rhs_i: warp wq takes rows i = wq, wq+8, ..., a lane three columns; all 36 loads of
-    // a lane are independent, so the whole product costs one L2 round trip.  Linv is stored with explicit zeros
-    // above the diagonal, so no triangle test is needed.
-    const int ln = tid & 31, wq = tid >> 5;
-    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+  // push of panel d into the 96 columns of panel d-1 in one round trip: thread (column, row half)
+  if (tid < 2 * PW) {
+    const int cl = tid % PW, h = tid / PW, c = c0 - PW + cl;
+    double s = 0.0;
+    if (do_push && c >= lo) {
+      double v[PW / 2];                     // all 48 loads in flight: one round trip
 #pragma unroll
-    for (int q = 0; q < PW / 8; ++q) {
-      const int i = wq + 8 * q;
-      const double ri = rhs[i];
-      p0 += Li[i * PW + ln] * ri; p1 += Li[i * PW + 32 + ln] * ri; p2 += Li[i * PW + 64 + ln] * ri;
-    }
-    __shared__ double part[8][PW];
-    part[wq][ln] = p0; part[wq][32 + ln] = p1; part[wq][64 + ln] = p2;
-    __syncthreads();
-    if (tid < w) {
-      double sacc = 0.0;
+      for (int q = 0; q < PW / 2; ++q) { const int i = h * (PW / 2) + q; v[q] = c >= rstart[i] ? val[rbase[i] + c] : 0.0; }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) sacc += part[q][tid];
-      x[c0 + tid] = sacc;
+      for (int q = 0; q < PW / 2; ++q) s += v[q] * xs[h * (PW / 2) + q];
     }
+    half[h][cl] = s;
+  }
+  __syncthreads();
+  if (tid < PW) {
+    const double tt = half[0][tid] + half[1][tid];
+    const int c = c0 - PW + tid;
+    if (do_push && c >= lo && c >= 0) acc[c] -= tt;
+    xs[tid] = (next_d >= 0 && tid < wn) ? rhs_pref - ((next_d == d - 1) ? tt : 0.0) : 0.0;   // rhs of panel d-1 (xs reused)
+  }
+  if (next_d < 0) return;
+  __syncthreads();
+  // x_j = sum_{i>=j} Linv[i][j] rhs_i: warp wq takes rows i = wq, wq+8, ..., a lane three columns.  Linv is stored with
+  // explicit zeros above the diagonal, so no triangle test is needed.
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < PW / 8; ++q) { const double ri = xs[wq + 8 * q]; p0 += li[q][0] * ri; p1 += li[q][1] * ri; p2 += li[q][2] * ri; }
+  part[wq][ln] = p0; part[wq][32 + ln] = p1; part[wq][64 + ln] = p2;
+  __syncthreads();
+  if (tid < wn) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sacc += part[q][tid];
+    x[cn0 + tid] = sacc;
   }
 }
 
@@ -849,15 +865,16 @@ int skyline_backward(SkylineFactor* f, double* y, std::string* err) {
   cudaStream_t st = f->stream;
   const int n = f->n, D = f->D;
   if (D == 0) return PGS_OK;
-  unsigned int* cnt = f->sched + 2;
+  const long long rhs_off = f->h_ptr[n];
   // x of the last panel (unless it is a given border panel)
-  if (D - 1 < f->D_elim) sky_backward_kernel<<<1, 256, 0, st>>>(D, n, 0, 0, D - 1, f->ptr, f->start, f->val, f->dinv, f->xacc, y, cnt);
+  if (D - 1 < f->D_elim) sky_backward_kernel<<<1, 256, 0, st>>>(D, n, 0, 0, D - 1, rhs_off, f->ptr, f->start, f->val, f->dinv, f->xacc, y);
   for (int d = D - 1; d >= 0; --d) {
     const int cols = d * PW - f->h_lo[d];
     const int next_d = (d - 1 >= 0 && d - 1 < f->D_elim) ? d - 1 : -1;
     if (cols <= 0 && next_d < 0) continue;
-    const int grid = std::max(1, std::min(592, (cols + 31) / 32));
-    sky_backward_kernel<<<grid, 256, 0, st>>>(d, n, f->h_lo[d], cols > 0 ? 1 : 0, next_d, f->ptr, f->start, f->val, f->dinv, f->xacc, y, cnt);
+    const int left = std::max(0, cols - PW);                      // columns left of panel d-1, shared by CTAs 1..
+    const int grid = 1 + std::min(591, (left + 31) / 32);
+    sky_backward_kernel<<<grid, 256, 0, st>>>(d, n, f->h_lo[d], cols > 0 ? 1 : 0, next_d, rhs_off, f->ptr, f->start, f->val, f->dinv, f->xacc, y);
   }
   SK(cudaGetLastError());
   return PGS_OK;
