@@ -194,7 +194,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// diag: factor the PW x PW diagonal block of panel d in shared memory, store L back, store X = L^-1.
+// diag: factor the PW x PW diagonal block of panel d in shared memory and store X = L^-1.
 // One CTA on the critical path of the whole factorisation, so every matrix-shaped piece runs on DMMA and the
 // inverse is built alongside the factor.  Twelve 8-column steps of two barrier phases each:
 //   phase A  row threads (tid < rows left): re-factor the 8x8 diagonal block in registers (redundantly, no
@@ -428,21 +428,17 @@ __global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, int prev, c
   }
   __syncthreads();
   DIAG_STAMP(2 + 2 * NB);
+  // Only Linv goes back to memory.  L_dd itself has no reader: trsm and the backward sweep multiply by Linv, and the rows
+  // below the panel hold X = A Linv^T, which IS their part of L.
   double* dout = dinv + (size_t)d * PW * PW;
-#pragma unroll 2
+#pragma unroll 4
   for (int i = wid; i < PW; i += 8) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = 2 * (lane + 32 * h);                        // j even: (j, j+1) both in the lower triangle unless j == i
       if (j >= PW) break;
-      const bool in_lo = i < w && j <= i;
       double2 x = make_double2(0.0, 0.0);
-      if (in_lo) {
-        const double2 l = *reinterpret_cast<const double2*>(&L[i * LDQ + j]);
-        x = *reinterpret_cast<const double2*>(&X[i * LDQ + j]);
-        if (j + 1 <= i) *reinterpret_cast<double2*>(val + rbase[i] + j) = l;
-        else { val[rbase[i] + j] = l.x; x.y = 0.0; }
-      }
+      if (i < w && j <= i) { x = *reinterpret_cast<const double2*>(&X[i * LDQ + j]); if (j == i) x.y = 0.0; }
       *reinterpret_cast<double2*>(dout + i * PW + j) = x;
     }
   }

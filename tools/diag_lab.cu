@@ -36,17 +36,14 @@ int main() {
   printf("load: %lld cycles\n", clk[1] - clk[0]);
   for (int I = 0; I < PW / 8; ++I) printf("step %2d: phase A %6lld  phase B %6lld cycles\n", I, clk[2 + 2 * I] - clk[1 + 2 * I], clk[3 + 2 * I] - clk[2 + 2 * I]);
   printf("finish: %lld  store: %lld cycles; total %lld cycles\n", clk[2 + 2 * (PW / 8)] - clk[1 + 2 * (PW / 8)], clk[3 + 2 * (PW / 8)] - clk[2 + 2 * (PW / 8)], clk[3 + 2 * (PW / 8)] - clk[0]);
-  // check: L L^T == A, X L == I
-  std::vector<double> Lh(n * n), Xh(n * n); int hf = 0;
-  CKL(cudaMemcpy(Lh.data(), val, sizeof(double) * n * n, cudaMemcpyDeviceToHost)); CKL(cudaMemcpy(Xh.data(), dinv, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+  // check: X A X^T == I  (X = L^-1; the kernel stores only X)
+  std::vector<double> Xh(n * n); int hf = 0;
+  CKL(cudaMemcpy(Xh.data(), dinv, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
   CKL(cudaMemcpy(&hf, fail, 4, cudaMemcpyDeviceToHost));
-  double e1m = 0, e2m = 0;
-  for (int i = 0; i < n; ++i) for (int j = 0; j <= i; ++j) {
-    double s = 0; for (int k = 0; k <= j; ++k) s += Lh[i * n + k] * Lh[j * n + k];
-    e1m = std::max(e1m, std::fabs(s - A[i * n + j]));
-    double t = 0; for (int k = j; k <= i; ++k) t += Xh[i * n + k] * Lh[k * n + j];
-    e2m = std::max(e2m, std::fabs(t - (i == j ? 1.0 : 0.0)));
-  }
-  printf("fail=%d  max|LL^T - A| = %.3e   max|X L - I| = %.3e\n", hf, e1m, e2m);
+  std::vector<double> XA(n * n, 0.0);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k <= i; ++k) s += Xh[i * n + k] * (k >= j ? A[k * n + j] : A[j * n + k]); XA[i * n + j] = s; }
+  double e1m = 0;
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { double s = 0; for (int k = 0; k <= j; ++k) s += XA[i * n + k] * Xh[j * n + k]; e1m = std::max(e1m, std::fabs(s - (i == j ? 1.0 : 0.0))); }
+  printf("fail=%d  max|X A X^T - I| = %.3e\n", hf, e1m);
   return 0;
 }
