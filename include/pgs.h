@@ -109,6 +109,11 @@ int pgs_set_nodes(pgs_handle h, int32_t n, const double* q_xyzw, const double* t
 int pgs_append_nodes(pgs_handle h, int32_t n, const double* q_xyzw, const double* t);   /* grow */
 int pgs_update_nodes(pgs_handle h, int32_t first, int32_t n, const double* q_xyzw, const double* t); /* new initial guesses */
 int pgs_get_poses(pgs_handle h, int32_t first, int32_t n, double* q_xyzw, double* t);   /* getNodePose, :197-214 */
+/* ceres::Problem::SetParameterBlockConstant (constant != 0) / SetParameterBlockVariable on the q and t blocks of nodes
+ * [first, first+n): what PoseGraphSLAM::load_state does to every keyframe of a session restored from disk
+ * (PoseGraphSLAM.cpp:40-170).  Constant blocks keep their value, get zero Jacobian columns and leave the step and
+ * gradient norms, as in Ceres' reduced program; residual blocks on them still count in the cost. */
+int pgs_set_constant_nodes(pgs_handle h, int32_t first, int32_t n, int32_t constant);
 int pgs_set_switches(pgs_handle h, int32_t first, int32_t n, const double* s);
 int pgs_get_switches(pgs_handle h, int32_t first, int32_t n, double* s);                /* get_loopedge_switching_variable_val, PoseGraphSLAM.h:219 */
 

@@ -42,6 +42,10 @@ int pgs_facade_loopclosure_pose_callback(pgs_facade_handle h, uint32_t sec0, uin
                                          const double* orientation_xyzw, float weight, const char* description);   /* 1 added, 0 dropped */
 int pgs_facade_rcvd_kidnap_indicator_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const char* frame_id);
 
+/* PoseGraphSLAM::load_state (src/PoseGraphSLAM.cpp:40-170): after the manager was restored from disk, turn every loaded
+ * keyframe into a CONSTANT optimisation variable (pose in its set root's frame) and move solvedUntil to the last one. */
+int pgs_facade_load_state(pgs_facade_handle h);
+
 /* one wake-up of the solver thread: 1 solved, 0 not triggered, <0 error */
 int pgs_facade_solve_once(pgs_facade_handle h, int32_t force);
 int pgs_facade_status(pgs_facade_handle h);

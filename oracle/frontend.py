@@ -245,6 +245,7 @@ class ReferenceFrontEnd:
         self.options = options
         self.opt_q, self.opt_t, self.opt_s = [], [], []
         self.solved_until = 0
+        self.n_constant = 0
         self.prev_loopedge_len = 0
         self.changes = {}
         # accumulated residual blocks
@@ -258,6 +259,22 @@ class ReferenceFrontEnd:
     def _set(self, i, T):
         q, t = pgo.mat4_to_pose(T)
         self.opt_q[i] = q; self.opt_t[i] = t
+
+    def load_state(self):
+        """PoseGraphSLAM::load_state (src/PoseGraphSLAM.cpp:40-170): every keyframe already in the manager becomes a
+        CONSTANT optimisation variable at ws_T_w * w_T_c; solvedUntil moves to the last one."""
+        m = self.m; W = m.worlds
+        for yp in range(len(self.opt_q), len(m.poses)):
+            world = m.which_world_is_this(m.stamps[yp]); setid = W.find_setID_of_world_i(world)
+            ws_T_w = np.eye(4)
+            if world >= 0 and world != setid:                      # :104-116
+                if not W.is_exist(setid, world):
+                    raise RuntimeError("reference exit(1)")
+                ws_T_w = W.getPoseBetweenWorlds(setid, world)
+            q, t = pgo.mat4_to_pose(ws_T_w @ m.poses[yp])           # :118-131
+            self.opt_q.append(q); self.opt_t.append(t)
+        self.n_constant = len(m.poses)                              # :150-151
+        self.solved_until = len(m.poses) - 1                        # :165
 
     def trigger(self, solve=True):
         m = self.m
@@ -348,6 +365,8 @@ class ReferenceFrontEnd:
     def problem(self):
         P = pgo.Problem()
         P.set_nodes(np.array(self.opt_q), np.array(self.opt_t))
+        if self.n_constant:
+            P.set_constant_nodes(0, self.n_constant)
         if self.odom:
             P.add_odom_edges([o[0] for o in self.odom], [o[1] for o in self.odom], np.array([o[2] for o in self.odom]),
                              np.array([o[3] for o in self.odom]), [o[4] for o in self.odom])

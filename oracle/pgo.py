@@ -134,6 +134,9 @@ class Problem:
         self.N = q.shape[0]
         self.L.pgo_set_nodes(self.h, C.c_int(self.N), qp, tp)
 
+    def set_constant_nodes(self, first, n, constant=True):
+        self.L.pgo_set_constant_nodes(self.h, C.c_int(first), C.c_int(n), C.c_int(int(constant)))
+
     def add_odom_edges(self, c1, c2, q, t, w):
         c1, c1p = _i(c1); c2, c2p = _i(c2); q, qp = _d(q); t, tp = _d(t); w, wp = _d(w)
         self.L.pgo_add_odom_edges(self.h, C.c_int(len(c1)), c1p, c2p, qp, tp, wp)

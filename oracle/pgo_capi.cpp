@@ -59,7 +59,12 @@ void* pgo_create() { return new Problem(); }
 void pgo_destroy(void* h) { delete (Problem*)h; }
 
 void pgo_set_nodes(void* h, int n, const double* q, const double* t) {
-  Problem& P = *(Problem*)h; P.N = n; P.q.assign(q, q + 4 * (size_t)n); P.t.assign(t, t + 3 * (size_t)n);
+  Problem& P = *(Problem*)h; P.N = n; P.q.assign(q, q + 4 * (size_t)n); P.t.assign(t, t + 3 * (size_t)n); P.node_const.clear();
+}
+void pgo_set_constant_nodes(void* h, int first, int n, int constant) {
+  Problem& P = *(Problem*)h;
+  if ((int)P.node_const.size() < P.N) P.node_const.resize(P.N, 0);
+  for (int i = first; i < first + n && i < P.N; ++i) P.node_const[i] = constant ? 1 : 0;
 }
 void pgo_add_odom_edges(void* h, int m, const int* c1, const int* c2, const double* q, const double* t, const double* w) {
   Problem& P = *(Problem*)h;

@@ -81,6 +81,11 @@ struct Problem {
   std::vector<double> sw;                   // switch variables (one per loop-edge slot)
   // NodePoseRegularization blocks
   std::vector<int> rn; std::vector<double> rq, rt, rw;
+  // ceres::Problem::SetParameterBlockConstant on a node's q and t blocks (reference PoseGraphSLAM.cpp:150-151, load_state):
+  // Ceres removes constant blocks from the reduced program, i.e. their Jacobian columns vanish and they leave the
+  // state vector whose norms drive the convergence tests.  Empty = no constant block.
+  std::vector<char> node_const;
+  bool is_const(int i) const { return i < (int)node_const.size() && node_const[i]; }
 
   int n_odom() const { return (int)oc1.size(); }
   int n_loop() const { return (int)lc1.size(); }
@@ -130,6 +135,13 @@ struct Problem {
       if (ad) eval_reg_autodiff(f, Q + 4 * a, T + 3 * a, r, J);
       else eval_reg_closed(f, Q + 4 * a, T + 3 * a, r, J);
       for (int i = 0; i < 6; ++i) cost += r[i] * r[i];
+    }
+    if (want_jac && !node_const.empty()) {      // zero the tangent columns of constant parameter blocks
+      for (int e = 0; e < Eo; ++e) for (int side = 0; side < 2; ++side) if (is_const(side ? oc2[e] : oc1[e]))
+        for (int i = 0; i < 6; ++i) for (int c = 0; c < 6; ++c) J_o[72 * (size_t)e + 12 * i + 6 * side + c] = 0.0;
+      for (int e = 0; e < El; ++e) for (int side = 0; side < 2; ++side) if (is_const(side ? lc2[e] : lc1[e]))
+        for (int i = 0; i < 7; ++i) for (int c = 0; c < 6; ++c) J_l[91 * (size_t)e + 13 * i + 6 * side + c] = 0.0;
+      for (int k = 0; k < K; ++k) if (is_const(rn[k])) for (int i = 0; i < 36; ++i) J_r[36 * (size_t)k + i] = 0.0;
     }
     return 0.5 * cost;
   }
@@ -210,6 +222,7 @@ struct Solver {
     for (int e = 0; e < Eo; ++e) touch(P.oc1[e], P.oc2[e]);
     for (int e = 0; e < El; ++e) { touch(P.lc1[e], P.lc2[e]); sw_used[P.lsi[e]] = 1; }
     for (int k = 0; k < K; ++k) node_used[P.rn[k]] = 1;
+    for (int i = 0; i < N; ++i) if (P.is_const(i)) node_used[i] = 0;   // constant blocks are not part of the reduced program
     std::vector<int> start(6 * (size_t)N);
     for (int i = 0; i < N; ++i) for (int c = 0; c < 6; ++c) start[6 * i + c] = 6 * nstart[i];
     A.init(6 * N, start);

@@ -227,6 +227,9 @@ class PoseGraphSolver:
         node, np_ = _i(node); q, qp = _d(q); t, tp = _d(t); w, wp = _d(w)
         self._ck(self.L.pgs_set_regularizers(self.h, C.c_int32(len(node)), np_, qp, tp, wp)); self.n_reg = len(node)
 
+    def set_constant_nodes(self, first, n, constant=True):
+        self._ck(self.L.pgs_set_constant_nodes(self.h, C.c_int32(first), C.c_int32(n), C.c_int32(int(constant))))
+
     def set_switches(self, s, first=0):
         s, sp = _d(s)
         self._ck(self.L.pgs_set_switches(self.h, C.c_int32(first), C.c_int32(len(s)), sp))

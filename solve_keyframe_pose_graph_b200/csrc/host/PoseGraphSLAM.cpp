@@ -84,6 +84,27 @@ void PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF() {
   }
 }
 
+bool PoseGraphSLAM::load_state() {
+  error_.clear();
+  const int node_len = manager->getNodeLen();
+  if (node_len == 0) return fail("load_state: no keyframes in the manager (the reference exits here, PoseGraphSLAM.cpp:54-59)");
+  const Worlds* worlds = manager->getWorldsConstPtr();
+  for (int yp = n_opt_variables(); yp < node_len; ++yp) {
+    const int world = manager->which_world_is_this(manager->getNodeTimestamp(yp));
+    const int setid = worlds->find_setID_of_world_i(world);
+    Matrix4d ws_T_w = Matrix4d::Identity();
+    if (world >= 0 && world != setid) {                                    // :104-116
+      bool ok = false;
+      if (worlds->is_exist(setid, world)) ws_T_w = worlds->getPoseBetweenWorlds(setid, world, &ok);
+      if (!ok) return fail("load_state: no relative pose between world " + std::to_string(world) + " and its set root " + std::to_string(setid));
+    }
+    allocate_and_append_new_opt_variable_withpose(ws_T_w * manager->getNodePose(yp));   // :118-131
+  }
+  n_constant_ = node_len;                                                  // SetParameterBlockConstant, :150-151
+  { std::lock_guard<std::mutex> lk(mutex_opt_vars); solved_until = node_len - 1; }     // :165
+  return true;
+}
+
 bool PoseGraphSLAM::solve_once(bool force) {
   error_.clear();
   const int node_len = manager->getNodeLen();
@@ -231,6 +252,7 @@ bool PoseGraphSLAM::solve_once(bool force) {
     int rc = PGS_OK;
     if (node_len > n_device_nodes_) rc = pgs_append_nodes(handle_, node_len - n_device_nodes_, &q[4 * (size_t)n_device_nodes_], &t[3 * (size_t)n_device_nodes_]);
     if (rc == PGS_OK) rc = pgs_update_nodes(handle_, 0, node_len, q.data(), t.data());
+    if (rc == PGS_OK && n_constant_ > n_constant_on_device_) { rc = pgs_set_constant_nodes(handle_, 0, n_constant_, 1); n_constant_on_device_ = n_constant_; }
     if (rc == PGS_OK && !new_la.empty()) rc = pgs_add_loop_edges(handle_, (int)new_la.size(), new_la.data(), new_lb.data(), new_lq.data(), new_lt.data(), new_lw.data());
     if (rc == PGS_OK && !new_odom.empty()) {
       std::vector<int> c1, c2; std::vector<double> oq, ot, ow;

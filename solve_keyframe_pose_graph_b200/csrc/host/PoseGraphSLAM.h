@@ -47,6 +47,11 @@ class PoseGraphSLAM {
   // One wake-up of the loop above.  Returns true if a solve was triggered.  force = solve even without
   // new loop edges.  On failure returns false and last_error() is non-empty.
   bool solve_once(bool force = false);
+  // After a session was restored into the manager (loadFromJSON + Worlds state): one optimisation variable per loaded
+  // keyframe, initialised to ws_T_w * w_T_c (its pose in the frame of its world's set root) and marked CONSTANT, and
+  // solvedUntil moved to the last of them (reference PoseGraphSLAM.cpp:40-170).  Later keyframes are optimised against
+  // this fixed backbone.  false: no keyframes, or a world whose set transform is unknown (the reference exits).
+  bool load_state();
   const std::string& last_error() const { return error_; }
 
   // Explicit-graph API (north_star).  Poses are 4x4: a_T_b for odometry (binds SixDOFError(a, b)),
@@ -109,6 +114,8 @@ class PoseGraphSLAM {
   std::vector<int> loop_slot_;       // manager loop-edge index -> device loop-edge index (-1: skipped, dead zone)
   int n_device_nodes_ = 0, n_device_loops_ = 0;
   int odom_scanned_until_ = 0;       // odometry edges exist for u <= this
+  int n_constant_ = 0;               // variables [0, n_constant_) are constant blocks (load_state)
+  int n_constant_on_device_ = 0;
 
   pgs_handle handle_ = nullptr;
   pgs_summary summary_{};

@@ -89,6 +89,11 @@ int pgs_facade_rcvd_kidnap_indicator_callback(pgs_facade_handle h, uint32_t sec,
   pgs::ros_shim::Header hd; hd.stamp.sec = sec; hd.stamp.nsec = nsec; hd.frame_id = frame_id;
   return pgs::ros_shim::rcvd_kidnap_indicator_callback(h->manager, hd) ? PGS_OK : PGS_ERR_STATE;
 }
+int pgs_facade_load_state(pgs_facade_handle h) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  return h->slam->load_state() ? PGS_OK : PGS_ERR_STATE;
+}
 int pgs_facade_solve_once(pgs_facade_handle h, int32_t force) {
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
   h->err.clear();

@@ -44,6 +44,7 @@ int pgs_set_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H
 int pgs_append_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); return h->s->set_nodes(n, q, t, true); }
 int pgs_update_nodes(pgs_handle h, int32_t first, int32_t n, const double* q, const double* t) { H(h); return h->s->update_nodes(first, n, q, t); }
 int pgs_get_poses(pgs_handle h, int32_t first, int32_t n, double* q, double* t) { H(h); return h->s->get_poses(first, n, q, t); }
+int pgs_set_constant_nodes(pgs_handle h, int32_t first, int32_t n, int32_t constant) { H(h); return h->s->set_constant(first, n, constant); }
 int pgs_set_switches(pgs_handle h, int32_t first, int32_t n, const double* s) { H(h); return h->s->set_switches(first, n, s); }
 int pgs_get_switches(pgs_handle h, int32_t first, int32_t n, double* s) { H(h); return h->s->get_switches(first, n, s); }
 int pgs_add_odom_edges(pgs_handle h, int32_t m, const int32_t* c1, const int32_t* c2, const double* q, const double* t, const double* w) {

@@ -44,7 +44,7 @@ struct SweepArgs {
 
 // ------------------------------------------------------------------ small math
 struct Q4 { double x, y, z, w; };
-struct P7 { Q4 q; double tx, ty, tz; };
+struct P7 { Q4 q; double tx, ty, tz; double fixed; };   // fixed: 1.0 for a constant parameter block (8th slot of the pose record), else 0.0
 
 __device__ __forceinline__ Q4 qmul(const Q4& a, const Q4& b) {
   Q4 r;
@@ -66,7 +66,7 @@ __device__ __forceinline__ void qtoR(const Q4& q, double R[9]) {
 __device__ __forceinline__ P7 load_pose(const double* __restrict__ pose, int i) {
   const double2* p = reinterpret_cast<const double2*>(pose + 8 * (size_t)i);
   const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-  P7 r; r.q.x = a.x; r.q.y = a.y; r.q.z = b.x; r.q.w = b.y; r.tx = c.x; r.ty = c.y; r.tz = d.x;
+  P7 r; r.q.x = a.x; r.q.y = a.y; r.q.z = b.x; r.q.w = b.y; r.tx = c.x; r.ty = c.y; r.tz = d.x; r.fixed = d.y;
   return r;
 }
 // M = (L(A) Rm(b))[0:3,0:3]: derivative of vec(A (x) dq (x) b) w.r.t. the half-angle increment of dq.
@@ -166,18 +166,19 @@ __global__ void __launch_bounds__(256, PGS_SWEEP_MINB) sweep_kernel(SweepArgs A)
 #pragma unroll
           for (int i = 0; i < 6; ++i) st_stream(r + i * TILE, ev[i]);
           double* J = A.o_J + (size_t)tile * (OD_J * TILE) + lane;
-          const double w2 = 2.0 * w;
+          // a constant parameter block (ceres SetParameterBlockConstant, reference PoseGraphSLAM.cpp:150-151) gets zero columns
+          const double wa = w * (1.0 - p1.fixed), wb = w * (1.0 - p2.fixed), wa2 = 2.0 * wa, wb2 = 2.0 * wb;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              st_stream(J + (i * 6 + j) * TILE, -w2 * Ba[3 * i + j]);             // d e_t / d th1
-              st_stream(J + (i * 6 + 3 + j) * TILE, w * Rt[3 * i + j]);           // d e_t / d t1
-              st_stream(J + ((3 + i) * 6 + j) * TILE, w2 * M[3 * i + j]);         // d e_r / d th1
+              st_stream(J + (i * 6 + j) * TILE, -wa2 * Ba[3 * i + j]);            // d e_t / d th1
+              st_stream(J + (i * 6 + 3 + j) * TILE, wa * Rt[3 * i + j]);          // d e_t / d t1
+              st_stream(J + ((3 + i) * 6 + j) * TILE, wa2 * M[3 * i + j]);        // d e_r / d th1
               st_stream(J + ((3 + i) * 6 + 3 + j) * TILE, 0.0);
-              st_stream(J + (36 + i * 6 + j) * TILE, w2 * Bv[3 * i + j]);         // d e_t / d th2
-              st_stream(J + (36 + i * 6 + 3 + j) * TILE, -w * Rt[3 * i + j]);     // d e_t / d t2
-              st_stream(J + (36 + (3 + i) * 6 + j) * TILE, -w2 * M[3 * i + j]);   // d e_r / d th2
+              st_stream(J + (36 + i * 6 + j) * TILE, wb2 * Bv[3 * i + j]);        // d e_t / d th2
+              st_stream(J + (36 + i * 6 + 3 + j) * TILE, -wb * Rt[3 * i + j]);    // d e_t / d t2
+              st_stream(J + (36 + (3 + i) * 6 + j) * TILE, -wb2 * M[3 * i + j]);  // d e_r / d th2
               st_stream(J + (36 + (3 + i) * 6 + 3 + j) * TILE, 0.0);
             }
           }
@@ -206,18 +207,18 @@ __global__ void __launch_bounds__(256, PGS_SWEEP_MINB) sweep_kernel(SweepArgs A)
           for (int i = 0; i < 6; ++i) st_stream(r + i * TILE, s * ev[i]);
           st_stream(r + 6 * TILE, r6);
           double* J = A.l_J + (size_t)lt * (LP_J * TILE) + lane;
-          const double s2 = 2.0 * s;
+          const double sa = s * (1.0 - p1.fixed), sb = s * (1.0 - p2.fixed), sa2 = 2.0 * sa, sb2 = 2.0 * sb;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              st_stream(J + (i * 6 + j) * TILE, -s2 * Ba[3 * i + j]);
-              st_stream(J + (i * 6 + 3 + j) * TILE, s * Rt[3 * i + j]);
-              st_stream(J + ((3 + i) * 6 + j) * TILE, s2 * M[3 * i + j]);
+              st_stream(J + (i * 6 + j) * TILE, -sa2 * Ba[3 * i + j]);
+              st_stream(J + (i * 6 + 3 + j) * TILE, sa * Rt[3 * i + j]);
+              st_stream(J + ((3 + i) * 6 + j) * TILE, sa2 * M[3 * i + j]);
               st_stream(J + ((3 + i) * 6 + 3 + j) * TILE, 0.0);
-              st_stream(J + (42 + i * 6 + j) * TILE, s2 * Bv[3 * i + j]);
-              st_stream(J + (42 + i * 6 + 3 + j) * TILE, -s * Rt[3 * i + j]);
-              st_stream(J + (42 + (3 + i) * 6 + j) * TILE, -s2 * M[3 * i + j]);
+              st_stream(J + (42 + i * 6 + j) * TILE, sb2 * Bv[3 * i + j]);
+              st_stream(J + (42 + i * 6 + 3 + j) * TILE, -sb * Rt[3 * i + j]);
+              st_stream(J + (42 + (3 + i) * 6 + j) * TILE, -sb2 * M[3 * i + j]);
               st_stream(J + (42 + (3 + i) * 6 + 3 + j) * TILE, 0.0);
             }
           }
@@ -268,8 +269,9 @@ __global__ void __launch_bounds__(256, PGS_SWEEP_MINB) sweep_kernel(SweepArgs A)
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              J[i * 6 + j] = 0.0; J[i * 6 + 3 + j] = w * Rf[3 * j + i];
-              J[(3 + i) * 6 + j] = 2.0 * w * sgn * M[3 * i + j]; J[(3 + i) * 6 + 3 + j] = 0.0;
+              const double wf = w * (1.0 - p.fixed);
+              J[i * 6 + j] = 0.0; J[i * 6 + 3 + j] = wf * Rf[3 * j + i];
+              J[(3 + i) * 6 + j] = 2.0 * wf * sgn * M[3 * i + j]; J[(3 + i) * 6 + 3 + j] = 0.0;
             }
         }
       }
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(256) retract_kernel(int N, int count_until, in
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
     const double* x = pose + 8 * (size_t)i; double* c = cpose + 8 * (size_t)i;
-    if (!node_used[i]) { for (int k = 0; k < 8; ++k) c[k] = x[k]; continue; }
+    if (!node_used[i]) { for (int k = 0; k < 8; ++k) c[k] = x[k]; continue; }   // unused or constant blocks stay as they are
     const double a0 = sign * dp[6 * (size_t)i], a1 = sign * dp[6 * (size_t)i + 1], a2 = sign * dp[6 * (size_t)i + 2];
     const double n = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
     double o[7];
@@ -668,7 +670,7 @@ __global__ void __launch_bounds__(256) retract_kernel(int N, int count_until, in
     const bool counted = i < count_until;
 #pragma unroll
     for (int k = 0; k < 7; ++k) { const double df = x[k] - o[k]; if (counted) { d2 += df * df; x2 += x[k] * x[k]; mx = fmax(mx, fabs(df)); } c[k] = o[k]; }
-    c[7] = 0.0;
+    c[7] = x[7];
   }
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_loop; e += stride) {
     const double s = sw[e], c = s + sign * ds[e];

@@ -18,12 +18,13 @@ namespace pgs {
 
 
 // ---- small pack/unpack kernels between the C-ABI's SoA (q[4N], t[3N], s[El] caller order) and the device layout
-__global__ void pack_pose_kernel(int first, int n, const double* __restrict__ q, const double* __restrict__ t, double* __restrict__ pose) {
+// the 8th slot of a pose record carries the constant-block flag (1.0 = constant), which the sweep turns into zero Jacobian columns
+__global__ void pack_pose_kernel(int first, int n, const double* __restrict__ q, const double* __restrict__ t, const char* __restrict__ fixed, double* __restrict__ pose) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double* p = pose + 8 * (size_t)(first + i);
   p[0] = q[4 * (size_t)i]; p[1] = q[4 * (size_t)i + 1]; p[2] = q[4 * (size_t)i + 2]; p[3] = q[4 * (size_t)i + 3];
-  p[4] = t[3 * (size_t)i]; p[5] = t[3 * (size_t)i + 1]; p[6] = t[3 * (size_t)i + 2]; p[7] = 0.0;
+  p[4] = t[3 * (size_t)i]; p[5] = t[3 * (size_t)i + 1]; p[6] = t[3 * (size_t)i + 2]; p[7] = fixed[first + i] ? 1.0 : 0.0;
 }
 __global__ void unpack_pose_kernel(int first, int n, const double* __restrict__ pose, double* __restrict__ q, double* __restrict__ t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,7 +104,7 @@ double Solver::toc() { cudaEventRecord(ev1, stream); cudaEventSynchronize(ev1); 
 int Solver::set_nodes(int n, const double* q, const double* t, bool append) {
   if (n < 0 || (n > 0 && (!q || !t))) return fail(PGS_ERR_INVALID_ARGUMENT, "set_nodes: null input");
   if (int rc = sync_params_to_host()) return rc;
-  if (!append) { h_q.clear(); h_t.clear(); }
+  if (!append) { h_q.clear(); h_t.clear(); h_node_const.clear(); }
   h_q.insert(h_q.end(), q, q + 4 * (size_t)n);
   h_t.insert(h_t.end(), t, t + 3 * (size_t)n);
   N = (int)(h_t.size() / 3);
@@ -123,6 +124,15 @@ int Solver::get_poses(int first, int n, double* q, double* t) {
   if (int rc = sync_params_to_host()) return rc;
   if (q) std::memcpy(q, &h_q[4 * (size_t)first], sizeof(double) * 4 * n);
   if (t) std::memcpy(t, &h_t[3 * (size_t)first], sizeof(double) * 3 * n);
+  return PGS_OK;
+}
+int Solver::set_constant(int first, int n, int constant) {
+  if (first < 0 || n < 0 || first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "set_constant_nodes: range out of bounds");
+  if (comm_owned) return fail(PGS_ERR_STATE, "set_constant_nodes: not supported on a multi-GPU handle");
+  if (int rc = sync_params_to_host()) return rc;
+  if ((int)h_node_const.size() < N) h_node_const.resize(N, 0);
+  for (int i = first; i < first + n; ++i) h_node_const[i] = constant ? 1 : 0;
+  structure_dirty = true; host_params_newer = true;   // node_used and the pose records' flag slot are rebuilt
   return PGS_OK;
 }
 int Solver::set_switches(int first, int n, const double* s) {
@@ -224,7 +234,10 @@ int Solver::finalize() {
   for (int e = 0; e < El; ++e) { inc_item[cur[lidx[e].x]++] = (e << 3) | 2; inc_item[cur[lidx[e].y]++] = (e << 3) | 3; }
   for (int k = 0; k < K; ++k) inc_item[cur[r_node[k]]++] = (k << 3) | 4;
   h_node_used.assign(std::max(N, 1), 0);
-  for (int i = 0; i < N; ++i) h_node_used[i] = inc_ptr[i + 1] > inc_ptr[i];
+  h_node_const.resize(std::max(N, 1), 0);
+  // a block is updated (and counted in the step / gradient norms) if some residual block uses it and it is not constant:
+  // Ceres' reduced program drops unused and constant parameter blocks alike
+  for (int i = 0; i < N; ++i) h_node_used[i] = inc_ptr[i + 1] > inc_ptr[i] && !h_node_const[i];
   // 3. distinct node pairs (hi, lo) and their edges (edge<<2 | kind<<1 | c1_is_hi)
   std::vector<std::pair<uint64_t, int>> keyed; keyed.reserve((size_t)Eo + El);
   auto key_of = [](int c1, int c2) { const uint64_t hi = (uint64_t)std::max(c1, c2), lo = (uint64_t)std::min(c1, c2); return (hi << 32) | lo; };
@@ -260,7 +273,7 @@ int Solver::finalize() {
   CU(d_inc_ptr.upload(inc_ptr, stream)); CU(d_inc_item.upload(inc_item, stream));
   CU(d_pe_ptr.upload(pe_ptr, stream)); CU(d_pe_item.upload(pe_item, stream)); CU(d_pair.upload(pairs, stream));
   CU(d_adj_ptr.upload(adj_ptr, stream)); CU(d_adj_item.upload(adj_item, stream));
-  CU(d_node_used.upload(h_node_used, stream));
+  CU(d_node_used.upload(h_node_used, stream)); CU(d_node_const.upload(h_node_const, stream));
   // 6. outputs and work arrays
   CU(d_pose.resize((size_t)N * 8, true)); CU(d_cpose.resize((size_t)N * 8, true));
   CU(d_sw.resize(std::max(El, 1), true)); CU(d_csw.resize(std::max(El, 1), true));
@@ -291,7 +304,7 @@ int Solver::sync_params_to_device() {
   if (N) {
     CU(cudaMemcpyAsync(d_stage_q.p, h_q.data(), sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(d_stage_t.p, h_t.data(), sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
-    pack_pose_kernel<<<cdiv(N, 256), 256, 0, stream>>>(0, N, d_stage_q.p, d_stage_t.p, d_pose.p);
+    pack_pose_kernel<<<cdiv(N, 256), 256, 0, stream>>>(0, N, d_stage_q.p, d_stage_t.p, d_node_const.p, d_pose.p);
   }
   if (El) {
     CU(cudaMemcpyAsync(d_stage_s.p, h_sw.data(), sizeof(double) * (size_t)El, cudaMemcpyHostToDevice, stream));
@@ -598,7 +611,7 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
   if (t) CU(cudaMemcpyAsync(d_stage_t.p, t, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
   if ((q || t) && N) {
     if (!q || !t) return fail(PGS_ERR_INVALID_ARGUMENT, "evaluate_from_host: q and t must be given together");
-    pack_pose_kernel<<<cdiv(N, 256), 256, 0, stream>>>(0, N, d_stage_q.p, d_stage_t.p, d_pose.p);
+    pack_pose_kernel<<<cdiv(N, 256), 256, 0, stream>>>(0, N, d_stage_q.p, d_stage_t.p, d_node_const.p, d_pose.p);
   }
   if (s && El) {
     CU(cudaMemcpyAsync(d_stage_s.p, s, sizeof(double) * (size_t)El, cudaMemcpyHostToDevice, stream));

@@ -54,6 +54,7 @@ class Solver {
   int set_nodes(int n, const double* q, const double* t, bool append);
   int update_nodes(int first, int n, const double* q, const double* t);
   int get_poses(int first, int n, double* q, double* t);
+  int set_constant(int first, int n, int constant);   // ceres::Problem::SetParameterBlockConstant / Variable on node blocks
   int set_switches(int first, int n, const double* s);
   int get_switches(int first, int n, double* s);
   int add_odom(int m, const int* c1, const int* c2, const double* q, const double* t, const double* w);
@@ -119,7 +120,7 @@ class Solver {
   std::vector<int> inv_perm_l;
   int n_pairs = 0;
   std::vector<int> h_pair_hi, h_pair_lo;
-  std::vector<char> h_node_used;
+  std::vector<char> h_node_used, h_node_const;
 
   // device
   int dev = 0; cudaStream_t stream = nullptr;
@@ -130,7 +131,7 @@ class Solver {
   DBuf<int> d_rnode, d_perm_o, d_perm_l;
   DBuf<double> d_or, d_oJ, d_lr, d_lJ, d_gr, d_gJ;
   DBuf<int> d_inc_ptr, d_inc_item, d_pe_ptr, d_pe_item, d_adj_ptr, d_adj_item;
-  DBuf<char> d_node_used;
+  DBuf<char> d_node_used, d_node_const;
   DBuf<double> d_Hd, d_g, d_Ho, d_lv, d_lh, d_lg, d_lvt, d_lw, d_lgt;
   DBuf<double> d_scale_p, d_scale_s, d_diag_p, d_diag_s;
   DBuf<double> d_Ad, d_Ao, d_b, d_y, d_dp, d_ds;

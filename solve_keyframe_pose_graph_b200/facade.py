@@ -110,6 +110,9 @@ class Facade:
             self.add_loop_edges(g["la"], g["lb"], g["lq"], g["lt"], g["lw"])
 
     # ---- solve
+    def load_state(self):
+        self._ck(self.L.pgs_facade_load_state(self.h))
+
     def solve_once(self, force=False):
         return self._ck(self.L.pgs_facade_solve_once(self.h, C.c_int32(int(force)))) == 1
 

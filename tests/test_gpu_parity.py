@@ -129,3 +129,28 @@ def test_tight_options_reach_the_same_minimiser_as_the_oracle():
     assert np.array_equal(S.switches() > 0.5, O.switches() > 0.5) and np.abs(S.switches() - O.switches()).max() < 1e-6
     gp, gs = S.gradient()
     assert np.abs(gp).max() < 1e-5 * max(1.0, ss["initial_cost"]) and len(ss["iterations"]) < 100    # a stationary point, reached before the cap
+
+
+@pytest.mark.parametrize("solver", [pgs.capi.SKYLINE_CHOLESKY, pgs.capi.BLOCK_PCG])
+def test_constant_parameter_blocks_match_oracle(solver):
+    """pgs_set_constant_nodes = ceres SetParameterBlockConstant (what PoseGraphSLAM::load_state does, PoseGraphSLAM.cpp:150-151):
+    zero Jacobian columns, untouched values, same trajectory and same minimum as the oracle with the same blocks fixed."""
+    g = random_graph(160, 3, 30, outlier_frac=0.1, seed=41)
+    O = load_oracle(g); O.set_constant_nodes(0, 70); O.set_constant_nodes(100, 3)
+    S = load_pgs(g, linear_solver=solver, pcg_tolerance=1e-12); S.set_constant_nodes(0, 70); S.set_constant_nodes(100, 3)
+    eo = O.evaluate(autodiff=True); es = S.evaluate()
+    for k in ("r_o", "J_o", "r_l", "J_l", "r_r", "J_r"):
+        assert rel_err(es[k], eo[k]) < 1e-12, k
+    assert np.all(es["J_o"][g["oc1"] < 70][:, :, :6] == 0) and np.any(es["J_o"][g["oc1"] >= 103][:, :, :6] != 0)
+    so = O.solve(); ss = S.solve()
+    assert ss["termination"] == so["termination"] and len(ss["iterations"]) == len(so["iterations"])
+    for a, b in zip(ss["iterations"], so["iterations"]):
+        assert a["step_is_successful"] == b["step_is_successful"]
+        assert abs(a["cost"] - b["cost"]) <= 1e-6 * max(1e-12, abs(b["cost"]))
+    qo, to = O.poses(); qs, ts = S.poses()
+    fixed = np.r_[0:70, 100:103]
+    assert np.array_equal(ts[fixed], g["t"][fixed]) and np.array_equal(qs[fixed], g["q"][fixed])      # bit for bit
+    assert np.abs(ts - to).max() < 1e-5 and rot_angle_between(qs, qo).max() < 1e-4
+    assert np.array_equal(S.switches() > 0.5, O.switches() > 0.5)
+    S.set_constant_nodes(0, 160, False)                                                                  # SetParameterBlockVariable
+    assert S.solve()["final_cost"] < ss["final_cost"]

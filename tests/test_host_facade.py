@@ -193,3 +193,32 @@ def test_ros_message_callbacks_build_the_same_session_as_the_plain_ingest():
     (qa, ta), (qb, tb) = A.poses(), B.poses()
     assert np.allclose(ta, tb, atol=1e-9) and [A.world_setid(w) for w in range(3)] == [B.world_setid(w) for w in range(3)]
     A.close(); B.close()
+
+
+def test_load_state_restores_a_constant_backbone(tmp_path):
+    # PoseGraphSLAM::load_state (src/PoseGraphSLAM.cpp:40-170) after a save / load round trip, dry run: variables of the
+    # restored keyframes sit at ws_T_w * w_T_c, solvedUntil is the last of them, and the next trigger only adds odometry
+    # edges for the keyframes that arrive afterwards — facade vs the oracle front-end
+    g = synth.generate_config(4, n_nodes=50, n_worlds=3, n_interworld=9)
+    A = facade.Facade(odom_fanout=3, dry_run=True); A.ingest(g); assert A.solve_once()          # merges the three worlds
+    assert A.save_json(tmp_path) & 1
+    M = frontend.Manager(); M.ingest(g)
+    R0 = frontend.ReferenceFrontEnd(M, odom_fanout=3); R0.trigger(solve=False)                  # same merges in the oracle's Worlds
+    F = facade.Facade(odom_fanout=3, dry_run=True)
+    F.load_worlds_state(tmp_path / "solved_posegraph.json")                                     # Worlds first (Composer.cpp:1137), then the keyframes
+    with pytest.raises(pgs.PgsError):
+        F.load_state()                                                                           # no keyframes yet (the reference exits)
+    F.close()
+    F = facade.Facade(odom_fanout=3, dry_run=True); F.load_posegraph_json(tmp_path); F.n_loop = len(g["la"])
+    R = frontend.ReferenceFrontEnd(M, odom_fanout=3)
+    # worlds of F are not merged yet (log_posegraph.json carries no relative poses): nodes of worlds 1, 2 have set id == world id
+    F.load_state(); R2 = frontend.ReferenceFrontEnd(frontend.Manager(), odom_fanout=3)
+    assert F.solved_until() == g["N"] - 1 and F.n_nodes() == g["N"]
+    q, t = F.poses()
+    assert np.allclose(t, g["t"], atol=1e-12)                                                    # ws_T_w = I while the worlds are separate
+    R.load_state()                                                                               # merged worlds: poses move into the set root's frame
+    ww = np.array([M.which_world_is_this(int(s)) for s in g["stamps"]])
+    moved = np.abs(np.array(R.opt_t) - g["t"]).max(axis=1) > 1e-9
+    root = M.worlds.find_setID_of_world_i(0)
+    assert R.solved_until == g["N"] - 1 and R.n_constant == g["N"] and not moved[ww == root].any() and moved[(ww >= 0) & (ww != root)].all()
+    F.close(); A.close()

@@ -71,3 +71,38 @@ def test_multi_world_session_matches_the_oracle_front_end():
     # dead-zone keyframes are in no residual block: their parameter blocks keep the initial guess in both
     _compare(F, R, len(g["la"]))
     F.close()
+
+
+def test_restored_session_is_a_constant_backbone_for_new_keyframes(tmp_path):
+    """load_state (PoseGraphSLAM.cpp:40-170) after a save / load round trip: the restored keyframes are constant blocks,
+    keyframes and loop edges that arrive afterwards are optimised against them — facade vs oracle front-end."""
+    g = synth.generate_config(2, n_nodes=700, n_loop=120)
+    cut = 450
+    first = {k: (v[:cut] if k in ("stamps", "q", "t") else v) for k, v in g.items()}; first["N"] = cut
+    keep = (g["la"] < cut) & (g["lb"] < cut)
+    for k in ("la", "lb", "lq", "lt", "lw"):
+        first[k] = g[k][keep]
+    A = facade.Facade(odom_fanout=3, dry_run=True); A.ingest(first)
+    assert A.save_json(tmp_path) & 1
+    F = facade.Facade(odom_fanout=3); F.load_posegraph_json(tmp_path); F.n_loop = int(keep.sum())
+    M = frontend.Manager(); M.ingest(first)
+    R = frontend.ReferenceFrontEnd(M, odom_fanout=3, options=pgo.default_options())
+    F.load_state(); R.load_state()
+    assert F.solved_until() == R.solved_until == cut - 1 and F.n_nodes() == cut
+    q0, t0 = F.poses()
+    # the rest of the session arrives
+    F.add_nodes(g["stamps"][cut:], g["q"][cut:], g["t"][cut:])
+    for i in range(cut, g["N"]):
+        M.add_node(g["stamps"][i], g["q"][i], g["t"][i])
+    late = np.where(~keep)[0]
+    F.add_loop_edges(g["la"][late], g["lb"][late], g["lq"][late], g["lt"][late], g["lw"][late])
+    for e in late:
+        M.add_loop_edge(g["la"][e], g["lb"][e], g["lq"][e], g["lt"][e], g["lw"][e])
+    assert F.solve_once()
+    so = R.trigger(solve=True); ss = F.summary()
+    assert ss["termination"] == so["termination"] and abs(ss["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]
+    q, t = F.poses()
+    assert np.array_equal(t[:cut], t0) and np.array_equal(q[:cut], q0)          # the backbone did not move
+    assert np.abs(t[cut:] - g["t"][cut:]).max() > 1e-3                          # the new keyframes did
+    _compare(F, R, len(g["la"]))
+    F.close(); A.close()
