@@ -225,4 +225,9 @@ bool loadSolvedPoseGraph(const std::string& file, SolvedPoseGraph* out, std::str
   return true;
 }
 
+// member spellings of the reference
+bool NodeDataManager::saveAsJSON(const std::string& base_path) const { return pgs::saveAsJSON(*this, base_path, nullptr); }
+bool NodeDataManager::loadFromJSON(const std::string& base_path, const std::vector<bool>& edge_mask) { return pgs::loadFromJSON(*this, base_path, edge_mask, true, nullptr); }
+bool PoseGraphSLAM::saveAsJSON(const std::string base_path) const { return pgs::saveAsJSON(*this, *manager, base_path, nullptr); }
+
 }  // namespace pgs

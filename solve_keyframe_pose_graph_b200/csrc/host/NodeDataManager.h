@@ -30,6 +30,10 @@ class NodeDataManager {
   bool add_loop_edge_by_index(int a, int b, const Matrix4d& b_T_a, double weight, const std::string& description = "");
   bool rcvd_kidnap_indicator(int64_t stamp_ns, bool kidnapped);
 
+  // ---- on-disk state (NodeDataManager.cpp:503-754); defined in GraphIO.cpp
+  bool saveAsJSON(const std::string& base_path) const;                                             // log_posegraph.json
+  bool loadFromJSON(const std::string& base_path, const std::vector<bool>& edge_mask = {});      // + kidnap signals replayed
+
   // ---- node getters
   int getNodeLen() const;
   bool getNodePose(int i, Matrix4d& w_T_cam) const;

@@ -52,6 +52,7 @@ class PoseGraphSLAM {
   // solvedUntil moved to the last of them (reference PoseGraphSLAM.cpp:40-170).  Later keyframes are optimised against
   // this fixed backbone.  false: no keyframes, or a world whose set transform is unknown (the reference exits).
   bool load_state();
+  bool saveAsJSON(const std::string base_path) const;      // log_optimized_poses.json (PoseGraphSLAM.cpp:1111-1207); defined in GraphIO.cpp
   const std::string& last_error() const { return error_; }
 
   // Explicit-graph API (north_star).  Poses are 4x4: a_T_b for odometry (binds SixDOFError(a, b)),
