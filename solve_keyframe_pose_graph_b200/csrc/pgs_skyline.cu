@@ -10,18 +10,18 @@
 // every (row, panel) intersection is a full PW-wide, 16-byte aligned segment.  One extra row n carries b^T:
 // factoring it along with the matrix performs the forward substitution for free (row n of L is (L^-1 b)^T).
 //
-// Right-looking by panels of PW columns; the panel chain runs one panel ahead of the bulk update on a second,
-// high-priority stream:
+// Right-looking by panels of PW columns on three streams; the panel chain runs one panel ahead of the bulk update:
 //   chain stream   C(d):     1 CTA.  Applies the one update the bulk has not yet given the diagonal block — the
 //                            rank-96 product of X[d, d-1] from trsm(d-1) — then L_dd = chol(A_dd) and Linv = L_dd^-1,
-//                            every matrix-shaped piece on FP64 tensor cores (DMMA).  Waits for trsm(d-1).
-//   main stream    trsm(d):  X = A[R, panel] * Linv^T for the rows R below the panel whose envelope reaches it.
+//                            every matrix-shaped piece on FP64 tensor cores (DMMA).  Waits for trsm(d-1), rest(d-2).
+//   panel stream   trsm(d):  X = A[R, panel] * Linv^T for the rows R below the panel whose envelope reaches it.
 //                            Waits for C(d).
-//                  update(d): A[r, c] -= X[r,:] . X[c,:] for r, c in R, c <= r, except the diagonal block of panel
-//                            d+1 (C(d+1) does that one itself, which is what lets it start right after trsm(d)
-//                            instead of after the whole update).  128x64 DMMA tiles, persistent CTAs fed by an
-//                            atomic tile counter, accumulators preloaded with A so the epilogue is a plain store.
-// so C(d+1) overlaps update(d) and the factorisation runs at max(C + trsm, trsm + update) per panel.
+//                  next(d):  the update tiles that hold the columns of panel d+1 (what trsm(d+1) needs), except the
+//                            diagonal block of panel d+1: C(d+1) does that one itself, which is what lets it start
+//                            right after trsm(d) instead of after the update.  Waits for rest(d-1).
+//   main stream    rest(d):  every other tile of A[r, c] -= X[r,:] . X[c,:], r, c in R, c <= r.  128x64 DMMA tiles,
+//                            accumulators preloaded with A so the epilogue is a plain store.  Waits for trsm(d).
+// so C(d+1), next(d) and rest(d) overlap, and a panel costs max(C + trsm, rest) (c3: ~55 us).
 // then a backward sweep (one launch per panel) solves L^T x = y.
 //
 // Partial factorisation (multi-GPU domain decomposition): only the first n_elim panels are
@@ -41,7 +41,6 @@ namespace pgs {
 constexpr int PW = 96;            // panel width in scalars = 16 nodes
 constexpr int PN = PW / 6;
 constexpr int TR = 32;            // trsm rows per CTA
-constexpr int LDP = PW + 2;       // padded leading dimension of PW-wide shared tiles: even (16-B rows), LDP/2 odd
 constexpr int LDT = PW + 4;       // 100 doubles = 200 words = 8 mod 32: conflict-free DMMA fragment loads (8 rows x 4 k per half-warp pair)
 constexpr int UM = 128, UN = 64;  // update tiles: rows x cols
 constexpr int KC = 32;            // update K chunk
