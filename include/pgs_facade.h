@@ -49,11 +49,18 @@ int pgs_facade_load_state(pgs_facade_handle h);
 /* one wake-up of the solver thread: 1 solved, 0 not triggered, <0 error */
 int pgs_facade_solve_once(pgs_facade_handle h, int32_t force);
 int pgs_facade_status(pgs_facade_handle h);
+/* The way keyframe_pose_graph_slam_node.cpp runs the solver (:353,475-477,494,505): enable, run
+ * reinit_ceres_problem_onnewloopedge_optimize6DOF() on its own std::thread polling at rate_hz (the reference's 0.5 Hz
+ * when rate_hz <= 0), disable + join.  Ingest calls and getters may be used concurrently from other threads. */
+int pgs_facade_thread_start(pgs_facade_handle h, double rate_hz);
+int pgs_facade_thread_stop(pgs_facade_handle h);      /* returns the number of solves the thread triggered */
 
 /* results (PoseGraphSLAM getters) */
 int32_t pgs_facade_n_nodes(pgs_facade_handle h);
 int32_t pgs_facade_solved_until(pgs_facade_handle h);
-int pgs_facade_get_poses(pgs_facade_handle h, double* q_xyzw, double* t);     /* all nNodes() */
+/* getAllNodePose: the first min(nNodes(), cap) optimised poses; returns how many were written (the solver thread may
+ * append variables between a pgs_facade_n_nodes() call and this one, hence the capacity) */
+int pgs_facade_get_poses(pgs_facade_handle h, int32_t cap, double* q_xyzw, double* t);
 int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s);       /* per manager loop edge */
 int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* iters, int32_t cap);
 

@@ -8,6 +8,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -65,14 +66,16 @@ class NodeDataManager {
   int which_world_nolock(int64_t t) const;
 
   mutable std::mutex node_mutex;
-  std::vector<Matrix4d> node_pose;
-  std::vector<int64_t> node_timestamps;
+  // deques: the getters hand out references (as the reference's do) while the ingest thread appends; a deque's
+  // push_back never moves existing elements, a vector's reallocation would leave those references dangling
+  std::deque<Matrix4d> node_pose;
+  std::deque<int64_t> node_timestamps;
 
   mutable std::mutex edge_mutex;
-  std::vector<std::pair<int, int>> loopclosure_edges;
-  std::vector<double> loopclosure_edges_goodness;
-  std::vector<Matrix4d> loopclosure_p_T_c;
-  std::vector<std::string> loopclosure_description;
+  std::deque<std::pair<int, int>> loopclosure_edges;
+  std::deque<double> loopclosure_edges_goodness;
+  std::deque<Matrix4d> loopclosure_p_T_c;
+  std::deque<std::string> loopclosure_description;
 
   mutable std::mutex mutex_kidnap;
   std::vector<int64_t> kidnap_starts, kidnap_ends;

@@ -78,7 +78,7 @@ bool PoseGraphSLAM::addLoopEdge(int a, int b, const Matrix4d& b_T_a, double weig
 void PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF() {
   const auto period = std::chrono::duration<double>(1.0 / std::max(1e-3, opt_.loop_rate_hz));
   while (isEnabled) {
-    solve_once(false);
+    if (solve_once(false)) ++n_solves_;
     status = 0;
     std::this_thread::sleep_for(period);
   }

@@ -43,6 +43,8 @@ class PoseGraphSLAM {
   void reinit_ceres_problem_onnewloopedge_optimize6DOF_disable() { isEnabled = false; }
   // -1 nothing happening, 0 sleeping, 1 setting up, 2 solve in progress, 3 solve finished (PoseGraphSLAM.h:100-105)
   int get_reinit_ceres_problem_onnewloopedge_optimize6DOF_status() { return status; }
+  void set_loop_rate_hz(double hz) { if (hz > 0) opt_.loop_rate_hz = hz; }   // the reference hard-codes 0.5 Hz (:1257)
+  int n_solves() const { return n_solves_; }
 
   // One wake-up of the loop above.  Returns true if a solve was triggered.  force = solve even without
   // new loop edges.  On failure returns false and last_error() is non-empty.
@@ -94,6 +96,7 @@ class PoseGraphSLAM {
   PoseGraphSLAMOptions opt_;
   std::atomic<bool> isEnabled;
   std::atomic<int> status;
+  std::atomic<int> n_solves_{0};
   std::string error_;
 
   mutable std::mutex mutex_opt_vars;

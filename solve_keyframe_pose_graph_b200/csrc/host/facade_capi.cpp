@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "Composer.h"
 #include "GraphIO.h"
@@ -15,9 +17,11 @@ struct pgs_facade_s {
   pgs::NodeDataManager manager;
   pgs::PoseGraphSLAM* slam = nullptr;
   pgs::Composer* composer = nullptr;
+  std::thread solver_thread;
   int device = 0;
   std::string err;
-  ~pgs_facade_s() { delete composer; delete slam; }
+  void stop_thread() { if (solver_thread.joinable()) { slam->reinit_ceres_problem_onnewloopedge_optimize6DOF_disable(); solver_thread.join(); } }
+  ~pgs_facade_s() { stop_thread(); delete composer; delete slam; }
 };
 
 extern "C" {
@@ -101,15 +105,30 @@ int pgs_facade_solve_once(pgs_facade_handle h, int32_t force) {
   if (!ok && !h->slam->last_error().empty()) return PGS_ERR_STATE;
   return ok ? 1 : 0;
 }
+int pgs_facade_thread_start(pgs_facade_handle h, double rate_hz) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  if (h->solver_thread.joinable()) return PGS_ERR_STATE;
+  h->slam->set_loop_rate_hz(rate_hz);
+  h->slam->reinit_ceres_problem_onnewloopedge_optimize6DOF_enable();
+  h->solver_thread = std::thread(&pgs::PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF, h->slam);
+  return PGS_OK;
+}
+int pgs_facade_thread_stop(pgs_facade_handle h) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  h->stop_thread();
+  return h->slam->n_solves();
+}
 int pgs_facade_status(pgs_facade_handle h) { return h ? h->slam->get_reinit_ceres_problem_onnewloopedge_optimize6DOF_status() : -1; }
 int32_t pgs_facade_n_nodes(pgs_facade_handle h) { return h ? h->slam->nNodes() : 0; }
 int32_t pgs_facade_solved_until(pgs_facade_handle h) { return h ? h->slam->solvedUntil() : 0; }
-int pgs_facade_get_poses(pgs_facade_handle h, double* q, double* t) {
-  if (!h) return PGS_ERR_INVALID_ARGUMENT;
-  const int n = h->slam->nNodes();
-  for (int i = 0; i < n; ++i) { double qq[4], tt[3]; pgs::mat_to_raw_xyzw(h->slam->getNodePose(i), qq, tt);
-    if (q) std::memcpy(q + 4 * (size_t)i, qq, 32); if (t) std::memcpy(t + 3 * (size_t)i, tt, 24); }
-  return PGS_OK;
+int pgs_facade_get_poses(pgs_facade_handle h, int32_t cap, double* q, double* t) {
+  if (!h || cap < 0) return PGS_ERR_INVALID_ARGUMENT;
+  std::vector<double> qq, tt;
+  h->slam->getAllNodeRaw(qq, tt);                       // one consistent snapshot under the variables' mutex
+  const int n = std::min<int>((int)(tt.size() / 3), cap);
+  if (q && n) std::memcpy(q, qq.data(), sizeof(double) * 4 * (size_t)n);
+  if (t && n) std::memcpy(t, tt.data(), sizeof(double) * 3 * (size_t)n);
+  return n;
 }
 int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s) {
   if (!h || !s) return PGS_ERR_INVALID_ARGUMENT;

@@ -116,6 +116,12 @@ class Facade:
     def solve_once(self, force=False):
         return self._ck(self.L.pgs_facade_solve_once(self.h, C.c_int32(int(force)))) == 1
 
+    def thread_start(self, rate_hz=0.0):
+        self._ck(self.L.pgs_facade_thread_start(self.h, C.c_double(rate_hz)))
+
+    def thread_stop(self):
+        return self._ck(self.L.pgs_facade_thread_stop(self.h))
+
     def status(self):
         return self.L.pgs_facade_status(self.h)
 
@@ -127,9 +133,9 @@ class Facade:
         return self.L.pgs_facade_solved_until(self.h)
 
     def poses(self):
-        n = self.n_nodes(); q = np.zeros((n, 4)); t = np.zeros((n, 3))
-        self._ck(self.L.pgs_facade_get_poses(self.h, q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp)))
-        return q, t
+        n = self.n_nodes(); q = np.zeros((max(n, 1), 4)); t = np.zeros((max(n, 1), 3))
+        m = self._ck(self.L.pgs_facade_get_poses(self.h, C.c_int32(n), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp)))
+        return q[:m], t[:m]
 
     def switches(self):
         s = np.zeros(max(self.n_loop, 1))

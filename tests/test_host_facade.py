@@ -222,3 +222,40 @@ def test_load_state_restores_a_constant_backbone(tmp_path):
     root = M.worlds.find_setID_of_world_i(0)
     assert R.solved_until == g["N"] - 1 and R.n_constant == g["N"] and not moved[ww == root].any() and moved[(ww >= 0) & (ww != root)].all()
     F.close(); A.close()
+
+
+def test_solver_thread_with_concurrent_ingest_and_getters():
+    # the reference's threading model (keyframe_pose_graph_slam_node.cpp:353,475-477): the solver polls on its own thread
+    # while the ROS callbacks append keyframes / loop edges and the Composer reads poses.  Dry run, 500 Hz polling.
+    import threading, time
+    g = synth.generate_config(2, n_nodes=400, n_loop=60)
+    order = np.argsort(np.maximum(g["la"], g["lb"]), kind="stable")
+    F = facade.Facade(odom_fanout=3, dry_run=True)
+    F.thread_start(500.0)
+    stop = False; seen = []
+    def reader():                                   # what the Composer / Viz threads do at 30 Hz
+        while not stop:
+            n = F.n_nodes()
+            if n:
+                q, t = F.poses(); assert len(t) >= n and np.isfinite(t).all()
+            seen.append((F.status(), F.solved_until()))
+    th = threading.Thread(target=reader); th.start()
+    epos = 0
+    for lo in range(0, 400, 50):
+        F.add_nodes(g["stamps"][lo:lo + 50], g["q"][lo:lo + 50], g["t"][lo:lo + 50])
+        take = []
+        while epos < len(order) and max(g["la"][order[epos]], g["lb"][order[epos]]) < lo + 50:
+            take.append(order[epos]); epos += 1
+        if take:
+            take = np.array(take); F.add_loop_edges(g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
+        time.sleep(0.02)
+    time.sleep(0.1)
+    n_solves = F.thread_stop(); stop = True; th.join()
+    assert n_solves >= 2 and epos == len(order)
+    assert F.solved_until() == 399 and F.n_nodes() == 400 and F.status() in (0, 3)
+    assert all(s in (-1, 0, 1, 2, 3) for s, _ in seen) and [u for _, u in seen] == sorted(u for _, u in seen)   # solvedUntil never goes back
+    # same graph as a single sequential trigger: same odometry terms (order aside) and the same final guesses for the last chunk
+    G = facade.Facade(odom_fanout=3, dry_run=True); G.ingest(g); assert G.solve_once()
+    a, b = F.odom_terms(), G.odom_terms()
+    assert sorted(zip(a["u"].tolist(), a["umf"].tolist())) == sorted(zip(b["u"].tolist(), b["umf"].tolist()))
+    F.close(); G.close()
