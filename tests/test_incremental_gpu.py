@@ -124,7 +124,8 @@ def test_solver_thread_on_the_device_with_concurrent_ingest_composer_and_getters
                 if F.n_keyframes():
                     T, wid = F.compose()
                     assert np.isfinite(T).all() and np.allclose(T[:, 3, :], [0, 0, 0, 1]) and len(T) == len(wid)
-                    q, t = F.poses(); assert np.isfinite(t).all() and abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-9
+                    q, t = F.poses()                     # empty until the first trigger has allocated variables
+                    assert np.isfinite(t).all() and (len(q) == 0 or abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-9)
                     passes[0] += 1
         except Exception as ex:   # surfaced in the main thread
             errors.append(ex)
