@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import frontend, pgo
+import solve_keyframe_pose_graph_b200 as pgs
 from solve_keyframe_pose_graph_b200 import facade, synth
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_solved_posegraph_sample.json")
@@ -91,4 +92,22 @@ def test_solved_posegraph_written_after_a_device_compose(tmp_path):
     for m_ in range(3):
         for n_ in range(3):
             assert np.allclose(G.pose_between_worlds(m_, n_), F.pose_between_worlds(m_, n_), atol=1e-9)
+    F.close(); G.close()
+
+
+def test_worlds_op_log_example_from_the_reference_replays(tmp_path):
+    # the example the reference gives for the union-find op-log (src/Worlds.cpp:549-554)
+    state = {"WorldsData": {"rel_pose_between_worlds__wb_T_wa": [], "vec_world_starts": [{"stampNSec": 10}, {"stampNSec": 20}, {"stampNSec": 30}],
+                            "vec_world_ends": [{"stampNSec": 15}, {"stampNSec": 25}],
+                            "disjoint_set": {"debug_string": "\\t\\t\\tadd_element( 0)\\n\\t\\t\\tadd_element( 1)\\n\\t\\t\\tadd_element( 2)\\n\\t\\t\\tunion_sets( 0,2)\\n",
+                                             "log_string": "add_element:0;add_element:1;add_element:2;union_sets:0,2;"}}}
+    f = tmp_path / "solved_posegraph.json"; f.write_text(json.dumps(state))
+    F = facade.Facade(dry_run=True); F.load_worlds_state(f)
+    # union_sets(max, min) with link-by-rank: on the tie world 0 stays the root (src/Worlds.cpp:168, DisjointSet.h:241-257)
+    assert [F.world_setid(w) for w in range(4)] == [0, 1, 0, -1]
+    bad = dict(state); bad["WorldsData"] = dict(state["WorldsData"], disjoint_set={"debug_string": "", "log_string": "add_element:0;merge:0,1;"})
+    g = tmp_path / "bad.json"; g.write_text(json.dumps(bad))
+    G = facade.Facade(dry_run=True)
+    with pytest.raises(pgs.PgsError, match="unknown op"):
+        G.load_worlds_state(g)
     F.close(); G.close()
