@@ -259,3 +259,27 @@ def test_solver_thread_with_concurrent_ingest_and_getters():
     a, b = F.odom_terms(), G.odom_terms()
     assert sorted(zip(a["u"].tolist(), a["umf"].tolist())) == sorted(zip(b["u"].tolist(), b["umf"].tolist()))
     F.close(); G.close()
+
+
+def test_explicit_graph_api_add_odometry_edge_and_add_loop_edge():
+    # north_star's explicit-graph entry points (absent in the reference): with derive_odometry off the problem contains
+    # exactly the blocks that were added, in order, and a trigger fires on explicit odometry edges alone
+    g = synth.generate_config(1)                                  # 50-node chain, one loop edge
+    F = facade.Facade(odom_fanout=5, derive_odometry=False, dry_run=True)
+    F.add_nodes(g["stamps"], g["q"], g["t"])
+    assert not F.solve_once()                                     # nothing to solve yet
+    rng = np.random.default_rng(0)
+    added = []
+    for u in range(1, g["N"]):
+        q = rng.normal(size=4); q /= np.linalg.norm(q); t = rng.normal(size=3); w = float(rng.uniform(0.1, 1.0))
+        F.add_odometry_edge(u, u - 1, q, t, w); added.append((u, u - 1, q, t, w))
+    with pytest.raises(pgs.PgsError):
+        F.add_odometry_edge(3, 99, [0, 0, 0, 1.0], [0, 0, 0.0], 1.0)   # node out of range
+    assert F.solve_once()                                         # explicit odometry edges alone trigger
+    o = F.odom_terms()
+    assert list(o["u"]) == [a[0] for a in added] and list(o["umf"]) == [a[1] for a in added]
+    assert np.allclose(o["w"], [a[4] for a in added]) and np.allclose(o["t"], np.array([a[3] for a in added]), atol=1e-12)
+    assert np.all(np.abs(np.sum(o["q"] * np.array([a[2] for a in added]), axis=1)) > 1 - 1e-12)
+    F.add_loop_edges(g["la"], g["lb"], g["lq"], g["lt"], g["lw"])  # addLoopEdge: stored in the manager, bound as (b, a, switch)
+    assert F.solve_once() and len(F.odom_terms()["u"]) == len(added)   # no derived odometry was added behind our back
+    F.close()

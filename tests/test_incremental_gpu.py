@@ -150,3 +150,30 @@ def test_solver_thread_on_the_device_with_concurrent_ingest_composer_and_getters
     assert np.abs(t - g["gt_t"]).max() < np.abs(g["t"] - g["gt_t"]).max() + 1e-6      # loop closures pulled the drift in, not out
     sw = F.switches(); assert (sw > 0.5).mean() > 0.9                                  # no outliers in this graph: edges stay on
     F.close()
+
+
+def test_explicit_graph_through_the_facade_matches_the_solver_and_the_oracle():
+    """addOdometryEdge / addLoopEdge (the entry points north_star names): the same explicit graph through the facade
+    (derive_odometry off), through the raw C-ABI solver and through the oracle."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util_graphs import load_oracle, load_pgs, random_graph, rot_angle_between
+    g = random_graph(150, 3, 25, outlier_frac=0.1, seed=51, reg=False)
+    F = facade.Facade(derive_odometry=False)
+    stamps = (np.arange(g["N"], dtype=np.int64) + 10) * 10**8
+    F.add_nodes(stamps, g["q"], g["t"])
+    for e in range(len(g["oc1"])):
+        F.add_odometry_edge(int(g["oc1"][e]), int(g["oc2"][e]), g["oq"][e], g["ot"][e], float(g["ow"][e]))
+    F.add_loop_edges(g["la"], g["lb"], g["lq"], g["lt"], g["lw"])
+    assert F.solve_once()
+    r = F.reg_terms()                                   # the facade anchors the set root itself (PoseGraphSLAM.cpp:1801-1850)
+    g2 = dict(g, rn=r["node"], rq=r["q"], rt=r["t"], rw=r["w"])
+    O = load_oracle(g2); so = O.solve()
+    S = load_pgs(g2); ss = S.solve()
+    fs = F.summary()
+    assert fs["termination"] == so["termination"] == ss["termination"]
+    assert abs(fs["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"] and abs(ss["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]
+    q, t = F.poses(); qo, to = O.poses()
+    assert np.abs(t - to).max() < 1e-5 and rot_angle_between(q, qo).max() < 1e-4
+    assert np.array_equal(F.switches() > 0.5, O.switches() > 0.5)
+    F.close(); S.close()
