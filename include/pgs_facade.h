@@ -37,7 +37,8 @@ int pgs_facade_add_odometry_edge(pgs_facade_handle h, int32_t a, int32_t b, cons
 
 /* ROS-message entry points (csrc/host/RosShim.h): the fields of nav_msgs/Odometry, LoopEdge.msg and std_msgs/Header
  * as plain arguments, routed through the reference's callback names.  frame_id: "kidnapped" / "unkidnapped". */
-int pgs_facade_camera_pose_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const double* position_xyz, const double* orientation_xyzw);
+int pgs_facade_camera_pose_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const double* position_xyz, const double* orientation_xyzw,
+                                    const double* covariance36 /* pose.covariance, may be NULL */);
 int pgs_facade_loopclosure_pose_callback(pgs_facade_handle h, uint32_t sec0, uint32_t nsec0, uint32_t sec1, uint32_t nsec1, const double* position_xyz,
                                          const double* orientation_xyzw, float weight, const char* description);   /* 1 added, 0 dropped */
 int pgs_facade_rcvd_kidnap_indicator_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const char* frame_id);

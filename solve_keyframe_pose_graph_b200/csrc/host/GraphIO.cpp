@@ -56,7 +56,8 @@ bool saveAsJSON(const NodeDataManager& m, const std::string& base_path, std::str
   Json all;
   all["meta_data"]["getNodeLen"] = Json(m.getNodeLen());
   all["meta_data"]["getEdgeLen"] = Json(m.getEdgeLen());
-  const std::string zero_cov = [] { std::string s; for (int r = 0; r < 6; ++r) { for (int c = 0; c < 6; ++c) { s += "0"; if (c < 5) s += ","; } if (r < 5) s += ";"; } return s; }();
+  auto cov_string = [](const double* c36) { std::string s; char b[40];
+    for (int r = 0; r < 6; ++r) { for (int c = 0; c < 6; ++c) { snprintf(b, sizeof(b), "%.16g", c36[6 * r + c]); s += b; if (c < 5) s += ","; } if (r < 5) s += ";"; } return s; };
   all["nodes"] = Json::array();
   for (int i = 0; i < m.getNodeLen(); ++i) {
     Json node;
@@ -66,7 +67,8 @@ bool saveAsJSON(const NodeDataManager& m, const std::string& base_path, std::str
     const Matrix4d& wTc = m.getNodePose(i);
     node["wTc"] = Json(mat_to_string(wTc));
     node["wTc_pretty"] = Json(prettyprintMatrix4d(wTc));
-    node["cov"] = Json(zero_cov);                       // covariances are not kept (the reference writes an uninitialised matrix here, :531-535)
+    double cov[36] = {}; m.getNodeCov(i, cov);
+    node["cov"] = Json(cov_string(cov));                // the reference serialises cov BEFORE reading it (:531-535): its files hold garbage here
     all["nodes"].push_back(node);
   }
   all["loopedges"] = Json::array();
@@ -132,7 +134,13 @@ bool loadFromJSON(NodeDataManager& m, const std::string& base_path, const std::v
     while (k < ev.size() && ev[k].first < st) { m.rcvd_kidnap_indicator(ev[k].first, ev[k].second != 0); ++k; }
     Matrix4d wTc;
     if (!string_to_mat(nodes[i].at("wTc").as_string(), wTc)) return set_err(err, "node " + std::to_string(i) + ": wTc is not a 4x4 matrix string");
-    m.add_node(st, wTc);
+    double cov[36] = {}; bool have_cov = false;          // cov: 6x6 as "a,..;..." (PoseManipUtils.cpp:298-320); tolerate the reference's garbage
+    if (nodes[i].contains("cov")) {
+      std::vector<double> v; std::string tok;
+      for (char c : nodes[i].at("cov").as_string() + ";") { if (c == ',' || c == ';') { if (!tok.empty()) { try { v.push_back(std::stod(tok)); } catch (...) { v.clear(); break; } tok.clear(); } } else if (c != ' ') tok.push_back(c); }
+      if (v.size() == 36) { for (int k = 0; k < 36; ++k) cov[k] = v[k]; have_cov = true; }
+    }
+    m.add_node(st, wTc, have_cov ? cov : nullptr);
   }
   while (k < ev.size()) { m.rcvd_kidnap_indicator(ev[k].first, ev[k].second != 0); ++k; }
   for (size_t i = 0; i < edges.size(); ++i) {

@@ -7,10 +7,13 @@ namespace pgs {
 NodeDataManager::NodeDataManager() : current_kidnap_status(false) { worlds_handle_raw_ptr = new Worlds(); }
 NodeDataManager::~NodeDataManager() { delete worlds_handle_raw_ptr; }
 
-void NodeDataManager::add_node(int64_t stamp_ns, const Matrix4d& w_T_cam) {
+void NodeDataManager::add_node(int64_t stamp_ns, const Matrix4d& w_T_cam, const double* cov36) {
   std::lock_guard<std::mutex> lk(node_mutex);
   node_timestamps.push_back(stamp_ns);
   node_pose.push_back(w_T_cam);
+  std::array<double, 36> cov{};                                                 // NodeDataManager.cpp:55-63
+  if (cov36) for (int k = 0; k < 36; ++k) cov[k] = cov36[k];
+  node_pose_covariance.push_back(cov);
   if (node_pose.size() == 1) worlds_handle_raw_ptr->world_starts(stamp_ns);   // fresh start: world 0 (NodeDataManager.cpp:80-84)
 }
 
@@ -60,6 +63,12 @@ bool NodeDataManager::getNodePose(int i, Matrix4d& w_T_cam) const {
   w_T_cam = node_pose[i]; return true;
 }
 const Matrix4d& NodeDataManager::getNodePose(int i) const { std::lock_guard<std::mutex> lk(node_mutex); return node_pose[i]; }
+bool NodeDataManager::getNodeCov(int i, double* cov36) const {
+  std::lock_guard<std::mutex> lk(node_mutex);
+  if (i < 0 || i >= (int)node_pose_covariance.size() || !cov36) return false;
+  for (int k = 0; k < 36; ++k) cov36[k] = node_pose_covariance[i][k];
+  return true;
+}
 bool NodeDataManager::nodePoseExists(int i) const { std::lock_guard<std::mutex> lk(node_mutex); return i >= 0 && i < (int)node_pose.size(); }
 int64_t NodeDataManager::getNodeTimestamp(int i) const {
   std::lock_guard<std::mutex> lk(node_mutex);

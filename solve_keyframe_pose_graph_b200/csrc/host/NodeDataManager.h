@@ -4,8 +4,9 @@
 //   camera_pose_callback          (NodeDataManager.cpp:23-103)  -> add_node()
 //   loopclosure_pose_callback     (NodeDataManager.cpp:107-189) -> add_loop_edge() (timestamp lookup, 1 ms tolerance)
 //   rcvd_kidnap_indicator_callback(NodeDataManager.cpp:763-792) -> rcvd_kidnap_indicator()
-// Covariances, JSON and extrinsics are out of scope (never read by the solver).
+// Covariances are stored and round-trip through the state file but are never read by the solver; extrinsics are out of scope.
 #pragma once
+#include <array>
 #include <atomic>
 #include <cstdint>
 #include <deque>
@@ -25,7 +26,8 @@ class NodeDataManager {
   ~NodeDataManager();
 
   // ---- ingest
-  void add_node(int64_t stamp_ns, const Matrix4d& w_T_cam);
+  // cov36: row-major 6x6 pose covariance of the Odometry message (kept for the state file only; the solver never reads it)
+  void add_node(int64_t stamp_ns, const Matrix4d& w_T_cam, const double* cov36 = nullptr);
   // Returns false (edge dropped) when either timestamp matches no node, as the reference does (:181-185).
   bool add_loop_edge(int64_t stamp_a_ns, int64_t stamp_b_ns, const Matrix4d& b_T_a, double weight, const std::string& description = "");
   bool add_loop_edge_by_index(int a, int b, const Matrix4d& b_T_a, double weight, const std::string& description = "");
@@ -40,6 +42,7 @@ class NodeDataManager {
   bool getNodePose(int i, Matrix4d& w_T_cam) const;
   const Matrix4d& getNodePose(int i) const;
   bool nodePoseExists(int i) const;
+  bool getNodeCov(int i, double* cov36) const;               // reference NodeDataManager.cpp:363-381
   int64_t getNodeTimestamp(int i) const;
   // ---- edge getters
   int getEdgeLen() const;
@@ -70,6 +73,7 @@ class NodeDataManager {
   // push_back never moves existing elements, a vector's reallocation would leave those references dangling
   std::deque<Matrix4d> node_pose;
   std::deque<int64_t> node_timestamps;
+  std::deque<std::array<double, 36>> node_pose_covariance;
 
   mutable std::mutex edge_mutex;
   std::deque<std::pair<int, int>> loopclosure_edges;

@@ -6,7 +6,7 @@
 //   from 1"; float32 weight; string description) -> loopclosure_pose_callback (:107-189)
 //   std_msgs/Header with frame_id "kidnapped" / "unkidnapped" -> rcvd_kidnap_indicator_callback (:763-792)
 // Quaternions arrive as (x,y,z,w) fields and are assembled with Eigen's Quaterniond(w,x,y,z) constructor order, as
-// the reference does (:36-41,131-133).  Covariances are dropped (never read by the solver).
+// the reference does (:36-41,131-133).  The pose covariance is stored with the keyframe (state file only).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -31,7 +31,7 @@ inline Matrix4d pose_to_mat(const Pose& p) {
   return raw_xyzw_to_mat(q, t);
 }
 
-inline void camera_pose_callback(NodeDataManager& m, const Odometry& msg) { m.add_node(msg.header.stamp.toNSec(), pose_to_mat(msg.pose.pose)); }
+inline void camera_pose_callback(NodeDataManager& m, const Odometry& msg) { m.add_node(msg.header.stamp.toNSec(), pose_to_mat(msg.pose.pose), msg.pose.covariance); }
 // false: one of the two timestamps matched no keyframe within 1 ms and the edge was dropped (:181-185)
 inline bool loopclosure_pose_callback(NodeDataManager& m, const LoopEdge& msg) {
   return m.add_loop_edge(msg.timestamp0.toNSec(), msg.timestamp1.toNSec(), pose_to_mat(msg.pose_1T0), (double)msg.weight, msg.description);

@@ -75,9 +75,10 @@ static pgs::ros_shim::Pose make_pose(const double* p, const double* q) {
   P.orientation.x = q[0]; P.orientation.y = q[1]; P.orientation.z = q[2]; P.orientation.w = q[3];
   return P;
 }
-int pgs_facade_camera_pose_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const double* p, const double* q) {
+int pgs_facade_camera_pose_callback(pgs_facade_handle h, uint32_t sec, uint32_t nsec, const double* p, const double* q, const double* cov36) {
   if (!h || !p || !q) return PGS_ERR_INVALID_ARGUMENT;
   pgs::ros_shim::Odometry msg; msg.header.stamp.sec = sec; msg.header.stamp.nsec = nsec; msg.pose.pose = make_pose(p, q);
+  if (cov36) std::memcpy(msg.pose.covariance, cov36, sizeof(double) * 36);
   pgs::ros_shim::camera_pose_callback(h->manager, msg);
   return PGS_OK;
 }

@@ -80,9 +80,12 @@ class Facade:
         self._ck(self.L.pgs_facade_add_odometry_edge(self.h, C.c_int32(a), C.c_int32(b), qp, tp, C.c_double(w)))
 
     # ---- ROS-message entry points (reference callback names, csrc/host/RosShim.h)
-    def camera_pose_callback(self, stamp_ns, position, orientation_xyzw):
+    def camera_pose_callback(self, stamp_ns, position, orientation_xyzw, covariance=None):
         p, pp = _d(position); q, qp = _d(orientation_xyzw)
-        self._ck(self.L.pgs_facade_camera_pose_callback(self.h, C.c_uint32(int(stamp_ns) // 10**9), C.c_uint32(int(stamp_ns) % 10**9), pp, qp))
+        cp = None
+        if covariance is not None:
+            cov, cp = _d(np.asarray(covariance).reshape(36))
+        self._ck(self.L.pgs_facade_camera_pose_callback(self.h, C.c_uint32(int(stamp_ns) // 10**9), C.c_uint32(int(stamp_ns) % 10**9), pp, qp, cp))
 
     def loopclosure_pose_callback(self, stamp0_ns, stamp1_ns, position, orientation_xyzw, weight=1.0, description=""):
         p, pp = _d(position); q, qp = _d(orientation_xyzw)

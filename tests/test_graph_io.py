@@ -111,3 +111,22 @@ def test_worlds_op_log_example_from_the_reference_replays(tmp_path):
     with pytest.raises(pgs.PgsError, match="unknown op"):
         G.load_worlds_state(g)
     F.close(); G.close()
+
+
+def test_pose_covariance_round_trips_through_log_posegraph(tmp_path):
+    # nav_msgs/Odometry pose.covariance is kept with the keyframe (NodeDataManager.cpp:55-63) and written as a 6x6 string
+    rng = np.random.default_rng(2)
+    F = facade.Facade(dry_run=True)
+    covs = []
+    for i in range(5):
+        A = rng.normal(size=(6, 6)); cov = A @ A.T; covs.append(cov)
+        F.camera_pose_callback(10**9 + i * 10**8, [float(i), 0.0, 0.0], [0, 0, 0, 1.0], cov)
+    F.save_json(tmp_path)
+    J = json.load(open(tmp_path / "log_posegraph.json"))
+    for i, n in enumerate(J["nodes"]):
+        M = np.array([[float(x) for x in row.split(",")] for row in n["cov"].split(";")])
+        assert M.shape == (6, 6) and np.allclose(M, covs[i], rtol=1e-15, atol=0)
+    G = facade.Facade(dry_run=True); G.load_posegraph_json(tmp_path); G.save_json(tmp_path / "..")
+    J2 = json.load(open(tmp_path / ".." / "log_posegraph.json"))
+    assert [n["cov"] for n in J2["nodes"]] == [n["cov"] for n in J["nodes"]]
+    F.close(); G.close()
