@@ -65,10 +65,30 @@ class Iteration(C.Structure):
     ]
 
 
+def _host_arch():
+    """What -march=native means on this host (the Makefile stores the same string beside the library)."""
+    try:
+        out = subprocess.run(["g++", "-march=native", "-Q", "--help=target"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            if "-march=" in line:
+                return "".join(line.split())
+    except (OSError, subprocess.SubprocessError):
+        pass
+    return None
+
+
 def build(force=False):
     so = os.path.join(_HERE, "libpgo.so")
     srcs = [os.path.join(_HERE, f) for f in ("pgo_capi.cpp", "pgo_core.hpp", "pgo_solver.hpp")]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if not stale:   # built with -march=native on another machine (the library travels with the repo snapshot)?
+        try:
+            built_for = open(so + ".arch").read().strip()
+        except OSError:
+            built_for = None
+        here = _host_arch()
+        stale = here is not None and built_for != here
+    if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return so
 
@@ -76,9 +96,7 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "libpgo.so")
-        if not os.path.exists(so):
-            build()
+        so = build()
         L = C.CDLL(so)
         L.pgo_create.restype = C.c_void_p
         L.pgo_evaluate.restype = C.c_double
