@@ -112,3 +112,62 @@ def test_oracle_reproduces_committed_golden(name):
     assert np.allclose(d["iter_radius"], G["iter_radius"], rtol=1e-9)
     assert np.abs(d["t"] - G["t"]).max() < 1e-7 and np.abs(d["switches"] - G["switches"]).max() < 1e-7
     assert np.allclose(d["J_o_head"], G["J_o_head"], atol=1e-12) and np.allclose(d["J_l_head"], G["J_l_head"], atol=1e-12)
+
+
+def _scipy_residual_vector(g):
+    """The whole residual vector of the reference's problem (CeresResidues.h:47-66,105-127,186-198) written with scipy
+    rotations and 4x4 matrices only: nothing of the oracle's code is involved.  x = [q (4N), t (3N), s (El)]; the
+    quaternions are normalised inside, so the ambient problem has the manifold problem's stationary points."""
+    from scipy.spatial.transform import Rotation as Rot
+    N, El = g["N"], len(g["la"])
+
+    def edge(q1, t1, q2, t2, oq, ot):
+        R1, R2, Ro = Rot.from_quat(q1), Rot.from_quat(q2), Rot.from_quat(oq)
+        R12 = R1.inv() * R2
+        dq = (R12.inv() * Ro).as_quat()
+        dq = dq if dq[3] >= 0 else -dq                           # the sign Hamilton products give near the solution
+        return np.r_[R12.inv().apply(ot - R1.inv().apply(t2 - t1)), 2 * dq[:3]]
+
+    def T44(q, t):
+        T = np.eye(4); T[:3, :3] = Rot.from_quat(q).as_matrix(); T[:3, 3] = t; return T
+
+    def fun(x):
+        q = x[:4 * N].reshape(N, 4); q = q / np.linalg.norm(q, axis=1, keepdims=True)
+        t = x[4 * N:7 * N].reshape(N, 3); s = x[7 * N:]
+        out = []
+        for e in range(len(g["oc1"])):
+            a, b = g["oc1"][e], g["oc2"][e]
+            out.append(g["ow"][e] * edge(q[a], t[a], q[b], t[b], g["oq"][e], g["ot"][e]))
+        for e in range(El):
+            c1, c2 = g["lb"][e], g["la"][e]                        # loop edge (a,b) is bound as (b,a), PoseGraphSLAM.cpp:1553-1554
+            out.append(s[e] * np.r_[edge(q[c1], t[c1], q[c2], t[c2], g["lq"][e], g["lt"][e]), 1.0 - s[e]])
+        for k in range(len(g["rn"])):
+            D = np.linalg.inv(T44(g["rq"][k], g["rt"][k])) @ T44(q[g["rn"][k]], t[g["rn"][k]])
+            dq = Rot.from_matrix(D[:3, :3]).as_quat(); dq = dq if dq[3] >= 0 else -dq
+            out.append(g["rw"][k] * np.r_[D[:3, 3], 2 * dq[:3]])
+        return np.concatenate(out)
+    return fun
+
+
+def test_minimiser_agrees_with_an_independent_scipy_least_squares_solve():
+    """Parity pin that involves neither the oracle's functors nor its LM: MINPACK's Levenberg-Marquardt on a scipy
+    restatement of the residuals, started at the same point, must end in the minimiser the oracle finds under tight
+    options: same cost to 1e-9 relative, poses within north_star's 1e-5 m / 1e-4 rad (MINPACK differentiates by finite
+    differences, so it stalls a little short along the weak whole-trajectory mode), switches to 1e-5."""
+    from scipy.optimize import least_squares
+    from util_graphs import rot_angle_between
+    g = random_graph(14, 2, 3, seed=31)
+    N, El = g["N"], len(g["la"])
+    fun = _scipy_residual_vector(g)
+    x0 = np.r_[g["q"].ravel(), g["t"].ravel(), np.full(El, 0.99)]
+    P = load_oracle(g)
+    assert abs(0.5 * np.sum(fun(x0) ** 2) - P.evaluate(jac=False)["cost"]) <= 1e-12 * max(1.0, P.evaluate(jac=False)["cost"])
+    sol = least_squares(fun, x0, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=20000)
+    s = P.solve(pgo.default_options(max_num_iterations=300, function_tolerance=1e-16, parameter_tolerance=1e-15, gradient_tolerance=1e-13))
+    assert abs(sol.cost - s["final_cost"]) <= 1e-9 * s["final_cost"], (sol.cost, s["final_cost"], s["termination"])
+    q = sol.x[:4 * N].reshape(N, 4); q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    t = sol.x[4 * N:7 * N].reshape(N, 3)
+    qo, to = P.poses()
+    assert np.abs(t - to).max() < 1e-5
+    assert rot_angle_between(q, qo).max() < 1e-4
+    assert np.abs(sol.x[7 * N:] - P.switches()).max() < 1e-5
