@@ -79,7 +79,7 @@ def _host_arch():
 
 def build(force=False):
     so = os.path.join(_HERE, "libpgo.so")
-    srcs = [os.path.join(_HERE, f) for f in ("pgo_capi.cpp", "pgo_core.hpp", "pgo_solver.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("pgo_capi.cpp", "pgo_core.hpp", "pgo_solver.hpp", "pgo_fourdof.hpp")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if not stale:   # built with -march=native on another machine (the library travels with the repo snapshot)?
         try:
@@ -101,6 +101,10 @@ def lib():
         L.pgo_create.restype = C.c_void_p
         L.pgo_evaluate.restype = C.c_double
         L.pgo_time_sweep.restype = C.c_double
+        L.pgo_fourdof_eval.restype = C.c_double
+        L.pgo_angle_plus.restype = C.c_double; L.pgo_angle_plus.argtypes = [C.c_double, C.c_double]
+        L.pgo_angle_plus_jacobian.restype = C.c_double; L.pgo_angle_plus_jacobian.argtypes = [C.c_double]
+        L.pgo_ypr_to_R.argtypes = [C.c_double, C.c_double, C.c_double, c_dp]
         for name in ("pgo_destroy", "pgo_set_nodes", "pgo_add_odom_edges", "pgo_add_loop_edges", "pgo_set_regularizers",
                      "pgo_set_switches", "pgo_get_poses", "pgo_get_switches", "pgo_evaluate", "pgo_time_sweep",
                      "pgo_linear_step", "pgo_solve"):
@@ -284,3 +288,39 @@ def node_reg(q1, t1, qf, tf, w, autodiff=True, jac=True):
     lib().pgo_node_reg(C.c_int(int(autodiff)), a[0][1], a[1][1], a[2][1], a[3][1], C.c_double(w), r.ctypes.data_as(c_dp),
                        J.ctypes.data_as(c_dp) if jac else None)
     return (r, J) if jac else r
+
+
+FOURDOF_SHAPES = {0: (6, 12, 4), 1: (7, 13, 4), 2: (4, 8, 3)}   # kind -> residual rows, tangent columns, doubles per rotation record
+
+
+def fourdof_eval(kind, rot, t, c1, c2, obs_rot, obs_t, weight=None, sw=None, jac=True):
+    """The reference's alternative functors over an edge list (pgo_fourdof.hpp; kinds and layouts as in
+    include/pgs_fourdof.h).  Returns dict(cost, r[E,NR], J[E,NR,NC])."""
+    NR, NC, RW = FOURDOF_SHAPES[kind]
+    rot, rotp = _d(np.asarray(rot).reshape(-1, RW)); t, tp = _d(np.asarray(t).reshape(-1, 3))
+    c1, c1p = _i(c1); c2, c2p = _i(c2)
+    E = len(c1)
+    obs_rot, orp = _d(np.asarray(obs_rot).reshape(E, RW)); obs_t, otp = _d(np.asarray(obs_t).reshape(E, 3))
+    wp = sp = None
+    if weight is not None:
+        weight, wp = _d(weight)
+    if sw is not None:
+        sw, sp = _d(sw)
+    r = np.zeros((E, NR)); J = np.zeros((E, NR, NC))
+    cost = lib().pgo_fourdof_eval(C.c_int(kind), C.c_int(len(rot)), rotp, tp, C.c_int(E), c1p, c2p, orp, otp, wp, sp,
+                                  r.ctypes.data_as(c_dp), J.ctypes.data_as(c_dp) if jac else None)
+    return dict(cost=cost, r=r, J=J) if jac else dict(cost=cost, r=r)
+
+
+def angle_plus(theta, delta):
+    return lib().pgo_angle_plus(theta, delta)
+
+
+def angle_plus_jacobian(theta):
+    return lib().pgo_angle_plus_jacobian(theta)
+
+
+def ypr_to_R(yaw, pitch, roll):
+    R = np.zeros(9)
+    lib().pgo_ypr_to_R(yaw, pitch, roll, R.ctypes.data_as(c_dp))
+    return R.reshape(3, 3)

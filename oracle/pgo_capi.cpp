@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdlib>
 #include "pgo_solver.hpp"
+#include "pgo_fourdof.hpp"
 
 namespace pgo {
 double wall_seconds() {
@@ -168,6 +169,36 @@ void pgo_node_reg(int mode, const double* q1, const double* t1, const double* qf
   NodePoseRegularization f{pose_to_mat4(qf, tf), w};
   if (mode) eval_reg_autodiff(f, q1, t1, r, J); else eval_reg_closed(f, q1, t1, r, J);
 }
+// ---- the reference's alternative (switched-off) functors, batched over an edge list (pgo_fourdof.hpp).
+// kind 0 FourDOFError, 1 FourDOFErrorWithSwitchingConstraints, 2 QinFourDOFWeightError; array meanings as in
+// include/pgs_fourdof.h.  J may be null.  Returns 1/2 sum r^2.
+double pgo_fourdof_eval(int kind, int n_nodes, const double* rot, const double* t, int n_edges, const int* c1, const int* c2, const double* obs_rot,
+                        const double* obs_t, const double* weight, const double* sw, double* r, double* J) {
+  (void)n_nodes;
+  const int NR = kind == 0 ? 6 : kind == 1 ? 7 : 4, NC = kind == 0 ? 12 : kind == 1 ? 13 : 8;
+  double cost = 0;
+  for (int e = 0; e < n_edges; ++e) {
+    const int a = c1[e], b = c2[e];
+    double* re = r + (size_t)NR * e; double* Je = J ? J + (size_t)NR * NC * e : nullptr;
+    if (kind == 2) {
+      QinFourDOFWeightError f{obs_t[3 * e], obs_t[3 * e + 1], obs_t[3 * e + 2], obs_rot[3 * e], obs_rot[3 * e + 1], obs_rot[3 * e + 2]};
+      eval_qin_autodiff(f, rot + 3 * (size_t)a, t + 3 * (size_t)a, rot + 3 * (size_t)b, t + 3 * (size_t)b, re, Je);
+    } else {
+      const Quat<double> oq{obs_rot[4 * e], obs_rot[4 * e + 1], obs_rot[4 * e + 2], obs_rot[4 * e + 3]};
+      const Vec3<double> ot{obs_t[3 * e], obs_t[3 * e + 1], obs_t[3 * e + 2]};
+      if (kind == 0) { FourDOFError f{oq, ot, weight[e]}; eval_fourdof_autodiff(f, rot + 4 * (size_t)a, t + 3 * (size_t)a, rot + 4 * (size_t)b, t + 3 * (size_t)b, re, Je); }
+      else { FourDOFErrorWithSwitchingConstraints f{oq, ot, weight ? weight[e] : 1.0};
+        eval_fourdof_switch_autodiff(f, rot + 4 * (size_t)a, t + 3 * (size_t)a, rot + 4 * (size_t)b, t + 3 * (size_t)b, sw + e, re, Je); }
+    }
+    for (int i = 0; i < NR; ++i) cost += re[i] * re[i];
+  }
+  return 0.5 * cost;
+}
+double pgo_angle_plus(double theta, double delta) { return angle_plus(theta, delta); }
+double pgo_angle_plus_jacobian(double theta) { return angle_plus_jacobian(theta); }
+// rawyprt_to_eigenmat's rotation (YawPitchRollToRotationMatrix, degrees) for the KATs: R[9] row-major
+void pgo_ypr_to_R(double yaw, double pitch, double roll, double* R9) { YawPitchRollToRotationMatrix(yaw, pitch, roll, R9); }
+
 int pgo_max_threads() {
   const unsigned n = std::thread::hardware_concurrency();
   return n ? (int)n : 1;

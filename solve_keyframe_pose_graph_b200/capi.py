@@ -166,6 +166,43 @@ def compose_poses(mgr_T, world_id, slam_q, slam_t, solved_until, solved_until_wo
         L.pgs_compose_destroy(h)
 
 
+class FourDofInput(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_nodes", C.c_int32), ("rot", c_dp), ("t", c_dp), ("n_edges", C.c_int32), ("c1", c_ip), ("c2", c_ip),
+                ("obs_rot", c_dp), ("obs_t", c_dp), ("weight", c_dp), ("sw", c_dp)]
+
+
+FOURDOF_ERROR, FOURDOF_SWITCH, FOURDOF_QIN = 0, 1, 2
+FOURDOF_SHAPES = {0: (6, 12, 4), 1: (7, 13, 4), 2: (4, 8, 3)}   # kind -> residual rows, tangent columns, doubles per rotation record
+
+
+def fourdof_evaluate(kind, rot, t, c1, c2, obs_rot, obs_t, weight=None, sw=None, jac=True, device=0):
+    """include/pgs_fourdof.h in one call: the reference's alternative (switched-off) edge functors
+    (src/CeresResidues.h:252-546) over an edge list, on the device.  Returns dict(cost, r[E,NR], J[E,NR,NC], ms_kernel)."""
+    L = lib()
+    L.pgs_fourdof_last_error.restype = C.c_char_p; L.pgs_fourdof_last_error.argtypes = [C.c_void_p]
+    NR, NC, RW = FOURDOF_SHAPES[kind]
+    h = C.c_void_p()
+    if L.pgs_fourdof_create(C.c_int32(device), C.byref(h)) != 0:
+        raise PgsError("pgs_fourdof_create failed: no usable CUDA device (there is no CPU fallback)")
+    try:
+        rot, rp = _d(np.asarray(rot).reshape(-1, RW)); t, tp = _d(np.asarray(t).reshape(-1, 3))
+        c1, p1 = _i(c1); c2, p2 = _i(c2)
+        E = len(c1)
+        obs_rot, orp = _d(np.asarray(obs_rot).reshape(E, RW)); obs_t, otp = _d(np.asarray(obs_t).reshape(E, 3))
+        weight, wp = _d(weight); sw, sp = _d(sw)
+        inp = FourDofInput(kind, len(rot), rp, tp, E, p1, p2, orp, otp, wp, sp)
+        r = np.zeros((E, NR)); J = np.zeros((E, NR, NC)) if jac else None
+        cost = C.c_double(0)
+        rc = L.pgs_fourdof_evaluate(h, C.byref(inp), r.ctypes.data_as(c_dp), J.ctypes.data_as(c_dp) if jac else None, C.byref(cost))
+        if rc != 0:
+            raise PgsError(f"pgs_fourdof_evaluate failed ({rc}): {L.pgs_fourdof_last_error(h).decode()}")
+        ms = C.c_double(0)
+        L.pgs_fourdof_last_timing(h, C.byref(ms))
+        return dict(cost=cost.value, r=r, J=J, ms_kernel=ms.value)
+    finally:
+        L.pgs_fourdof_destroy(h)
+
+
 def default_options(**kw):
     o = Options()
     lib().pgs_default_options(C.byref(o))

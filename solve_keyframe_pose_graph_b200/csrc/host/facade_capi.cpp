@@ -238,8 +238,11 @@ int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, dou
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
   const auto& v = h->slam->odometry_terms();
   for (size_t i = 0; i < v.size(); ++i) {
-    if (u) u[i] = v[i].u; if (umf) umf[i] = v[i].umf; if (w) w[i] = v[i].weight;
-    if (q) std::memcpy(q + 4 * i, v[i].q, 32); if (t) std::memcpy(t + 3 * i, v[i].t, 24);
+    if (u) u[i] = v[i].u;
+    if (umf) umf[i] = v[i].umf;
+    if (w) w[i] = v[i].weight;
+    if (q) std::memcpy(q + 4 * i, v[i].q, 32);
+    if (t) std::memcpy(t + 3 * i, v[i].t, 24);
   }
   return PGS_OK;
 }
@@ -249,8 +252,10 @@ int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t* node, double* q, doub
   const auto& v = h->slam->regularization_terms();
   for (size_t i = 0; i < v.size(); ++i) {
     double qq[4], tt[3]; pgs::mat_to_raw_xyzw(v[i].anchor, qq, tt);
-    if (node) node[i] = v[i].node; if (w) w[i] = v[i].weight;
-    if (q) std::memcpy(q + 4 * i, qq, 32); if (t) std::memcpy(t + 3 * i, tt, 24);
+    if (node) node[i] = v[i].node;
+    if (w) w[i] = v[i].weight;
+    if (q) std::memcpy(q + 4 * i, qq, 32);
+    if (t) std::memcpy(t + 3 * i, tt, 24);
   }
   return PGS_OK;
 }
