@@ -104,5 +104,17 @@ inline Matrix4d ypr2R(const double ypr[3]) {
   T(2, 0) = -sp;     T(2, 1) = cp * sr;                T(2, 2) = cp * cr;
   return T;
 }
+// rawyprt_to_eigenmat / eigenmat_to_rawyprt (reference PoseManipUtils.cpp:101-141): the (ypr degrees, t) record of the
+// __USE_YPR_REP variable store (PoseGraphSLAM.cpp:199-213,228-247) and of QinFourDOFWeightError's constants
+// (include/pgs_fourdof.h)
+inline Matrix4d rawyprt_to_mat(const double* ypr, const double* t) {
+  Matrix4d T = ypr2R(ypr);
+  T(0, 3) = t[0]; T(1, 3) = t[1]; T(2, 3) = t[2];
+  return T;
+}
+inline void mat_to_rawyprt(const Matrix4d& T, double* ypr, double* t) {
+  R2ypr(T, ypr);
+  t[0] = T(0, 3); t[1] = T(1, 3); t[2] = T(2, 3);
+}
 
 }  // namespace pgs
