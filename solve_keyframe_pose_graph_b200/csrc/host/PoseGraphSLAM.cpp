@@ -69,7 +69,7 @@ bool PoseGraphSLAM::addOdometryEdge(int a, int b, const Matrix4d& a_T_b, double 
   if (a < 0 || b < 0 || a == b || a >= manager->getNodeLen() || b >= manager->getNodeLen()) return false;
   OdomTerm o; o.u = a; o.umf = b; o.weight = weight;
   mat_to_raw_xyzw(a_T_b, o.q, o.t);
-  pending_explicit_odom_.push_back(o);
+  { std::lock_guard<std::mutex> lk(mutex_pending_); pending_explicit_odom_.push_back(o); }
   return true;
 }
 bool PoseGraphSLAM::addLoopEdge(int a, int b, const Matrix4d& b_T_a, double weight) { return manager->add_loop_edge_by_index(a, b, b_T_a, weight, "addLoopEdge"); }
@@ -110,7 +110,9 @@ bool PoseGraphSLAM::solve_once(bool force) {
   const int node_len = manager->getNodeLen();
   const int loopedge_len = manager->getEdgeLen();
   // trigger only on new loop edges, never while kidnapped (PoseGraphSLAM.cpp:1306-1319)
-  if (!force && prev_loopedge_len == loopedge_len && pending_explicit_odom_.empty()) { status = 0; return false; }
+  bool explicit_pending;
+  { std::lock_guard<std::mutex> lk(mutex_pending_); explicit_pending = !pending_explicit_odom_.empty(); }
+  if (!force && prev_loopedge_len == loopedge_len && !explicit_pending) { status = 0; return false; }
   if (manager->curr_kidnap_status()) { status = 0; return false; }
   if (node_len == 0) { status = 0; return false; }
   status = 1;
@@ -178,8 +180,9 @@ bool PoseGraphSLAM::solve_once(bool force) {
       }
     }
   }
-  for (const OdomTerm& o : pending_explicit_odom_) new_odom.push_back(o);
-  pending_explicit_odom_.clear();
+  { std::lock_guard<std::mutex> lk(mutex_pending_);
+    for (const OdomTerm& o : pending_explicit_odom_) new_odom.push_back(o);
+    pending_explicit_odom_.clear(); }
   {
     std::lock_guard<std::mutex> lk(mutex_residue_info);
     for (const OdomTerm& o : new_odom) odometry_edges_terms.push_back(std::make_tuple(o.u, o.umf, (float)o.weight, std::string("")));

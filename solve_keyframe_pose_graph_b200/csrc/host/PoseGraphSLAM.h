@@ -114,6 +114,7 @@ class PoseGraphSLAM {
   std::map<int, std::tuple<int, int>> changes_to_setid_on_set_union;
   std::vector<RegTerm> reg_terms_;
   std::vector<OdomTerm> odom_terms_;
+  mutable std::mutex mutex_pending_;          // addOdometryEdge may run on the ingest thread while the solver thread drains the list
   std::vector<OdomTerm> pending_explicit_odom_;
   std::vector<int> loop_slot_;       // manager loop-edge index -> device loop-edge index (-1: skipped, dead zone)
   int n_device_nodes_ = 0, n_device_loops_ = 0;
