@@ -169,10 +169,21 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(args.config, p, 1), "sample": "one full sweep of the workload per step"},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                             "sample": "full config-3 sweep (Jet autodiff functors) per step, all host threads"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+def cpu_model():
+    """Host CPU model string for the cpu_baseline object (core count and CPU model stated)."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def main():
@@ -265,7 +276,7 @@ def main():
         t1 = P.time_sweep(autodiff=True, threads=1, reps=3)
         nthr = pgo.lib().pgo_max_threads()
         tN = P.time_sweep(autodiff=False, threads=nthr, reps=3)
-        cpu = {"value": Ecpu / t1, "unit": UNIT, "cores": 1, "kind": "port",
+        cpu = {"value": Ecpu / t1, "unit": UNIT, "cores": 1, "kind": "port", "cpu_model": cpu_model(),
                "sample": f"3 full sweeps of the same workload ({Ecpu} edges), best; Jet-autodiff functors, 1 thread (Ceres default num_threads=1)",
                "best_effort_all_cores": {"value": Ecpu / tN, "cores": nthr, "what": "closed-form Jacobians, std::thread over edges"}}
 
