@@ -94,6 +94,14 @@ int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* solved_posegra
 int pgs_io_load_solved_posegraph(const char* json_file, double* T, int64_t* stamp_ns, int32_t* world_id, int32_t* set_id, int32_t cap);
 
 /* introspection of the graph-construction rules (parity tests against the oracle front-end) */
+/* The blocks the reference's switched-off builds would add for this session (kind = pgs_fourdof_kind of pgs_fourdof.h:
+ * FourDOFError on the odometry edges, PoseGraphSLAM.cpp:1630; FourDOFErrorWithSwitchingConstraints on the loop edges,
+ * :1551; the __USE_YPR_REP build, QinFourDOFWeightError on odometry then loop edges, :1608-1626,1534-1548), and their
+ * evaluation on the device.  _size gives the array lengths; every output pointer may be NULL. */
+int pgs_facade_alternative_terms_size(pgs_facade_handle h, int32_t kind, int32_t* n_nodes, int32_t* n_edges);
+int pgs_facade_get_alternative_terms(pgs_facade_handle h, int32_t kind, double* rot, double* t, int32_t* c1, int32_t* c2, double* obs_rot, double* obs_t,
+                                     double* weight, double* sw);
+int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, double* r, double* J, double* cost);   /* r, J sized as in pgs_fourdof.h */
 int32_t pgs_facade_n_odom_terms(pgs_facade_handle h);
 int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w);
 int32_t pgs_facade_n_reg_terms(pgs_facade_handle h);

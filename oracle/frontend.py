@@ -362,6 +362,34 @@ class ReferenceFrontEnd:
         self.prev_loopedge_len = loopedge_len
         return summary
 
+    def alternative_terms(self, kind):
+        """The residual blocks the reference's SWITCHED-OFF builds add for the same session, as keyword arguments of
+        pgo.fourdof_eval: kind 0 FourDOFError::Create(u_M_umf, odom_edge_weight) on (u, u-f) (the commented call at
+        src/PoseGraphSLAM.cpp:1630); kind 1 FourDOFErrorWithSwitchingConstraints::Create(bTa, weight) on
+        (paur.second, paur.first, switch e) (:1551); kind 2 the __USE_YPR_REP build: (ypr, t) variables (:228-247),
+        QinFourDOFWeightError(u_M_umf translation, yaw of u_M_umf, pitch and roll of w_M_u) on (u, u-f) (:1608-1626), then
+        QinFourDOFWeightError(bTa translation, yaw of bTa, pitch and roll of the manager pose of paur.first) on
+        (paur.second, paur.first) (:1389-1392,1534-1548)."""
+        m = self.m
+        t = np.array(self.opt_t).reshape(-1, 3)
+        if kind == 0:
+            return dict(rot=np.array(self.opt_q).reshape(-1, 4), t=t, c1=[o[0] for o in self.odom], c2=[o[1] for o in self.odom],
+                        obs_rot=np.array([o[2] for o in self.odom]).reshape(-1, 4), obs_t=np.array([o[3] for o in self.odom]).reshape(-1, 3),
+                        weight=[o[4] for o in self.odom], sw=None)
+        if kind == 1:
+            return dict(rot=np.array(self.opt_q).reshape(-1, 4), t=t, c1=[l[2] for l in self.loops], c2=[l[1] for l in self.loops],
+                        obs_rot=np.array([l[3] for l in self.loops]).reshape(-1, 4), obs_t=np.array([l[4] for l in self.loops]).reshape(-1, 3),
+                        weight=[l[5] for l in self.loops], sw=[self.opt_s[l[0]] for l in self.loops])
+        ypr = np.array([pgo.r2ypr_deg(self.pose(i)) for i in range(len(self.opt_q))]).reshape(-1, 3)   # eigenmat_to_rawyprt
+        c1, c2, obs_rot, obs_t = [], [], [], []
+        for (u, umf, q, tt, w) in self.odom:
+            u_M_umf = pgo.pose_to_mat4(q, tt); own = pgo.r2ypr_deg(m.poses[u])
+            c1.append(u); c2.append(umf); obs_t.append(u_M_umf[:3, 3]); obs_rot.append([pgo.r2ypr_deg(u_M_umf)[0], own[1], own[2]])
+        for (e, a, b, q, tt, w) in self.loops:
+            bTa = m.edge_pose[e]; own = pgo.r2ypr_deg(m.poses[a])
+            c1.append(b); c2.append(a); obs_t.append(bTa[:3, 3]); obs_rot.append([pgo.r2ypr_deg(bTa)[0], own[1], own[2]])
+        return dict(rot=ypr, t=t, c1=c1, c2=c2, obs_rot=np.array(obs_rot).reshape(-1, 3), obs_t=np.array(obs_t).reshape(-1, 3), weight=None, sw=None)
+
     def problem(self):
         P = pgo.Problem()
         P.set_nodes(np.array(self.opt_q), np.array(self.opt_t))

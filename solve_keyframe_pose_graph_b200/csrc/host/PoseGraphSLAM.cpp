@@ -74,6 +74,49 @@ bool PoseGraphSLAM::addOdometryEdge(int a, int b, const Matrix4d& a_T_b, double 
 }
 bool PoseGraphSLAM::addLoopEdge(int a, int b, const Matrix4d& b_T_a, double weight) { return manager->add_loop_edge_by_index(a, b, b_T_a, weight, "addLoopEdge"); }
 
+// ---------------------------------------------------------------- the switched-off builds' blocks
+bool PoseGraphSLAM::alternative_terms(int kind, AlternativeTerms& out) const {
+  if (kind < 0 || kind > 2) return false;
+  out = AlternativeTerms();
+  out.kind = kind;
+  std::vector<double> q, t, sw;
+  { std::lock_guard<std::mutex> lk(mutex_opt_vars); q = _opt_quat_; t = _opt_t_; sw = _opt_switch_; }
+  const int n = (int)(t.size() / 3);
+  out.n_nodes = n; out.t = t;
+  if (kind == 2) {                                       // allocate_and_append_new_opt_variable_withpose under __USE_YPR_REP (:228-247)
+    out.rot.resize(3 * (size_t)n);
+    for (int i = 0; i < n; ++i) { double tt[3]; mat_to_rawyprt(raw_xyzw_to_mat(&q[4 * (size_t)i], &t[3 * (size_t)i]), &out.rot[3 * (size_t)i], tt); }
+  } else out.rot = q;
+  auto push_qin = [&](int i, int j, const Matrix4d& i_T_j, int pitch_roll_of) {   // QinFourDOFWeightError::Create(t, yaw(i_T_j), pitch, roll)
+    double rel[3], tr[3], own[3], tmp[3];
+    mat_to_rawyprt(i_T_j, rel, tr);
+    mat_to_rawyprt(manager->getNodePose(pitch_roll_of), own, tmp);
+    out.c1.push_back(i); out.c2.push_back(j);
+    out.obs_t.insert(out.obs_t.end(), tr, tr + 3);
+    out.obs_rot.push_back(rel[0]); out.obs_rot.push_back(own[1]); out.obs_rot.push_back(own[2]);
+  };
+  if (kind == 0 || kind == 2) {
+    for (const OdomTerm& o : odom_terms_) {
+      if (kind == 2) { push_qin(o.u, o.umf, raw_xyzw_to_mat(o.q, o.t), o.u); continue; }      // pitch / roll of w_M_u (:1609-1620)
+      out.c1.push_back(o.u); out.c2.push_back(o.umf);
+      out.obs_rot.insert(out.obs_rot.end(), o.q, o.q + 4); out.obs_t.insert(out.obs_t.end(), o.t, o.t + 3); out.weight.push_back(o.weight);
+    }
+  }
+  if (kind == 1 || kind == 2) {
+    for (int e = 0; e < (int)loop_slot_.size(); ++e) {
+      if (loop_slot_[e] < 0) continue;                                                            // an endpoint in a dead zone: no block (:1397-1401)
+      const std::pair<int, int> paur = manager->getEdgeIdxInfo(e);
+      const Matrix4d bTa = manager->getEdgePose(e);
+      if (kind == 2) { push_qin(paur.second, paur.first, bTa, paur.first); continue; }          // __w_T_first___ypr[1], [2] (:1389-1392,1541-1543)
+      double oq[4], ot[3]; mat_to_raw_xyzw(bTa, oq, ot);
+      out.c1.push_back(paur.second); out.c2.push_back(paur.first);
+      out.obs_rot.insert(out.obs_rot.end(), oq, oq + 4); out.obs_t.insert(out.obs_t.end(), ot, ot + 3);
+      out.weight.push_back(manager->getEdgeWeight(e)); out.sw.push_back(e < (int)sw.size() ? sw[e] : opt_.solver.switch_init);
+    }
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------- the solver thread
 void PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF() {
   const auto period = std::chrono::duration<double>(1.0 / std::max(1e-3, opt_.loop_rate_hz));

@@ -83,6 +83,18 @@ class PoseGraphSLAM {
   struct OdomTerm { int u, umf; double q[4], t[3], weight; };
   const std::vector<OdomTerm>& odometry_terms() const { return odom_terms_; }
   pgs_handle device_handle() { return handle_; }
+  // The residual blocks the reference's SWITCHED-OFF builds would add for the same session, in the
+  // array form include/pgs_fourdof.h takes.  kind 0: FourDOFError::Create(u_M_umf, odom_edge_weight) on (u, u-f), the
+  // commented call at PoseGraphSLAM.cpp:1630; kind 1: FourDOFErrorWithSwitchingConstraints::Create(bTa, weight) on
+  // (second, first, switch e), :1551; kind 2: the __USE_YPR_REP build — QinFourDOFWeightError on (ypr, t) variables for
+  // odometry (:1608-1626) followed by loop edges (:1389-1396,1534-1548; pitch / roll are read from paur.first there).
+  struct AlternativeTerms {
+    int kind = 0, n_nodes = 0;
+    std::vector<double> rot, t;                      // [4|3 n_nodes], [3 n_nodes]: the optimisation variables
+    std::vector<int32_t> c1, c2;
+    std::vector<double> obs_rot, obs_t, weight, sw;  // per block
+  };
+  bool alternative_terms(int kind, AlternativeTerms& out) const;
 
  private:
   bool fail(const std::string& msg) { error_ = msg; status = 0; return false; }

@@ -1,5 +1,6 @@
 // C view of the facade (include/pgs_facade.h).
 #include "../../../include/pgs_facade.h"
+#include "../../../include/pgs_fourdof.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -232,6 +233,37 @@ int pgs_io_load_solved_posegraph(const char* file, double* T, int64_t* stamp_ns,
     if (set_id) set_id[i] = g.set_id[i];
   }
   return n;
+}
+int pgs_facade_alternative_terms_size(pgs_facade_handle h, int32_t kind, int32_t* n_nodes, int32_t* n_edges) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::PoseGraphSLAM::AlternativeTerms A;
+  if (!h->slam->alternative_terms(kind, A)) { h->err = "alternative terms: kind must be 0, 1 or 2"; return PGS_ERR_INVALID_ARGUMENT; }
+  if (n_nodes) *n_nodes = A.n_nodes;
+  if (n_edges) *n_edges = (int32_t)A.c1.size();
+  return PGS_OK;
+}
+int pgs_facade_get_alternative_terms(pgs_facade_handle h, int32_t kind, double* rot, double* t, int32_t* c1, int32_t* c2, double* obs_rot, double* obs_t,
+                                     double* weight, double* sw) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::PoseGraphSLAM::AlternativeTerms A;
+  if (!h->slam->alternative_terms(kind, A)) { h->err = "alternative terms: kind must be 0, 1 or 2"; return PGS_ERR_INVALID_ARGUMENT; }
+  auto put = [](auto* dst, const auto& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(v[0]) * v.size()); };
+  put(rot, A.rot); put(t, A.t); put(c1, A.c1); put(c2, A.c2); put(obs_rot, A.obs_rot); put(obs_t, A.obs_t); put(weight, A.weight); put(sw, A.sw);
+  return PGS_OK;
+}
+int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, double* r, double* J, double* cost) {
+  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  pgs::PoseGraphSLAM::AlternativeTerms A;
+  if (!h->slam->alternative_terms(kind, A)) { h->err = "alternative terms: kind must be 0, 1 or 2"; return PGS_ERR_INVALID_ARGUMENT; }
+  pgs_fourdof_handle f = nullptr;
+  if (int rc = pgs_fourdof_create(h->device, &f)) { h->err = "pgs_fourdof_create: no usable CUDA device (there is no CPU fallback)"; return rc; }
+  pgs_fourdof_input in{};
+  in.kind = kind; in.n_nodes = A.n_nodes; in.rot = A.rot.data(); in.t = A.t.data(); in.n_edges = (int32_t)A.c1.size(); in.c1 = A.c1.data(); in.c2 = A.c2.data();
+  in.obs_rot = A.obs_rot.data(); in.obs_t = A.obs_t.data(); in.weight = A.weight.data(); in.sw = A.sw.data();
+  const int rc = pgs_fourdof_evaluate(f, &in, r, J, cost);
+  if (rc) h->err = pgs_fourdof_last_error(f);
+  pgs_fourdof_destroy(f);
+  return rc;
 }
 int32_t pgs_facade_n_odom_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->odometry_terms().size() : 0; }
 int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w) {

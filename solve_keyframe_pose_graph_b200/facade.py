@@ -197,6 +197,30 @@ class Facade:
         self._ck(self.L.pgs_facade_get_reg_terms(self.h, node.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
         return dict(node=node, q=q, t=t, w=w)
 
+    def alternative_terms(self, kind):
+        """Blocks of the reference's switched-off builds for this session (PoseGraphSLAM::alternative_terms), as the
+        keyword arguments of capi.fourdof_evaluate / oracle.pgo.fourdof_eval."""
+        nn = C.c_int32(0); ne = C.c_int32(0)
+        self._ck(self.L.pgs_facade_alternative_terms_size(self.h, C.c_int32(kind), C.byref(nn), C.byref(ne)))
+        n, m = nn.value, ne.value
+        rw = 3 if kind == 2 else 4
+        rot = np.zeros((n, rw)); t = np.zeros((n, 3)); c1 = np.zeros(m, np.int32); c2 = np.zeros(m, np.int32)
+        obs_rot = np.zeros((m, rw)); obs_t = np.zeros((m, 3)); weight = np.zeros(m); sw = np.zeros(m)
+        p = lambda a: a.ctypes.data_as(c_dp)
+        self._ck(self.L.pgs_facade_get_alternative_terms(self.h, C.c_int32(kind), p(rot), p(t), c1.ctypes.data_as(c_ip), c2.ctypes.data_as(c_ip),
+                                                         p(obs_rot), p(obs_t), p(weight), p(sw)))
+        return dict(rot=rot, t=t, c1=c1, c2=c2, obs_rot=obs_rot, obs_t=obs_t, weight=weight if kind in (0, 1) else None, sw=sw if kind == 1 else None)
+
+    def evaluate_alternative(self, kind, jac=True):
+        """Residuals, tangent Jacobians and cost of those blocks at the current optimisation variables, on the device."""
+        nn = C.c_int32(0); ne = C.c_int32(0)
+        self._ck(self.L.pgs_facade_alternative_terms_size(self.h, C.c_int32(kind), C.byref(nn), C.byref(ne)))
+        nr, nc = {0: (6, 12), 1: (7, 13), 2: (4, 8)}[kind]
+        r = np.zeros((ne.value, nr)); J = np.zeros((ne.value, nr, nc)) if jac else None
+        cost = C.c_double(0)
+        self._ck(self.L.pgs_facade_evaluate_alternative(self.h, C.c_int32(kind), r.ctypes.data_as(c_dp), J.ctypes.data_as(c_dp) if jac else None, C.byref(cost)))
+        return dict(cost=cost.value, r=r, J=J)
+
     def which_world(self, stamp):
         return self.L.pgs_facade_which_world(self.h, C.c_int64(int(stamp)))
 

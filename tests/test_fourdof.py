@@ -216,3 +216,59 @@ def test_device_evaluation_rejects_bad_input_and_accepts_an_empty_list():
         capi.fourdof_evaluate(1, **g)                                         # the switched functor needs its switch array
     e = capi.fourdof_evaluate(0, g["rot"], g["t"], [], [], np.zeros((0, 4)), np.zeros((0, 3)), weight=[])
     assert e["cost"] == 0.0 and e["r"].shape == (0, 6)
+
+
+# ------------------------------------------------------------------------------------------------ through the facade
+def _session(dry_run):
+    """A four-world session (config-4 recipe, reduced), in the facade and in the oracle's front-end restatement."""
+    from oracle import frontend
+    from solve_keyframe_pose_graph_b200 import facade, synth
+    g = synth.generate_config(4, n_nodes=120, n_interworld=18)
+    F = facade.Facade(odom_fanout=3, dry_run=dry_run); F.ingest(g)
+    M = frontend.Manager(); M.ingest(g)
+    R = frontend.ReferenceFrontEnd(M, odom_fanout=3)
+    return g, F, R
+
+
+def _same_terms(a, b):
+    assert np.array_equal(a["c1"], np.asarray(b["c1"], np.int32)) and np.array_equal(a["c2"], np.asarray(b["c2"], np.int32))
+    assert np.allclose(a["t"], b["t"], atol=1e-9) and np.allclose(a["obs_t"], b["obs_t"], atol=1e-9)
+    if a["rot"].shape[1] == 4:                                               # quaternions up to sign
+        assert np.all(np.abs(np.sum(a["rot"] * b["rot"], axis=1)) > 1 - 1e-12)
+        assert np.all(np.abs(np.sum(a["obs_rot"] * b["obs_rot"], axis=1)) > 1 - 1e-12)
+    else:                                                                    # degrees
+        assert np.allclose(a["rot"], b["rot"], atol=1e-7) and np.allclose(a["obs_rot"], b["obs_rot"], atol=1e-7)
+    for k in ("weight", "sw"):
+        assert (a[k] is None) == (b[k] is None) and (a[k] is None or np.allclose(a[k], b[k], rtol=1e-9, atol=0))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_facade_builds_the_blocks_of_the_switched_off_builds(kind):
+    g, F, R = _session(dry_run=True)
+    assert F.solve_once() and R.trigger(solve=False) is None
+    a, b = F.alternative_terms(kind), R.alternative_terms(kind)
+    n_odom, n_loop = len(R.odom), len(R.loops)
+    assert len(a["c1"]) == {0: n_odom, 1: n_loop, 2: n_odom + n_loop}[kind] and len(a["c1"]) > 0
+    _same_terms(a, b)
+    if kind == 1:
+        assert np.all(a["sw"] == 0.99)                                       # PoseGraphSLAM.cpp:353
+    if kind == 2:                                                            # pitch / roll of a loop block come from paur.first = the block's SECOND pose
+        own = np.array([pgo.r2ypr_deg(R.m.poses[int(i)]) for i in a["c2"][n_odom:]])
+        assert np.allclose(a["obs_rot"][n_odom:, 1:], own[:, 1:], atol=1e-7)
+    F.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_facade_evaluates_the_switched_off_blocks_on_the_device_after_a_solve(kind):
+    g, F, R = _session(dry_run=False)
+    assert F.solve_once() and R.trigger(solve=True) is not None              # both solved: variables and switches have moved
+    b = R.alternative_terms(kind)
+    terms = F.alternative_terms(kind)                                        # evaluate the oracle on the facade's own terms: isolates the kernel
+    want = pgo.fourdof_eval(kind, **terms)
+    got = F.evaluate_alternative(kind)
+    assert close(got["r"], want["r"], 1e-12) and close(got["J"], want["J"], 1e-12) and abs(got["cost"] - want["cost"]) <= 1e-12 * want["cost"]
+    # and the session-level answer agrees with the front-end restatement's own solve to the parity tolerance of the live path
+    ref = pgo.fourdof_eval(kind, **b)
+    assert abs(got["cost"] - ref["cost"]) <= 1e-3 * max(1.0, ref["cost"])      # degrees x 10 amplify the 1e-7 rad pose agreement
+    F.close()
