@@ -66,9 +66,11 @@ int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s);       /*
 int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* iters, int32_t cap);
 
 /* Composer (reference src/Composer.cpp:10-292): one pass of pose_assember_thread's loop body on the device
- * (include/pgs_compose.h).  out_T [n][16] row-major assembled pose per keyframe (global_lmb), out_world [n] its
- * world id (the key of global_jmb); either may be NULL.  Returns the number of keyframes, < 0 on error. */
-int pgs_facade_compose(pgs_facade_handle h, double* out_T, int32_t* out_world);
+ * (include/pgs_compose.h).  out_T [cap][16] row-major assembled pose per keyframe (global_lmb), out_world [cap] its
+ * world id (the key of global_jmb); either may be NULL.  Every keyframe the manager holds at the time of the call is
+ * assembled; the first min(that, cap) are written and their count is returned (< 0 on error) — the callbacks may
+ * append keyframes between a pgs_facade_n_keyframes() call and this one, hence the capacity. */
+int pgs_facade_compose(pgs_facade_handle h, int32_t cap, double* out_T, int32_t* out_world);
 int32_t pgs_facade_n_keyframes(pgs_facade_handle h);                          /* manager->getNodeLen() */
 /* get_last_known_camerapose (Composer.cpp:264-276): index of the last keyframe or -1; T16 / stamp may be NULL */
 int pgs_facade_last_known_camerapose(pgs_facade_handle h, double* T16, int64_t* stamp_ns);
@@ -93,19 +95,22 @@ int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* solved_posegra
 /* loads a solved_posegraph.json: n = number of keyframes (call with NULL outputs to size), poses [n][16], stamps, ids */
 int pgs_io_load_solved_posegraph(const char* json_file, double* T, int64_t* stamp_ns, int32_t* world_id, int32_t* set_id, int32_t cap);
 
-/* introspection of the graph-construction rules (parity tests against the oracle front-end) */
+/* introspection of the graph-construction rules (parity tests against the oracle front-end).  The lists behind these
+ * calls belong to the solver thread: while it runs (pgs_facade_thread_start) they return PGS_ERR_STATE.  The get_
+ * functions write at most cap entries (cap_nodes / cap_edges for the two-sized one) and return how many. */
 /* The blocks the reference's switched-off builds would add for this session (kind = pgs_fourdof_kind of pgs_fourdof.h:
  * FourDOFError on the odometry edges, PoseGraphSLAM.cpp:1630; FourDOFErrorWithSwitchingConstraints on the loop edges,
  * :1551; the __USE_YPR_REP build, QinFourDOFWeightError on odometry then loop edges, :1608-1626,1534-1548), and their
- * evaluation on the device.  _size gives the array lengths; every output pointer may be NULL. */
+ * evaluation on the device.  _size gives the array lengths; every output pointer may be NULL.  get_ returns the number of
+ * blocks written; evaluate_ fails with PGS_ERR_INVALID_ARGUMENT when there are more blocks than cap_edges. */
 int pgs_facade_alternative_terms_size(pgs_facade_handle h, int32_t kind, int32_t* n_nodes, int32_t* n_edges);
-int pgs_facade_get_alternative_terms(pgs_facade_handle h, int32_t kind, double* rot, double* t, int32_t* c1, int32_t* c2, double* obs_rot, double* obs_t,
-                                     double* weight, double* sw);
-int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, double* r, double* J, double* cost);   /* r, J sized as in pgs_fourdof.h */
-int32_t pgs_facade_n_odom_terms(pgs_facade_handle h);
-int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w);
+int pgs_facade_get_alternative_terms(pgs_facade_handle h, int32_t kind, int32_t cap_nodes, int32_t cap_edges, double* rot, double* t, int32_t* c1, int32_t* c2,
+                                     double* obs_rot, double* obs_t, double* weight, double* sw);
+int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, int32_t cap_edges, double* r, double* J, double* cost);   /* r, J sized as in pgs_fourdof.h */
+int32_t pgs_facade_n_odom_terms(pgs_facade_handle h);      /* count, or PGS_ERR_STATE while the solver thread runs */
+int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t cap, int32_t* u, int32_t* umf, double* q, double* t, double* w);
 int32_t pgs_facade_n_reg_terms(pgs_facade_handle h);
-int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t* node, double* q, double* t, double* w);
+int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t cap, int32_t* node, double* q, double* t, double* w);
 int32_t pgs_facade_which_world(pgs_facade_handle h, int64_t stamp_ns);
 int32_t pgs_facade_n_worlds(pgs_facade_handle h);
 int32_t pgs_facade_world_setid(pgs_facade_handle h, int32_t world);

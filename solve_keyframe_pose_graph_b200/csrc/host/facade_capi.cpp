@@ -144,13 +144,13 @@ int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* i
   for (int i = 0; iters && i < cap && i < (int)it.size(); ++i) iters[i] = it[i];
   return PGS_OK;
 }
-int pgs_facade_compose(pgs_facade_handle h, double* out_T, int32_t* out_world) {
-  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+int pgs_facade_compose(pgs_facade_handle h, int32_t cap, double* out_T, int32_t* out_world) {
+  if (!h || cap < 0) return PGS_ERR_INVALID_ARGUMENT;
   h->err.clear();
   if (!h->composer) h->composer = new pgs::Composer(&h->manager, h->slam, h->device);
   if (!h->composer->pose_assember_once()) { h->err = h->composer->last_error(); return PGS_ERR_CUDA; }
   const std::vector<pgs::Matrix4d> lmb = h->composer->get_global_lmb();
-  const int n = (int)lmb.size();
+  const int n = std::min<int>((int)lmb.size(), cap);     // keyframes may have arrived since the caller sized its buffers
   for (int i = 0; i < n; ++i) {
     if (out_T) std::memcpy(out_T + 16 * (size_t)i, lmb[i].m, 128);
     if (out_world) out_world[i] = h->manager.which_world_is_this(h->manager.getNodeTimestamp(i));
@@ -234,27 +234,39 @@ int pgs_io_load_solved_posegraph(const char* file, double* T, int64_t* stamp_ns,
   }
   return n;
 }
+// the term lists are written by the solver thread without a lock of their own: introspection only while it is stopped
+static bool introspection_blocked(pgs_facade_handle h) {
+  if (!h->solver_thread.joinable()) return false;
+  h->err = "introspection of the residual-block lists is not available while the solver thread runs (pgs_facade_thread_stop first)";
+  return true;
+}
 int pgs_facade_alternative_terms_size(pgs_facade_handle h, int32_t kind, int32_t* n_nodes, int32_t* n_edges) {
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  if (introspection_blocked(h)) return PGS_ERR_STATE;
   pgs::PoseGraphSLAM::AlternativeTerms A;
   if (!h->slam->alternative_terms(kind, A)) { h->err = "alternative terms: kind must be 0, 1 or 2"; return PGS_ERR_INVALID_ARGUMENT; }
   if (n_nodes) *n_nodes = A.n_nodes;
   if (n_edges) *n_edges = (int32_t)A.c1.size();
   return PGS_OK;
 }
-int pgs_facade_get_alternative_terms(pgs_facade_handle h, int32_t kind, double* rot, double* t, int32_t* c1, int32_t* c2, double* obs_rot, double* obs_t,
-                                     double* weight, double* sw) {
-  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+int pgs_facade_get_alternative_terms(pgs_facade_handle h, int32_t kind, int32_t cap_nodes, int32_t cap_edges, double* rot, double* t, int32_t* c1, int32_t* c2,
+                                     double* obs_rot, double* obs_t, double* weight, double* sw) {
+  if (!h || cap_nodes < 0 || cap_edges < 0) return PGS_ERR_INVALID_ARGUMENT;
+  if (introspection_blocked(h)) return PGS_ERR_STATE;
   pgs::PoseGraphSLAM::AlternativeTerms A;
   if (!h->slam->alternative_terms(kind, A)) { h->err = "alternative terms: kind must be 0, 1 or 2"; return PGS_ERR_INVALID_ARGUMENT; }
-  auto put = [](auto* dst, const auto& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(v[0]) * v.size()); };
-  put(rot, A.rot); put(t, A.t); put(c1, A.c1); put(c2, A.c2); put(obs_rot, A.obs_rot); put(obs_t, A.obs_t); put(weight, A.weight); put(sw, A.sw);
-  return PGS_OK;
+  const size_t nn = (size_t)std::min<int>(A.n_nodes, cap_nodes), ne = std::min<size_t>(A.c1.size(), (size_t)cap_edges), rw = kind == 2 ? 3 : 4;
+  auto put = [](auto* dst, const auto& v, size_t count) { count = std::min(count, v.size()); if (dst && count) std::memcpy(dst, v.data(), sizeof(v[0]) * count); };
+  put(rot, A.rot, rw * nn); put(t, A.t, 3 * nn); put(c1, A.c1, ne); put(c2, A.c2, ne); put(obs_rot, A.obs_rot, rw * ne); put(obs_t, A.obs_t, 3 * ne);
+  put(weight, A.weight, ne); put(sw, A.sw, ne);
+  return (int)ne;
 }
-int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, double* r, double* J, double* cost) {
+int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, int32_t cap_edges, double* r, double* J, double* cost) {
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
+  if (introspection_blocked(h)) return PGS_ERR_STATE;
   pgs::PoseGraphSLAM::AlternativeTerms A;
   if (!h->slam->alternative_terms(kind, A)) { h->err = "alternative terms: kind must be 0, 1 or 2"; return PGS_ERR_INVALID_ARGUMENT; }
+  if ((int64_t)A.c1.size() > (int64_t)cap_edges) { h->err = "evaluate_alternative: " + std::to_string(A.c1.size()) + " blocks, room for " + std::to_string(cap_edges); return PGS_ERR_INVALID_ARGUMENT; }
   pgs_fourdof_handle f = nullptr;
   if (int rc = pgs_fourdof_create(h->device, &f)) { h->err = "pgs_fourdof_create: no usable CUDA device (there is no CPU fallback)"; return rc; }
   pgs_fourdof_input in{};
@@ -265,31 +277,35 @@ int pgs_facade_evaluate_alternative(pgs_facade_handle h, int32_t kind, double* r
   pgs_fourdof_destroy(f);
   return rc;
 }
-int32_t pgs_facade_n_odom_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->odometry_terms().size() : 0; }
-int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t* u, int32_t* umf, double* q, double* t, double* w) {
-  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+int32_t pgs_facade_n_odom_terms(pgs_facade_handle h) { if (!h) return 0; if (introspection_blocked(h)) return PGS_ERR_STATE; return (int32_t)h->slam->odometry_terms().size(); }
+int pgs_facade_get_odom_terms(pgs_facade_handle h, int32_t cap, int32_t* u, int32_t* umf, double* q, double* t, double* w) {
+  if (!h || cap < 0) return PGS_ERR_INVALID_ARGUMENT;
+  if (introspection_blocked(h)) return PGS_ERR_STATE;
   const auto& v = h->slam->odometry_terms();
-  for (size_t i = 0; i < v.size(); ++i) {
+  const size_t n = std::min(v.size(), (size_t)cap);
+  for (size_t i = 0; i < n; ++i) {
     if (u) u[i] = v[i].u;
     if (umf) umf[i] = v[i].umf;
     if (w) w[i] = v[i].weight;
     if (q) std::memcpy(q + 4 * i, v[i].q, 32);
     if (t) std::memcpy(t + 3 * i, v[i].t, 24);
   }
-  return PGS_OK;
+  return (int)n;
 }
-int32_t pgs_facade_n_reg_terms(pgs_facade_handle h) { return h ? (int32_t)h->slam->regularization_terms().size() : 0; }
-int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t* node, double* q, double* t, double* w) {
-  if (!h) return PGS_ERR_INVALID_ARGUMENT;
+int32_t pgs_facade_n_reg_terms(pgs_facade_handle h) { if (!h) return 0; if (introspection_blocked(h)) return PGS_ERR_STATE; return (int32_t)h->slam->regularization_terms().size(); }
+int pgs_facade_get_reg_terms(pgs_facade_handle h, int32_t cap, int32_t* node, double* q, double* t, double* w) {
+  if (!h || cap < 0) return PGS_ERR_INVALID_ARGUMENT;
+  if (introspection_blocked(h)) return PGS_ERR_STATE;
   const auto& v = h->slam->regularization_terms();
-  for (size_t i = 0; i < v.size(); ++i) {
+  const size_t n = std::min(v.size(), (size_t)cap);
+  for (size_t i = 0; i < n; ++i) {
     double qq[4], tt[3]; pgs::mat_to_raw_xyzw(v[i].anchor, qq, tt);
     if (node) node[i] = v[i].node;
     if (w) w[i] = v[i].weight;
     if (q) std::memcpy(q + 4 * i, qq, 32);
     if (t) std::memcpy(t + 3 * i, tt, 24);
   }
-  return PGS_OK;
+  return (int)n;
 }
 int32_t pgs_facade_which_world(pgs_facade_handle h, int64_t stamp) { return h->manager.which_world_is_this(stamp); }
 int32_t pgs_facade_n_worlds(pgs_facade_handle h) { return h->manager.n_worlds(); }

@@ -161,7 +161,7 @@ class Facade:
         """One pass of Composer::pose_assember_thread on the device -> (T [n,4,4] assembled poses, world id [n])."""
         n = self.n_keyframes()
         T = np.zeros((max(n, 1), 4, 4)); w = np.zeros(max(n, 1), np.int32)
-        r = self._ck(self.L.pgs_facade_compose(self.h, T.ctypes.data_as(c_dp), w.ctypes.data_as(c_ip)))
+        r = self._ck(self.L.pgs_facade_compose(self.h, C.c_int32(n), T.ctypes.data_as(c_dp), w.ctypes.data_as(c_ip)))
         return T[:r], w[:r]
 
     def last_known_camerapose(self):
@@ -186,16 +186,16 @@ class Facade:
 
     # ---- introspection
     def odom_terms(self):
-        n = self.L.pgs_facade_n_odom_terms(self.h)
+        n = self._ck(self.L.pgs_facade_n_odom_terms(self.h))
         u = np.zeros(n, np.int32); v = np.zeros(n, np.int32); q = np.zeros((n, 4)); t = np.zeros((n, 3)); w = np.zeros(n)
-        self._ck(self.L.pgs_facade_get_odom_terms(self.h, u.ctypes.data_as(c_ip), v.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
-        return dict(u=u, umf=v, q=q, t=t, w=w)
+        m = self._ck(self.L.pgs_facade_get_odom_terms(self.h, C.c_int32(n), u.ctypes.data_as(c_ip), v.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
+        return dict(u=u[:m], umf=v[:m], q=q[:m], t=t[:m], w=w[:m])
 
     def reg_terms(self):
-        n = self.L.pgs_facade_n_reg_terms(self.h)
+        n = self._ck(self.L.pgs_facade_n_reg_terms(self.h))
         node = np.zeros(n, np.int32); q = np.zeros((n, 4)); t = np.zeros((n, 3)); w = np.zeros(n)
-        self._ck(self.L.pgs_facade_get_reg_terms(self.h, node.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
-        return dict(node=node, q=q, t=t, w=w)
+        m = self._ck(self.L.pgs_facade_get_reg_terms(self.h, C.c_int32(n), node.ctypes.data_as(c_ip), q.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp), w.ctypes.data_as(c_dp)))
+        return dict(node=node[:m], q=q[:m], t=t[:m], w=w[:m])
 
     def alternative_terms(self, kind):
         """Blocks of the reference's switched-off builds for this session (PoseGraphSLAM::alternative_terms), as the
@@ -207,8 +207,8 @@ class Facade:
         rot = np.zeros((n, rw)); t = np.zeros((n, 3)); c1 = np.zeros(m, np.int32); c2 = np.zeros(m, np.int32)
         obs_rot = np.zeros((m, rw)); obs_t = np.zeros((m, 3)); weight = np.zeros(m); sw = np.zeros(m)
         p = lambda a: a.ctypes.data_as(c_dp)
-        self._ck(self.L.pgs_facade_get_alternative_terms(self.h, C.c_int32(kind), p(rot), p(t), c1.ctypes.data_as(c_ip), c2.ctypes.data_as(c_ip),
-                                                         p(obs_rot), p(obs_t), p(weight), p(sw)))
+        self._ck(self.L.pgs_facade_get_alternative_terms(self.h, C.c_int32(kind), C.c_int32(n), C.c_int32(m), p(rot), p(t), c1.ctypes.data_as(c_ip),
+                                                         c2.ctypes.data_as(c_ip), p(obs_rot), p(obs_t), p(weight), p(sw)))
         return dict(rot=rot, t=t, c1=c1, c2=c2, obs_rot=obs_rot, obs_t=obs_t, weight=weight if kind in (0, 1) else None, sw=sw if kind == 1 else None)
 
     def evaluate_alternative(self, kind, jac=True):
@@ -218,7 +218,7 @@ class Facade:
         nr, nc = {0: (6, 12), 1: (7, 13), 2: (4, 8)}[kind]
         r = np.zeros((ne.value, nr)); J = np.zeros((ne.value, nr, nc)) if jac else None
         cost = C.c_double(0)
-        self._ck(self.L.pgs_facade_evaluate_alternative(self.h, C.c_int32(kind), r.ctypes.data_as(c_dp), J.ctypes.data_as(c_dp) if jac else None, C.byref(cost)))
+        self._ck(self.L.pgs_facade_evaluate_alternative(self.h, C.c_int32(kind), C.c_int32(ne.value), r.ctypes.data_as(c_dp), J.ctypes.data_as(c_dp) if jac else None, C.byref(cost)))
         return dict(cost=cost.value, r=r, J=J)
 
     def which_world(self, stamp):

@@ -250,6 +250,9 @@ def test_solver_thread_with_concurrent_ingest_and_getters():
             take = np.array(take); F.add_loop_edges(g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
         time.sleep(0.02)
     time.sleep(0.1)
+    for call in (F.odom_terms, F.reg_terms, lambda: F.alternative_terms(0)):      # the block lists belong to the running solver thread
+        with pytest.raises(pgs.PgsError, match="while the solver thread runs"):
+            call()
     n_solves = F.thread_stop(); stop = True; th.join()
     assert n_solves >= 2 and epos == len(order)
     assert F.solved_until() == 399 and F.n_nodes() == 400 and F.status() in (0, 3)
