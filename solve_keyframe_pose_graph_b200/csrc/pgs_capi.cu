@@ -1,4 +1,5 @@
 // extern "C" surface declared in include/pgs.h.  Thin: argument checks + dispatch into pgs::Solver.
+#include <exception>
 #include <new>
 #include <string>
 #include "pgs_solver.h"
@@ -9,6 +10,14 @@ static thread_local std::string g_create_error;
 struct pgs_solver_s { Solver* s; };
 
 #define H(h) do { if (!(h) || !(h)->s) return PGS_ERR_INVALID_ARGUMENT; } while (0)
+// No C++ exception may cross the C boundary (include/pgs.h): host-side containers can throw std::bad_alloc / length_error.
+#define GUARDED(h, expr)                                                                                              \
+  do {                                                                                                                \
+    try { return (expr); }                                                                                            \
+    catch (const std::bad_alloc&) { (h)->s->err = "out of host memory"; return PGS_ERR_OUT_OF_MEMORY; }               \
+    catch (const std::exception& e) { (h)->s->err = std::string("unexpected C++ exception: ") + e.what(); return PGS_ERR_STATE; } \
+    catch (...) { (h)->s->err = "unexpected C++ exception"; return PGS_ERR_STATE; }                                   \
+  } while (0)
 
 extern "C" {
 
@@ -28,41 +37,43 @@ int pgs_create(const pgs_options* opt, pgs_handle* out) {
   *out = nullptr;
   pgs_options o;
   if (opt) o = *opt; else pgs_default_options(&o);
-  Solver* s = new (std::nothrow) Solver(o);
-  if (!s) { g_create_error = "out of host memory"; return PGS_ERR_OUT_OF_MEMORY; }
-  const int rc = s->init();
-  if (rc != PGS_OK) { g_create_error = s->err; delete s; return rc; }
-  pgs_solver_s* h = new pgs_solver_s{s};
-  *out = h;
-  return PGS_OK;
+  Solver* s = nullptr;
+  try {
+    s = new Solver(o);
+    const int rc = s->init();
+    if (rc != PGS_OK) { g_create_error = s->err; delete s; return rc; }
+    *out = new pgs_solver_s{s};
+    return PGS_OK;
+  } catch (const std::bad_alloc&) { delete s; g_create_error = "out of host memory"; return PGS_ERR_OUT_OF_MEMORY; }
+  catch (const std::exception& e) { delete s; g_create_error = std::string("unexpected C++ exception: ") + e.what(); return PGS_ERR_STATE; }
 }
 int pgs_destroy(pgs_handle h) { if (!h) return PGS_OK; delete h->s; delete h; return PGS_OK; }
 const char* pgs_last_error(pgs_handle h) { return (h && h->s) ? h->s->err.c_str() : g_create_error.c_str(); }
 int pgs_get_sizes(pgs_handle h, pgs_sizes* out) { H(h); if (!out) return PGS_ERR_INVALID_ARGUMENT; h->s->sizes(out); return PGS_OK; }
 
-int pgs_set_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); return h->s->set_nodes(n, q, t, false); }
-int pgs_append_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); return h->s->set_nodes(n, q, t, true); }
-int pgs_update_nodes(pgs_handle h, int32_t first, int32_t n, const double* q, const double* t) { H(h); return h->s->update_nodes(first, n, q, t); }
-int pgs_get_poses(pgs_handle h, int32_t first, int32_t n, double* q, double* t) { H(h); return h->s->get_poses(first, n, q, t); }
-int pgs_set_constant_nodes(pgs_handle h, int32_t first, int32_t n, int32_t constant) { H(h); return h->s->set_constant(first, n, constant); }
-int pgs_set_switches(pgs_handle h, int32_t first, int32_t n, const double* s) { H(h); return h->s->set_switches(first, n, s); }
-int pgs_get_switches(pgs_handle h, int32_t first, int32_t n, double* s) { H(h); return h->s->get_switches(first, n, s); }
+int pgs_set_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); GUARDED(h, h->s->set_nodes(n, q, t, false)); }
+int pgs_append_nodes(pgs_handle h, int32_t n, const double* q, const double* t) { H(h); GUARDED(h, h->s->set_nodes(n, q, t, true)); }
+int pgs_update_nodes(pgs_handle h, int32_t first, int32_t n, const double* q, const double* t) { H(h); GUARDED(h, h->s->update_nodes(first, n, q, t)); }
+int pgs_get_poses(pgs_handle h, int32_t first, int32_t n, double* q, double* t) { H(h); GUARDED(h, h->s->get_poses(first, n, q, t)); }
+int pgs_set_constant_nodes(pgs_handle h, int32_t first, int32_t n, int32_t constant) { H(h); GUARDED(h, h->s->set_constant(first, n, constant)); }
+int pgs_set_switches(pgs_handle h, int32_t first, int32_t n, const double* s) { H(h); GUARDED(h, h->s->set_switches(first, n, s)); }
+int pgs_get_switches(pgs_handle h, int32_t first, int32_t n, double* s) { H(h); GUARDED(h, h->s->get_switches(first, n, s)); }
 int pgs_add_odom_edges(pgs_handle h, int32_t m, const int32_t* c1, const int32_t* c2, const double* q, const double* t, const double* w) {
-  H(h); return h->s->add_odom(m, c1, c2, q, t, w); }
+  H(h); GUARDED(h, h->s->add_odom(m, c1, c2, q, t, w)); }
 int pgs_add_loop_edges(pgs_handle h, int32_t m, const int32_t* a, const int32_t* b, const double* q, const double* t, const double* w) {
-  H(h); return h->s->add_loop(m, a, b, q, t, w); }
+  H(h); GUARDED(h, h->s->add_loop(m, a, b, q, t, w)); }
 int pgs_set_regularizers(pgs_handle h, int32_t k, const int32_t* node, const double* q, const double* t, const double* w) {
-  H(h); return h->s->set_regs(k, node, q, t, w); }
+  H(h); GUARDED(h, h->s->set_regs(k, node, q, t, w)); }
 int pgs_evaluate(pgs_handle h, double* cost, double* r_o, double* J_o, double* r_l, double* J_l, double* r_r, double* J_r) {
-  H(h); return h->s->evaluate(cost, r_o, J_o, r_l, J_l, r_r, J_r); }
-int pgs_gradient(pgs_handle h, double* gp, double* gs) { H(h); return h->s->gradient(gp, gs); }
+  H(h); GUARDED(h, h->s->evaluate(cost, r_o, J_o, r_l, J_l, r_r, J_r)); }
+int pgs_gradient(pgs_handle h, double* gp, double* gs) { H(h); GUARDED(h, h->s->gradient(gp, gs)); }
 int pgs_assemble(pgs_handle h, double* diag, int32_t* phi, int32_t* plo, double* off, double* lv, double* lh) {
-  H(h); return h->s->assemble(diag, phi, plo, off, lv, lh); }
-int pgs_linear_step(pgs_handle h, double radius, double* dp, double* ds, double* mcc, int32_t* it) { H(h); return h->s->linear_step(radius, dp, ds, mcc, it); }
-int pgs_solve(pgs_handle h, pgs_summary* sum, pgs_iteration* iters, int32_t cap) { H(h); return h->s->solve(sum, iters, cap); }
-int pgs_time_stream_write(pgs_handle h, int64_t bytes, int32_t reps, int32_t flush, double* ms) { H(h); return h->s->time_stream_write(bytes, reps, flush, ms); }
-int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush, double* ms, double* ms_kernel, int64_t* launches) { H(h); return h->s->time_sweep(mode, reps, flush, ms, ms_kernel, launches); }
-int pgs_evaluate_from_host(pgs_handle h, const double* q, const double* t, const double* s, double* cost) { H(h); return h->s->evaluate_from_host(q, t, s, cost); }
+  H(h); GUARDED(h, h->s->assemble(diag, phi, plo, off, lv, lh)); }
+int pgs_linear_step(pgs_handle h, double radius, double* dp, double* ds, double* mcc, int32_t* it) { H(h); GUARDED(h, h->s->linear_step(radius, dp, ds, mcc, it)); }
+int pgs_solve(pgs_handle h, pgs_summary* sum, pgs_iteration* iters, int32_t cap) { H(h); GUARDED(h, h->s->solve(sum, iters, cap)); }
+int pgs_time_stream_write(pgs_handle h, int64_t bytes, int32_t reps, int32_t flush, double* ms) { H(h); GUARDED(h, h->s->time_stream_write(bytes, reps, flush, ms)); }
+int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush, double* ms, double* ms_kernel, int64_t* launches) { H(h); GUARDED(h, h->s->time_sweep(mode, reps, flush, ms, ms_kernel, launches)); }
+int pgs_evaluate_from_host(pgs_handle h, const double* q, const double* t, const double* s, double* cost) { H(h); GUARDED(h, h->s->evaluate_from_host(q, t, s, cost)); }
 int64_t pgs_sweep_algorithmic_bytes(pgs_handle h) { if (!h || !h->s) return 0; return h->s->sweep_bytes(); }
 
 
@@ -70,7 +81,7 @@ int pgs_dist_unique_id(void* id128) {
   if (!id128) return PGS_ERR_INVALID_ARGUMENT;
   return pgs::Comm::unique_id(id128, &g_create_error);
 }
-int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128) { H(h); return h->s->dist_init(rank, world, id128); }
+int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128) { H(h); GUARDED(h, h->s->dist_init(rank, world, id128)); }
 int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out) { H(h); if (!out) return PGS_ERR_INVALID_ARGUMENT; return h->s->dist_stats(out); }
 int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t* c1, const int32_t* c2, int32_t n_loop, const int32_t* a,
                   const int32_t* b, int32_t n_reg, const int32_t* reg_node, int32_t* node_owner, int32_t* odom_owner, int32_t* loop_owner,

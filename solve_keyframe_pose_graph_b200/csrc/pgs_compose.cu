@@ -150,7 +150,7 @@ void pgs_compose_destroy(pgs_compose_handle h) {
 
 const char* pgs_compose_last_error(pgs_compose_handle h) { return h ? h->err.c_str() : "null handle"; }
 
-int pgs_compose_run(pgs_compose_handle h, const pgs_compose_input* in, double* out_T) {
+int pgs_compose_run(pgs_compose_handle h, const pgs_compose_input* in, double* out_T) try {
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
   if (!in || in->n_nodes < 0 || in->n_slam < 0 || in->n_worlds < 0 || (in->n_nodes > 0 && (!in->mgr_T || !in->world_id || !out_T)) ||
       (in->n_slam > 0 && (!in->slam_q || !in->slam_t)) || (in->n_worlds > 0 && (!in->world_end || !in->world_setid || !in->ws_exists || !in->ws_T_w))) {
@@ -192,6 +192,9 @@ int pgs_compose_run(pgs_compose_handle h, const pgs_compose_input* in, double* o
   CCU(cudaEventElapsedTime(&a, h->e1, h->e2)); CCU(cudaEventElapsedTime(&b, h->e0, h->e3));
   h->ms_kernel = a; h->ms_total = b;
   return PGS_OK;
+} catch (const std::exception& e) {   // nothing may be thrown across the C boundary
+  if (h) h->err = std::string("unexpected C++ exception: ") + e.what();
+  return PGS_ERR_STATE;
 }
 
 int pgs_compose_last_timing(pgs_compose_handle h, double* ms_kernel, double* ms_total) {

@@ -142,7 +142,7 @@ void pgs_fourdof_destroy(pgs_fourdof_handle h) {
 
 const char* pgs_fourdof_last_error(pgs_fourdof_handle h) { return h ? h->err.c_str() : "null handle"; }
 
-int pgs_fourdof_evaluate(pgs_fourdof_handle h, const pgs_fourdof_input* in, double* r, double* J, double* cost) {
+int pgs_fourdof_evaluate(pgs_fourdof_handle h, const pgs_fourdof_input* in, double* r, double* J, double* cost) try {
   using namespace pgs::fourdof;
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
   if (!in || in->kind < PGS_FOURDOF_ERROR || in->kind > PGS_FOURDOF_QIN || in->n_nodes < 0 || in->n_edges < 0) { h->err = "pgs_fourdof_evaluate: bad kind or negative size"; return PGS_ERR_INVALID_ARGUMENT; }
@@ -189,6 +189,9 @@ int pgs_fourdof_evaluate(pgs_fourdof_handle h, const pgs_fourdof_input* in, doub
   float ms = 0; FCU(cudaEventElapsedTime(&ms, h->e0, h->e1)); h->ms_kernel = ms;
   if (cost) { double c = 0; for (int k = 0; k < tiles; ++k) c += h->h_cost[k]; *cost = c; }   // tile order: reproducible
   return PGS_OK;
+} catch (const std::exception& e) {   // nothing may be thrown across the C boundary
+  if (h) h->err = std::string("unexpected C++ exception: ") + e.what();
+  return PGS_ERR_STATE;
 }
 
 int pgs_fourdof_last_timing(pgs_fourdof_handle h, double* ms_kernel) {
