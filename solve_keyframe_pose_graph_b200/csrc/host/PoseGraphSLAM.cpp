@@ -314,10 +314,12 @@ bool PoseGraphSLAM::solve_once(bool force) {
     n_device_nodes_ = node_len; n_device_loops_ += (int)new_la.size();
 
     status = 2;
-    iterations_.assign(opt_.solver.max_num_iterations + 8, pgs_iteration{});
-    rc = pgs_solve(handle_, &summary_, iterations_.data(), (int)iterations_.size());
+    pgs_summary sum{};
+    std::vector<pgs_iteration> its(opt_.solver.max_num_iterations + 8, pgs_iteration{});
+    rc = pgs_solve(handle_, &sum, its.data(), (int)its.size());
     if (rc != PGS_OK) return fail(std::string("pgs_solve: ") + pgs_last_error(handle_));
-    iterations_.resize(std::min<size_t>(iterations_.size(), (size_t)summary_.num_iterations));
+    its.resize(std::min<size_t>(its.size(), (size_t)std::max(sum.num_iterations, 0)));
+    { std::lock_guard<std::mutex> lk(mutex_summary_); summary_ = sum; iterations_.swap(its); }   // readers on other threads get copies
     // read the solution back and publish it under the mutex in one go: like Ceres with
     // update_state_every_iteration=false, readers only ever see the state of a finished solve
     std::vector<double> sw(n_device_loops_);

@@ -76,8 +76,8 @@ class PoseGraphSLAM {
   int get_loopedge_residue_info_size() const;
 
   // ---- introspection for tests / bench
-  const pgs_summary& last_summary() const { return summary_; }
-  const std::vector<pgs_iteration>& last_iterations() const { return iterations_; }
+  pgs_summary last_summary() const { std::lock_guard<std::mutex> lk(mutex_summary_); return summary_; }
+  std::vector<pgs_iteration> last_iterations() const { std::lock_guard<std::mutex> lk(mutex_summary_); return iterations_; }
   struct RegTerm { int node; Matrix4d anchor; double weight; };
   const std::vector<RegTerm>& regularization_terms() const { return reg_terms_; }
   struct OdomTerm { int u, umf; double q[4], t[3], weight; };
@@ -135,6 +135,7 @@ class PoseGraphSLAM {
   int n_constant_on_device_ = 0;
 
   pgs_handle handle_ = nullptr;
+  mutable std::mutex mutex_summary_;   // summary_ / iterations_ are published by the solver thread at the end of a solve
   pgs_summary summary_{};
   std::vector<pgs_iteration> iterations_;
 };

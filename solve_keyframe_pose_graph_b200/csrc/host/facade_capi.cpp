@@ -149,7 +149,7 @@ int pgs_facade_get_switches(pgs_facade_handle h, int32_t n, double* s) try {
 int pgs_facade_get_summary(pgs_facade_handle h, pgs_summary* s, pgs_iteration* iters, int32_t cap) try {
   if (!h) return PGS_ERR_INVALID_ARGUMENT;
   if (s) *s = h->slam->last_summary();
-  const auto& it = h->slam->last_iterations();
+  const std::vector<pgs_iteration> it = h->slam->last_iterations();
   for (int i = 0; iters && i < cap && i < (int)it.size(); ++i) iters[i] = it[i];
   return PGS_OK;
 } CATCH_FACADE(h)
