@@ -128,7 +128,7 @@ void PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF() {
 }
 
 bool PoseGraphSLAM::load_state() {
-  error_.clear();
+  clear_error();
   const int node_len = manager->getNodeLen();
   if (node_len == 0) return fail("load_state: no keyframes in the manager (the reference exits here, PoseGraphSLAM.cpp:54-59)");
   const Worlds* worlds = manager->getWorldsConstPtr();
@@ -149,7 +149,7 @@ bool PoseGraphSLAM::load_state() {
 }
 
 bool PoseGraphSLAM::solve_once(bool force) {
-  error_.clear();
+  clear_error();
   const int node_len = manager->getNodeLen();
   const int loopedge_len = manager->getEdgeLen();
   // trigger only on new loop edges, never while kidnapped (PoseGraphSLAM.cpp:1306-1319)

@@ -55,7 +55,7 @@ class PoseGraphSLAM {
   // this fixed backbone.  false: no keyframes, or a world whose set transform is unknown (the reference exits).
   bool load_state();
   bool saveAsJSON(const std::string base_path) const;      // log_optimized_poses.json (PoseGraphSLAM.cpp:1111-1207); defined in GraphIO.cpp
-  const std::string& last_error() const { return error_; }
+  std::string last_error() const { std::lock_guard<std::mutex> lk(mutex_error_); return error_; }   // a copy: the solver thread may rewrite it
 
   // Explicit-graph API (north_star).  Poses are 4x4: a_T_b for odometry (binds SixDOFError(a, b)),
   // b_T_a for loop edges (stored in the manager, bound as (b, a, switch)).
@@ -97,7 +97,8 @@ class PoseGraphSLAM {
   bool alternative_terms(int kind, AlternativeTerms& out) const;
 
  private:
-  bool fail(const std::string& msg) { error_ = msg; status = 0; return false; }
+  bool fail(const std::string& msg) { { std::lock_guard<std::mutex> lk(mutex_error_); error_ = msg; } status = 0; return false; }
+  void clear_error() { std::lock_guard<std::mutex> lk(mutex_error_); error_.clear(); }
   void allocate_and_append_new_opt_variable_withpose(const Matrix4d& pose);
   bool update_opt_variable_with(int i, const Matrix4d& pose);
   void allocate_and_append_new_edge_switch_var();
@@ -109,6 +110,7 @@ class PoseGraphSLAM {
   std::atomic<bool> isEnabled;
   std::atomic<int> status;
   std::atomic<int> n_solves_{0};
+  mutable std::mutex mutex_error_;
   std::string error_;
 
   mutable std::mutex mutex_opt_vars;

@@ -54,7 +54,11 @@ int pgs_facade_create(const pgs_facade_options* o, pgs_facade_handle* out) try {
   return PGS_OK;
 } CATCH_IO
 void pgs_facade_destroy(pgs_facade_handle h) { delete h; }
-const char* pgs_facade_last_error(pgs_facade_handle h) { return h ? (h->err.empty() ? h->slam->last_error().c_str() : h->err.c_str()) : ""; }
+const char* pgs_facade_last_error(pgs_facade_handle h) {
+  static thread_local std::string snapshot;     // valid until the calling thread asks again
+  try { snapshot = h ? (h->err.empty() ? h->slam->last_error() : h->err) : std::string(); } catch (...) { return "out of host memory"; }
+  return snapshot.c_str();
+}
 
 int pgs_facade_add_nodes(pgs_facade_handle h, int32_t n, const int64_t* stamps, const double* q, const double* t) try {
   if (!h || n < 0 || (n && (!stamps || !q || !t))) return PGS_ERR_INVALID_ARGUMENT;
