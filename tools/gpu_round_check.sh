@@ -3,6 +3,10 @@
 # sweep, launch list of the skyline factorisation.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+# round 1 ended with an xdist worker crash that was traced to a buffer overrun in pgs_facade_compose: confirm the fix, full output kept
+python -m pytest tests -m gpu -q -n 4 --dist loadfile > gpurun_out/gpu_suite_xdist.txt 2>&1; tail -3 gpurun_out/gpu_suite_xdist.txt
+python tools/facade_alternative_check.py 2>&1 | tail -4
+python tools/fourdof_bench.py > gpurun_out/fourdof_bench.txt 2>&1; cat gpurun_out/fourdof_bench.txt
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cut -c1-3000 gpurun_out/bench.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>&1; cut -c1-400 gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 5 --warmup 3 --no-lm --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
