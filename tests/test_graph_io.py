@@ -169,3 +169,29 @@ def test_mutated_state_files_are_rejected_or_loaded_but_never_crash(tmp_path):
                 rejected += 1
         G.close(); shutil.rmtree(d)
     assert accepted > 0 and rejected > 0
+
+
+def test_replay_tool_reads_a_recorded_run_and_compares_with_its_recorded_solution(tmp_path):
+    """tests/replay_reference_run.py on a directory laid out as the reference leaves it (log_posegraph.json +
+    log_optimized_poses.json).  The recorded solution here is the oracle's own, written in the reference's format, so the
+    CPU replay must land on it: this checks the readers, the block construction from a recorded graph and the comparison,
+    which is what a real recorded run would go through."""
+    import replay_reference_run as rr
+    from oracle import frontend, pgo
+    g = synth.generate_config(2, n_nodes=150, n_loop=20)
+    F = facade.Facade(dry_run=True); F.ingest(g); assert F.solve_once(); F.save_json(tmp_path); F.close()
+    M = frontend.Manager(); M.ingest(g)
+    R = frontend.ReferenceFrontEnd(M, odom_fanout=5); s = R.trigger(solve=True)
+    J = json.load(open(tmp_path / "log_optimized_poses.json"))
+    assert len(J["PoseGraphSLAM_nodes"]) == 150
+    for i, node in enumerate(J["PoseGraphSLAM_nodes"]):
+        node["wTc_opt"] = facade.io_mat_to_string(pgo.pose_to_mat4(R.opt_q[i], R.opt_t[i]))
+    for e in J["PoseGraphSLAM_loopedgeinfo"]:
+        e["switching_var_after_opt"] = R.opt_s[e["getEdge_i"]]
+    json.dump(J, open(tmp_path / "log_optimized_poses.json", "w"))
+    out = rr.replay(str(tmp_path), use_oracle=True, fanout=5)
+    assert out["nodes"] == 150 and out["loop_edges"] == 20 and out["blocks"]["odometry"] == len(R.odom) and out["blocks"]["regularisers"] == 1
+    assert out["translation_dev_m"]["max"] < 1e-9 and out["rotation_dev_rad"]["max"] < 1e-7
+    assert out["switches"] == dict(compared=20, same_state=20)
+    assert abs(out["cost_of_reference_solution"] - s["final_cost"]) <= 1e-9 * s["final_cost"] and out["cost_at_odometry"] > s["final_cost"]
+    assert abs(out["final_cost"] - s["final_cost"]) <= 1e-12 * s["final_cost"]
