@@ -1,10 +1,9 @@
 // Minimal JSON value / parser / writer for the reference's on-disk formats.  The reference
 // uses nlohmann::json (vendored, out of scope); the writer reproduces what `dump(4)` / `std::setw(4) << j` emit —
-// keys in alphabetical order (nlohmann's object is a std::map), 4-space indent, integers as integers, doubles in
-// shortest round-trip form with a trailing ".0" when integral — so files written here diff cleanly against files
-// written by the reference.
+// keys in alphabetical order (nlohmann's object is a std::map), 4-space indent, integers as integers, doubles through
+// the library's own Grisu2 + layout rule (Grisu2.h) — so files written here are byte-identical to what the reference's
+// build writes for the same values (tests/test_reference_json.py checks that against the reference's vendored library).
 #pragma once
-#include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -12,6 +11,8 @@
 #include <memory>
 #include <string>
 #include <vector>
+
+#include "Grisu2.h"
 
 namespace pgs {
 
@@ -78,9 +79,7 @@ class Json {
       case Int: out += std::to_string(i_); break;
       case Double: {
         if (!std::isfinite(d_)) { out += "null"; break; }          // nlohmann writes null for NaN / inf
-        char b[40]; auto r = std::to_chars(b, b + sizeof(b), d_); std::string s(b, r.ptr);
-        if (s.find_first_of(".eE") == std::string::npos) s += ".0";
-        out += s; break;
+        out += grisu2::to_string(d_); break;
       }
       case String: write_string(out, s_); break;
       case Array:
