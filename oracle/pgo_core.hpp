@@ -12,9 +12,12 @@
 //
 // "Parity unpinned": the reference ships no test that pins a numerical result of this
 // path and Ceres/Eigen are not available in the build container, so this restatement is
-// anchored only by its own known-answer tests (tests/test_oracle_*.py): functor KATs,
+// anchored by its own known-answer tests (tests/test_oracle_*.py): functor KATs,
 // Jet-autodiff == closed form == central differences, dense cross-checks of the linear
-// solve.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
+// solve — and, for the TEXT of the functors, by the reference's own src/CeresResidues.h
+// compiled unmodified over a stand-in for the Eigen/Ceres API (oracle/shim/,
+// oracle/_ref/libref_functors.so, tests/test_reference_functors.py).  Eigen's arithmetic
+// and Ceres' minimiser remain restated.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
 // arm may include or link this directory.  The product (solve_keyframe_pose_graph_b200/)
 // never does.
 #pragma once
@@ -56,6 +59,18 @@ template <int N> inline Jet<N> sqrt(const Jet<N>& f) {
   Jet<N> h; h.a = std::sqrt(f.a); const double d = 0.5 / h.a;
   for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * d; return h; }
 inline double sqrt(double x) { return std::sqrt(x); }
+// trigonometry for the (switched-off) yaw/pitch/roll functors, pgo_fourdof.hpp
+template <int N> inline Jet<N> sin(const Jet<N>& f) { Jet<N> h; h.a = std::sin(f.a); const double c = std::cos(f.a);
+  for (int i = 0; i < N; ++i) h.v[i] = c * f.v[i]; return h; }
+template <int N> inline Jet<N> cos(const Jet<N>& f) { Jet<N> h; h.a = std::cos(f.a); const double s = -std::sin(f.a);
+  for (int i = 0; i < N; ++i) h.v[i] = s * f.v[i]; return h; }
+// ceres/jet.h: atan2(g, f) = atan2(g.a, f.a), derivative (-g.a f.v + f.a g.v) / (f.a^2 + g.a^2)
+template <int N> inline Jet<N> atan2(const Jet<N>& g, const Jet<N>& f) { Jet<N> h; h.a = std::atan2(g.a, f.a);
+  const double tmp = 1.0 / (f.a * f.a + g.a * g.a);
+  for (int i = 0; i < N; ++i) h.v[i] = tmp * (-g.a * f.v[i] + f.a * g.v[i]); return h; }
+inline double sin(double x) { return std::sin(x); }
+inline double cos(double x) { return std::cos(x); }
+inline double atan2(double y, double x) { return std::atan2(y, x); }
 inline double scalar_of(double x) { return x; }
 template <int N> inline double scalar_of(const Jet<N>& x) { return x.a; }
 

@@ -16,18 +16,6 @@
 
 namespace pgo {
 
-template <int N> inline Jet<N> sin(const Jet<N>& f) { Jet<N> h; h.a = std::sin(f.a); const double c = std::cos(f.a);
-  for (int i = 0; i < N; ++i) h.v[i] = c * f.v[i]; return h; }
-template <int N> inline Jet<N> cos(const Jet<N>& f) { Jet<N> h; h.a = std::cos(f.a); const double s = -std::sin(f.a);
-  for (int i = 0; i < N; ++i) h.v[i] = s * f.v[i]; return h; }
-// ceres/jet.h: atan2(g, f) = atan2(g.a, f.a), derivative (-g.a f.v + f.a g.v) / (f.a^2 + g.a^2)
-template <int N> inline Jet<N> atan2(const Jet<N>& g, const Jet<N>& f) { Jet<N> h; h.a = std::atan2(g.a, f.a);
-  const double tmp = 1.0 / (f.a * f.a + g.a * g.a);
-  for (int i = 0; i < N; ++i) h.v[i] = tmp * (-g.a * f.v[i] + f.a * g.v[i]); return h; }
-inline double sin(double x) { return std::sin(x); }
-inline double cos(double x) { return std::cos(x); }
-inline double atan2(double y, double x) { return std::atan2(y, x); }
-
 // src/CeresResidues.h:226-243
 template <class T> inline void R2ypr_T(const Mat3<T>& R, T ypr[3]) {
   const T n0 = R.m[0][0], n1 = R.m[1][0], n2 = R.m[2][0];   // n = R.col(0)
