@@ -5,31 +5,18 @@
 // Eigen / Ceres API that file uses, because neither library exists in this container (see oracle/shim/mini_eigen.hpp
 // for exactly what that does and does not pin).  oracle/Makefile builds this into oracle/_ref/libref_functors.so;
 // tests/test_reference_functors.py compares the oracle's restatement (pgo_core.hpp, pgo_fourdof.hpp) with it.
+// The same library holds the reference's src/utils/PoseManipUtils.cpp, compiled from where it lies as a second
+// translation unit (conversions between (quaternion, t), (yaw/pitch/roll, t) and 4x4, R2ypr / ypr2R, the
+// `data_pretty` printer and the `a,b;c,d` matrix parser), reachable through the ref_pmu_* functions below.
 // Differentiation: the functors are instantiated with pgo::Jet (ambient parameters), then every quaternion block is
 // multiplied by the 4x3 Plus-Jacobian of EigenQuaternionParameterization — what ceres::AutoDiffCostFunction and the
 // local parameterisation do.
+#include <cstring>
 #include <type_traits>
 
 #include "pgo_core.hpp"           // pgo::Jet with its sqrt / sin / cos / atan2 (found by ADL from the reference's templates), quat_plus_jacobian
 
 #include "CeresResidues.h"        // -I /root/reference/src : the reference's file
-
-// Two members of the reference's PoseManipUtils that the (switched-off) FourDOF constructors call; PoseManipUtils.cpp
-// itself needs more of Eigen than the shim has, so these two are restated from src/utils/PoseManipUtils.cpp:136-158.
-// The values they produce (the observation as yaw/pitch/roll) are stored by the constructors and never read.
-Vector3d PoseManipUtils::R2ypr(const Matrix3d& R) {
-  Vector3d n = R.col(0), o = R.col(1), a = R.col(2);
-  Vector3d ypr(3);
-  const double y = atan2(n(1), n(0));
-  const double p = atan2(-n(2), n(0) * cos(y) + n(1) * sin(y));
-  const double r = atan2(a(0) * sin(y) - a(1) * cos(y), -o(0) * sin(y) + o(1) * cos(y));
-  ypr(0) = y; ypr(1) = p; ypr(2) = r;
-  return ypr / M_PI * 180.0;
-}
-void PoseManipUtils::eigenmat_to_rawyprt(const Matrix4d& T, Vector3d& ypr, Vector3d& t) {
-  ypr = R2ypr(T.topLeftCorner<3, 3>());
-  t << T(0, 3), T(1, 3), T(2, 3);
-}
 
 namespace {
 
@@ -112,6 +99,14 @@ void ref_qin(double yaw_i, const double* ti, double yaw_j, const double* tj, con
     for (int c = 0; c < 8; ++c) J[8 * i + c] = res[i].v[c] * (c == 0 ? Pi : c == 4 ? Pj : 1.0);
   }
 }
+// ---- the reference's PoseManipUtils (src/utils/PoseManipUtils.cpp, real source)
+void ref_pmu_raw_xyzw_to_eigenmat(const double* q, const double* t, double* M16) { Matrix4d M; PoseManipUtils::raw_xyzw_to_eigenmat(q, t, M); for (int i = 0; i < 16; ++i) M16[i] = M.a[i]; }
+void ref_pmu_eigenmat_to_raw_xyzw(const double* M16, double* q, double* t) { PoseManipUtils::eigenmat_to_raw_xyzw(mat16(M16), q, t); }
+void ref_pmu_rawyprt_to_eigenmat(const double* ypr, const double* t, double* M16) { Matrix4d M; PoseManipUtils::rawyprt_to_eigenmat(ypr, t, M); for (int i = 0; i < 16; ++i) M16[i] = M.a[i]; }
+void ref_pmu_eigenmat_to_rawyprt(const double* M16, double* ypr, double* t) { PoseManipUtils::eigenmat_to_rawyprt(mat16(M16), ypr, t); }
+int ref_pmu_prettyprint(const double* M16, char* out, int cap) { const std::string s = PoseManipUtils::prettyprintMatrix4d(mat16(M16)); if ((int)s.size() + 1 > cap) return -1; std::memcpy(out, s.c_str(), s.size() + 1); return (int)s.size(); }
+int ref_pmu_string_to_eigenmat(const char* s, double* M16) { Matrix4d M = Matrix4d::Zero(); const bool ok = PoseManipUtils::string_to_eigenmat(std::string(s), M); for (int i = 0; i < 16; ++i) M16[i] = M.a[i]; return ok ? 1 : 0; }
+
 double ref_normalize_angle(double a) { return NormalizeAngle(a); }
 double ref_angle_plus(double theta, double delta) { AngleLocalParameterization p; double out; p(&theta, &delta, &out); return out; }
 void ref_ypr_to_R(double y, double p, double r, double* R9) { YawPitchRollToRotationMatrix(y, p, r, R9); }

@@ -11,8 +11,10 @@
 //
 // Deliberately small and slow: every matrix is a runtime-sized value with room for 6x6; no expression templates.
 #pragma once
+#include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -79,6 +81,11 @@ template <class T> Dyn<T> operator*(const T& s, const Dyn<T>& x) { Dyn<T> o(x.r,
 template <class T> Dyn<T> operator*(const Dyn<T>& x, const T& s) { Dyn<T> o(x.r, x.c); for (int i = 0; i < x.r * x.c; ++i) o.a[i] = x.a[i] * s; return o; }
 template <class T> Dyn<T> operator/(const Dyn<T>& x, const T& s) { Dyn<T> o(x.r, x.c); for (int i = 0; i < x.r * x.c; ++i) o.a[i] = x.a[i] / s; return o; }
 template <class T> Dyn<T> operator*(const T& s, const BlockRef<T>& b) { return s * Dyn<T>(b); }
+// console output only (the reference prints matrices in its debug helpers); not Eigen's IOFormat
+template <class T> std::ostream& operator<<(std::ostream& os, const Dyn<T>& m) {
+  for (int i = 0; i < m.r; ++i) { for (int j = 0; j < m.c; ++j) os << (j ? " " : "") << m(i, j); if (i + 1 < m.r) os << "\n"; }
+  return os;
+}
 
 template <class T> Dyn<T> Dyn<T>::inverse() const {
   assert(r == 4 && c == 4);
@@ -114,7 +121,9 @@ struct Matrix : Dyn<T> {
   Matrix(const BlockRef<T>& b) : Matrix(Dyn<T>(b)) {}
   static Matrix Identity() { Matrix m; for (int i = 0; i < R && i < C; ++i) m(i, i) = T(1.0); return m; }
   static Matrix Zero() { return Matrix(); }
+  Matrix(const T& x, const T& y, const T& z) : Dyn<T>(R, C) { assert(R * C == 3); this->a[0] = x; this->a[1] = y; this->a[2] = z; }
   using Dyn<T>::topLeftCorner;
+  template <int P, int Q> BlockRef<T> topLeftCorner() { return BlockRef<T>{this, 0, 0, P, Q}; }
   template <int P, int Q> Matrix<T, P, Q> topLeftCorner() const { return Matrix<T, P, Q>(static_cast<const Dyn<T>&>(*this).topLeftCorner(P, Q)); }
   template <class U> Matrix<U, R, C> cast() const { return Matrix<U, R, C>(Dyn<T>::template cast<U>()); }
   Matrix<T, R, C> inverse() const { return Matrix<T, R, C>(Dyn<T>::inverse()); }
@@ -147,6 +156,7 @@ struct Quaternion {
     }
     x_ = q[0]; y_ = q[1]; z_ = q[2]; w_ = q[3];
   }
+  explicit Quaternion(const BlockRef<T>& b) : Quaternion(Dyn<T>(b)) {}
   const T& x() const { return x_; } const T& y() const { return y_; } const T& z() const { return z_; } const T& w() const { return w_; }
   Quaternion conjugate() const { return Quaternion(w_, -x_, -y_, -z_); }
   Quaternion operator*(const Quaternion& b) const {                        // Hamilton product

@@ -136,3 +136,68 @@ def test_angle_helpers_equal_the_reference_source(ref):
         ref.ref_r2ypr(ptr(R9), ptr(ypr))
         M = np.eye(4); M[:3, :3] = R9.reshape(3, 3)
         assert np.allclose(ypr, pgo.r2ypr_deg(M), rtol=0, atol=1e-12) and np.allclose(ypr, [y, p, r], atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ PoseManipUtils (real source)
+@pytest.fixture(scope="module")
+def pmu(ref):
+    ref.ref_pmu_raw_xyzw_to_eigenmat.argtypes = [dp, dp, dp]
+    ref.ref_pmu_eigenmat_to_raw_xyzw.argtypes = [dp, dp, dp]
+    ref.ref_pmu_rawyprt_to_eigenmat.argtypes = [dp, dp, dp]
+    ref.ref_pmu_eigenmat_to_rawyprt.argtypes = [dp, dp, dp]
+    ref.ref_pmu_prettyprint.argtypes = [dp, C.c_char_p, C.c_int]
+    ref.ref_pmu_string_to_eigenmat.argtypes = [C.c_char_p, dp]
+    return ref
+
+
+def test_pose_conversions_equal_the_reference_pose_manip_utils(pmu):
+    """src/utils/PoseManipUtils.cpp compiled from where it lies (over the same shim): (q xyzw, t) <-> 4x4 and
+    (yaw, pitch, roll degrees, t) <-> 4x4 against the oracle's helpers, both hemispheres and all branches of
+    Quaterniond(Matrix3d)."""
+    rng = np.random.default_rng(6)
+    M = np.zeros(16); q2 = np.zeros(4); t2 = np.zeros(3); ypr = np.zeros(3)
+    for k in range(300):
+        q, t = arr(rq(rng)), arr(rng.normal(size=3) * 10)
+        if k % 3 == 0:                                                   # rotations by ~pi: the trace <= 0 branches
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = np.pi - rng.uniform(0, 0.05)
+            q = arr(np.r_[np.sin(ang / 2) * ax, np.cos(ang / 2)])
+        pmu.ref_pmu_raw_xyzw_to_eigenmat(ptr(q), ptr(t), ptr(M))
+        assert np.array_equal(M.reshape(4, 4), pgo.pose_to_mat4(q, t))
+        pmu.ref_pmu_eigenmat_to_raw_xyzw(ptr(M), ptr(q2), ptr(t2))
+        qo, to = pgo.mat4_to_pose(M.reshape(4, 4))
+        assert np.array_equal(q2, qo) and np.array_equal(t2, to) and abs(abs(float(np.dot(q2, q))) - 1) < 1e-12
+        pmu.ref_pmu_eigenmat_to_rawyprt(ptr(M), ptr(ypr), ptr(t2))
+        assert np.allclose(ypr, pgo.r2ypr_deg(M.reshape(4, 4)), rtol=0, atol=1e-12)
+        M2 = np.zeros(16)
+        pmu.ref_pmu_rawyprt_to_eigenmat(ptr(ypr), ptr(t), ptr(M2))      # ypr2R = Rz Ry Rx as three products (:162-187)
+        assert np.allclose(M2.reshape(4, 4)[:3, :3], pgo.ypr_to_R(*ypr), rtol=0, atol=1e-15)
+        assert np.allclose(M2.reshape(4, 4), M.reshape(4, 4), rtol=0, atol=1e-12)
+
+
+def test_matrix_text_formats_equal_the_reference_pose_manip_utils(pmu):
+    """The `data_pretty` printer and the `a,b,c,d;...` parser of the reference, byte for byte / value for value, against
+    the product's (csrc/host/GraphIO.cpp through the C-ABI) — including values that print as -0.000 and 10.000."""
+    from solve_keyframe_pose_graph_b200 import facade
+    rng = np.random.default_rng(7)
+    buf = C.create_string_buffer(256); M2 = np.zeros(16)
+    for k in range(300):
+        q, t = rq(rng), rng.normal(size=3) * 10.0 ** rng.integers(-5, 3)
+        if k % 4 == 0:
+            t[rng.integers(0, 3)] = -1e-5                                # "-0.000"
+        if k % 5 == 0:
+            q = np.array([0, 0, 0, 1.0]) if k % 10 else pgo.quat_plus(np.array([0, 0, 0, 1.0]), [0, 0, 1e-7])
+        M = arr(pgo.pose_to_mat4(q, t))
+        assert pmu.ref_pmu_prettyprint(ptr(M), buf, 256) > 0
+        assert facade.io_prettyprint(M) == buf.value.decode()
+        for layout in (False, True):                                     # log_posegraph.json and solved_posegraph.json spellings
+            s = facade.io_mat_to_string(M, solved_layout=layout)
+            ours = facade.io_string_to_mat(s)                            # 16 significant digits (Eigen FullPrecision): close, not lossless
+            assert np.allclose(ours, M.reshape(4, 4), rtol=1e-15, atol=1e-300)
+            if not layout:                                               # the reference's parser reads the ';' layout (:272-295)
+                assert pmu.ref_pmu_string_to_eigenmat(s.encode(), ptr(M2)) == 1 and np.array_equal(M2.reshape(4, 4), ours)
+    # the strings quoted in the reference's own source parse the same way in both
+    import json
+    sample = json.load(open(os.path.join(HERE, "golden", "reference_solved_posegraph_sample.json")))
+    for node in sample["SolvedPoseGraph"]:
+        T = facade.io_string_to_mat(node["w_T_c"]["data"])
+        assert pmu.ref_pmu_prettyprint(ptr(arr(T)), buf, 256) > 0 and buf.value.decode() == node["w_T_c"]["data_pretty"]
