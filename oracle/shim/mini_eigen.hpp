@@ -15,6 +15,7 @@
 #include <cassert>
 #include <cmath>
 #include <iostream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -60,6 +61,7 @@ struct Dyn {
   Dyn topLeftCorner(int rr, int cc) const { Dyn o(rr, cc); for (int i = 0; i < rr; ++i) for (int j = 0; j < cc; ++j) o(i, j) = (*this)(i, j); return o; }
   Dyn topRows(int n) const { return topLeftCorner(n, c); }
   Dyn& operator*=(const T& s) { for (int i = 0; i < r * c; ++i) a[i] = a[i] * s; return *this; }
+  inline Dyn& operator*=(const Dyn& o);
   CommaInit<T> operator<<(const T& v) { a[0] = v; return CommaInit<T>{this, 1}; }
   template <class U> Dyn<U> cast() const { Dyn<U> o(r, c); for (int i = 0; i < r * c; ++i) o.a[i] = U(a[i]); return o; }
   Dyn transpose() const { Dyn o(c, r); for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) o(j, i) = (*this)(i, j); return o; }
@@ -77,6 +79,7 @@ template <class T> Dyn<T> operator*(const Dyn<T>& x, const Dyn<T>& y) {
   for (int i = 0; i < x.r; ++i) for (int j = 0; j < y.c; ++j) { T s = x(i, 0) * y(0, j); for (int k = 1; k < x.c; ++k) s = s + x(i, k) * y(k, j); o(i, j) = s; }
   return o;
 }
+template <class T> inline Dyn<T>& Dyn<T>::operator*=(const Dyn<T>& o) { const Dyn<T> p = (*this) * o; for (int i = 0; i < p.r * p.c; ++i) a[i] = p.a[i]; return *this; }
 template <class T> Dyn<T> operator*(const T& s, const Dyn<T>& x) { Dyn<T> o(x.r, x.c); for (int i = 0; i < x.r * x.c; ++i) o.a[i] = s * x.a[i]; return o; }
 template <class T> Dyn<T> operator*(const Dyn<T>& x, const T& s) { Dyn<T> o(x.r, x.c); for (int i = 0; i < x.r * x.c; ++i) o.a[i] = x.a[i] * s; return o; }
 template <class T> Dyn<T> operator/(const Dyn<T>& x, const T& s) { Dyn<T> o(x.r, x.c); for (int i = 0; i < x.r * x.c; ++i) o.a[i] = x.a[i] / s; return o; }
@@ -113,14 +116,39 @@ template <class T> Dyn<T> Dyn<T>::inverse() const {
   return o;
 }
 
+// Eigen's IOFormat as far as the reference uses it: IOFormat(FullPrecision, DontAlignCols, ", ", "\n") (RawFileIO.h:95-106).
+// FullPrecision prints 16 significant digits for double (the sample quoted in src/NodeDataManager.cpp:892-995 shows them).
+enum { FullPrecision = -1, StreamPrecision = -2, DontAlignCols = 1 };
+struct IOFormat {
+  int precision, flags; std::string coeffSeparator, rowSeparator;
+  IOFormat(int p = StreamPrecision, int f = 0, const std::string& cs = " ", const std::string& rs = "\n") : precision(p), flags(f), coeffSeparator(cs), rowSeparator(rs) {}
+};
+template <class T> struct Formatted { const Dyn<T>* m; IOFormat f; };
+template <class T> std::ostream& operator<<(std::ostream& os, const Formatted<T>& w) {
+  const std::streamsize old = os.precision(w.f.precision == FullPrecision ? 16 : os.precision());
+  for (int i = 0; i < w.m->r; ++i) { for (int j = 0; j < w.m->c; ++j) os << (j ? w.f.coeffSeparator : "") << (*w.m)(i, j); if (i + 1 < w.m->r) os << w.f.rowSeparator; }
+  os.precision(old);
+  return os;
+}
+template <class Derived> struct MatrixBase {
+  const Derived& derived() const { return *static_cast<const Derived*>(this); }
+  template <class D = Derived> Formatted<typename D::Scalar> format(const IOFormat& f) const { return Formatted<typename D::Scalar>{&derived(), f}; }
+  template <class D = Derived> int rows() const { return static_cast<const D*>(this)->r; }
+  template <class D = Derived> int cols() const { return static_cast<const D*>(this)->c; }
+};
+
 template <class T, int R, int C>
-struct Matrix : Dyn<T> {
+struct Matrix : Dyn<T>, MatrixBase<Matrix<T, R, C>> {
+  typedef T Scalar;
   Matrix() : Dyn<T>(R, C) {}
   explicit Matrix(int) : Dyn<T>(R, C) {}                                   // "Matrix<T,3,1> ypr(3)"
   Matrix(const Dyn<T>& d) : Dyn<T>(R, C) { assert(d.r * d.c == R * C); for (int i = 0; i < R * C; ++i) this->a[i] = d.a[i]; }
   Matrix(const BlockRef<T>& b) : Matrix(Dyn<T>(b)) {}
   static Matrix Identity() { Matrix m; for (int i = 0; i < R && i < C; ++i) m(i, i) = T(1.0); return m; }
   static Matrix Zero() { return Matrix(); }
+  static Matrix Zero(int rr, int cc = 1) { Matrix m; assert(rr * cc <= 36); m.r = rr; m.c = cc; return m; }   // the "dynamic" stand-ins
+  using Dyn<T>::rows;
+  using Dyn<T>::cols;
   Matrix(const T& x, const T& y, const T& z) : Dyn<T>(R, C) { assert(R * C == 3); this->a[0] = x; this->a[1] = y; this->a[2] = z; }
   using Dyn<T>::topLeftCorner;
   template <int P, int Q> BlockRef<T> topLeftCorner() { return BlockRef<T>{this, 0, 0, P, Q}; }
@@ -132,6 +160,10 @@ typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<double, 6, 6> MatrixXd;      // "dynamic" types only appear in declarations the tests never reach
+typedef Matrix<float, 6, 6> MatrixXf;
+typedef Matrix<double, 6, 1> VectorXd;
+typedef Matrix<int, 6, 1> VectorXi;
 
 template <class T>
 struct Quaternion {

@@ -1,0 +1,215 @@
+"""The front-end rules against THE REFERENCE'S OWN FRONT END (SURVEY §8a rows "graph construction", "initial guesses",
+"world / set bookkeeping", "variable store"; §8f-1 incremental triggers).
+
+oracle/_ref/libref_frontend.so is the reference's src/NodeDataManager.cpp, src/Worlds.cpp, src/PoseGraphSLAM.cpp,
+src/utils/PoseManipUtils.cpp and src/utils/RawFileIO.cpp compiled UNMODIFIED, from where they lie, over oracle/shim/
+(stand-ins for the Eigen / Ceres / roscpp / message / OpenCV names they use; wrapper oracle/ref_frontend_capi.cpp).  The
+ROS callbacks receive messages built from the same arrays the product's facade ingests; the reference's solver thread
+runs PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF() itself, single-stepped through a gate in the
+ros::Rate stand-in; the stand-in ceres::Problem records what the reference builds and ceres::Solve snapshots it without
+minimising.  The product's facade (dry run: same rule, no device) and the oracle's Python front-end must have built, after
+every wake-up: the same residual blocks between the same keyframes with the same observations and weights, the same
+regularisers, the same initial guess for every keyframe, the same solvedUntil and the same world / set state.
+Built only where the reference tree exists; the tests skip without the library."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frontend, pgo
+from solve_keyframe_pose_graph_b200 import facade, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_frontend.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libref_frontend.so not built (needs /root/reference; make -C oracle)")
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+class ReferenceNode:
+    """The reference's NodeDataManager + PoseGraphSLAM behind oracle/ref_frontend_capi.cpp."""
+
+    def __init__(self):
+        # NodeDataManager::camera_pose_callback keeps a function-local `static bool` for "first keyframe ever"
+        # (src/NodeDataManager.cpp:25): one manager per loaded image.  Every instance here loads its own copy of the library.
+        import shutil
+        import tempfile
+        self._dir = tempfile.mkdtemp(prefix="refslam_")
+        private_copy = os.path.join(self._dir, "libref_frontend.so")
+        shutil.copy(REF_SO, private_copy)
+        L = self.L = C.CDLL(private_copy)
+        L.refslam_create.restype = C.c_void_p
+        for f, extra in dict(refslam_destroy=[], refslam_wakeup=[], refslam_n_blocks=[], refslam_unknown_blocks=[], refslam_n_vars=[], refslam_n_switches=[],
+                             refslam_solved_until=[], refslam_status=[], refslam_n_nodes=[], refslam_n_edges=[], refslam_n_worlds=[],
+                             refslam_world_setid=[C.c_int], refslam_world_start=[C.c_int], refslam_world_end=[C.c_int], refslam_which_world=[C.c_longlong],
+                             refslam_add_node=[C.c_longlong, dp, dp], refslam_add_loop_edge=[C.c_longlong, C.c_longlong, dp, dp, C.c_float],
+                             refslam_kidnap=[C.c_longlong, C.c_int], refslam_get_blocks=[ip, ip, ip, ip, dp, dp], refslam_get_vars=[dp, dp, dp, ip],
+                             refslam_pose_between_worlds=[C.c_int, C.c_int, dp], refslam_get_node_pose=[C.c_int, dp]).items():
+            getattr(L, f).argtypes = [C.c_void_p] + extra
+        self.h = L.refslam_create()
+        assert self.h, "one reference instance at a time"
+
+    def close(self):
+        if self.h:
+            self.L.refslam_destroy(self.h); self.h = None
+            import shutil
+            shutil.rmtree(self._dir, ignore_errors=True)
+
+    def add_nodes(self, stamps, q, t):
+        for s, qq, tt in zip(stamps, np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(t, dtype=np.float64)):
+            self.L.refslam_add_node(self.h, int(s), qq.ctypes.data_as(dp), tt.ctypes.data_as(dp))
+
+    def add_loop_edges(self, stamps, a, b, q, t, w):
+        for aa, bb, qq, tt, ww in zip(a, b, np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(t, dtype=np.float64), w):
+            self.L.refslam_add_loop_edge(self.h, int(stamps[aa]), int(stamps[bb]), qq.ctypes.data_as(dp), tt.ctypes.data_as(dp), float(ww))
+
+    def kidnap(self, stamp, kidnapped):
+        self.L.refslam_kidnap(self.h, int(stamp), int(kidnapped))
+
+    def wakeup(self):
+        return self.L.refslam_wakeup(self.h) == 1
+
+    def blocks(self):
+        n = self.L.refslam_n_blocks(self.h)
+        assert self.L.refslam_unknown_blocks(self.h) == 0
+        ty = np.zeros(n, np.int32); c1 = np.zeros(n, np.int32); c2 = np.zeros(n, np.int32); sw = np.zeros(n, np.int32); obs = np.zeros((n, 4, 4)); w = np.zeros(n)
+        self.L.refslam_get_blocks(self.h, ty.ctypes.data_as(ip), c1.ctypes.data_as(ip), c2.ctypes.data_as(ip), sw.ctypes.data_as(ip), obs.ctypes.data_as(dp), w.ctypes.data_as(dp))
+        return dict(type=ty, c1=c1, c2=c2, sw=sw, obs=obs, w=w)
+
+    def variables(self):
+        n, m = self.L.refslam_n_vars(self.h), self.L.refslam_n_switches(self.h)
+        q = np.zeros((n, 4)); t = np.zeros((n, 3)); s = np.zeros(max(m, 1)); c = np.zeros(n, np.int32)
+        self.L.refslam_get_vars(self.h, q.ctypes.data_as(dp), t.ctypes.data_as(dp), s.ctypes.data_as(dp), c.ctypes.data_as(ip))
+        return q, t, s[:m], c
+
+    def pose_between_worlds(self, m, n):
+        T = np.zeros((4, 4))
+        return T if self.L.refslam_pose_between_worlds(self.h, m, n, T.ctypes.data_as(dp)) else None
+
+
+def mats(q, t):
+    return np.array([pgo.pose_to_mat4(qq, tt) for qq, tt in zip(q, t)]).reshape(-1, 4, 4)
+
+
+def same_quats(a, b):
+    return len(a) == len(b) and (len(a) == 0 or np.all(np.abs(np.sum(a * b, axis=1)) > 1 - 1e-12))
+
+
+def compare(R, F, P, fanout):
+    """R: the reference (real code), F: the product's facade (dry run), P: the oracle's Python front-end — after a wake-up that triggered."""
+    B = R.blocks()
+    od, lo, rg = B["type"] == 0, B["type"] == 1, B["type"] == 2
+    # ---- odometry blocks: SixDOFError::Create(u_M_umf, odom_edge_weight) on (u, u-f)   [PoseGraphSLAM.cpp:1570-1639]
+    o = F.alternative_terms(0)                                        # the facade's odometry blocks with their observations
+    assert np.array_equal(B["c1"][od], o["c1"]) and np.array_equal(B["c2"][od], o["c2"])
+    assert np.allclose(B["w"][od], o["weight"], rtol=1e-9, atol=0)
+    assert np.allclose(B["obs"][od], mats(o["obs_rot"], o["obs_t"]), rtol=0, atol=1e-9)
+    assert [(x[0], x[1]) for x in P.odom] == list(zip(B["c1"][od].tolist(), B["c2"][od].tolist()))
+    assert np.allclose([x[4] for x in P.odom], B["w"][od], rtol=1e-9, atol=0)
+    # ---- loop blocks: SixDOFErrorWithSwitchingConstraints::Create(bTa, weight) on (second, first, switch e)   [:1381-1559]
+    l = F.alternative_terms(1)
+    assert np.array_equal(B["c1"][lo], l["c1"]) and np.array_equal(B["c2"][lo], l["c2"])
+    assert np.allclose(B["obs"][lo], mats(l["obs_rot"], l["obs_t"]), rtol=0, atol=1e-9) and np.allclose(B["w"][lo], l["weight"], rtol=1e-6)
+    assert [(x[2], x[1], x[0]) for x in P.loops] == list(zip(B["c1"][lo].tolist(), B["c2"][lo].tolist(), B["sw"][lo].tolist()))
+    # ---- regularisers: one per set-root world, anchored at the CURRENT estimate of its first keyframe   [:1801-1850]
+    r = F.reg_terms()
+    assert np.array_equal(B["c1"][rg], r["node"]) and np.allclose(B["w"][rg], r["w"], rtol=1e-12)
+    assert np.allclose(B["obs"][rg], mats(r["q"], r["t"]), rtol=0, atol=1e-9)
+    assert [x[0] for x in P.regs] == B["c1"][rg].tolist() and np.allclose([x[3] for x in P.regs], B["w"][rg], rtol=1e-12)
+    # ---- optimisation variables = the initial guesses of this wake-up   [:226-361, 1649-1793]
+    q, t, s, const = R.variables()
+    fq, ft = F.poses()
+    assert len(t) == len(ft) and np.allclose(t, ft, rtol=0, atol=1e-8) and same_quats(q, fq)
+    assert np.allclose(t, np.array(P.opt_t).reshape(-1, 3), rtol=0, atol=1e-8) and same_quats(q, np.array(P.opt_q).reshape(-1, 4))
+    assert np.all(s == 0.99) and not const.any()                      # switches start at 0.99 (:353); nothing is marked constant in the live path
+    # ---- bookkeeping after the wake-up
+    assert R.L.refslam_solved_until(R.h) == F.solved_until() == P.solved_until
+    assert R.L.refslam_n_worlds(R.h) == F.n_worlds()
+    for w in range(F.n_worlds()):
+        assert R.L.refslam_world_setid(R.h, w) == F.world_setid(w) == P.m.worlds.find_setID_of_world_i(w)
+        assert R.L.refslam_world_start(R.h, w) == F.world_start(w) and R.L.refslam_world_end(R.h, w) == F.world_end(w)
+    return B
+
+
+def test_single_world_session_in_three_wakeups_matches_the_reference_front_end():
+    g = synth.generate_config(2, n_nodes=240, n_loop=36)
+    order = np.argsort(np.maximum(g["la"], g["lb"]), kind="stable")
+    R = ReferenceNode(); F = facade.Facade(odom_fanout=5, dry_run=True); M = frontend.Manager(); P = frontend.ReferenceFrontEnd(M, odom_fanout=5)
+    try:
+        epos = 0; triggered = 0
+        for lo in range(0, 240, 80):
+            sl = slice(lo, lo + 80)
+            R.add_nodes(g["stamps"][sl], g["q"][sl], g["t"][sl]); F.add_nodes(g["stamps"][sl], g["q"][sl], g["t"][sl])
+            for i in range(lo, lo + 80):
+                M.add_node(int(g["stamps"][i]), g["q"][i], g["t"][i])
+            take = []
+            while epos < len(order) and max(g["la"][order[epos]], g["lb"][order[epos]]) < lo + 80:
+                take.append(order[epos]); epos += 1
+            take = np.array(take, dtype=int)
+            if len(take):
+                R.add_loop_edges(g["stamps"], g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
+                F.add_loop_edges(g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
+                for e in take:
+                    M.add_loop_edge(int(g["la"][e]), int(g["lb"][e]), g["lq"][e], g["lt"][e], float(g["lw"][e]))
+            fired = R.wakeup()
+            assert fired == F.solve_once() == (len(take) > 0)
+            if fired:
+                P.trigger(solve=False); triggered += 1
+                B = compare(R, F, P, 5)
+                assert (B["type"] == 0).sum() == sum(min(5, u) for u in range(lo + 80)) and (B["type"] == 1).sum() == epos and (B["type"] == 2).sum() == 1
+            assert not R.wakeup() and not F.solve_once()                      # nothing new: the loop goes back to sleep (:1306-1312)
+        assert triggered >= 2 and epos == len(order)
+    finally:
+        R.close(); F.close()
+
+
+def test_two_world_session_with_a_kidnap_matches_the_reference_front_end():
+    """World 0, a kidnap, world 1, then loop edges from world 1 back into world 0: the first of them fixes the relative
+    pose of the worlds from odometry (:1459-1464), the sets merge, and every keyframe of world 1 is initialised in the
+    frame of the set root."""
+    rng = np.random.default_rng(9)
+    g = synth.generate_config(4, n_nodes=60, n_interworld=10)
+    stamps, k0, k1 = g["stamps"], g["k0"], g["k1"]
+    w0 = np.nonzero(stamps <= k0[0])[0]; w1 = np.nonzero((stamps > k1[0]) & (stamps <= k0[1]))[0]
+    dead = np.nonzero((stamps > k0[0]) & (stamps <= k1[0]))[0]
+    keep = np.r_[w0, dead, w1]
+    assert np.array_equal(keep, np.arange(len(keep)))
+    n = len(keep)
+    R = ReferenceNode(); F = facade.Facade(odom_fanout=5, dry_run=True); M = frontend.Manager(); P = frontend.ReferenceFrontEnd(M, odom_fanout=5)   # the reference hard-codes f = 1..5 (:1577)
+
+    def nodes(idx):
+        R.add_nodes(stamps[idx], g["q"][idx], g["t"][idx]); F.add_nodes(stamps[idx], g["q"][idx], g["t"][idx])
+        for i in idx:
+            M.add_node(int(stamps[i]), g["q"][i], g["t"][i])
+
+    def loops(pairs):
+        for a, b in pairs:                                                    # observation: noisy relative pose of the odometry frames, any value will do
+            T = pgo.inv4(pgo.pose_to_mat4(g["q"][b], g["t"][b])) @ pgo.pose_to_mat4(g["q"][a], g["t"][a])
+            q, t = pgo.mat4_to_pose(T); t = t + rng.normal(size=3) * 0.05
+            R.add_loop_edges(stamps, [a], [b], [q], [t], [1.0]); F.add_loop_edges([a], [b], [q], [t], [1.0]); M.add_loop_edge(a, b, q, t, 1.0)
+
+    try:
+        # wake-up 1: world 0 with two loop edges inside it
+        nodes(w0); loops([(int(w0[-5]), int(w0[3])), (int(w0[-12]), int(w0[8]))])
+        assert R.wakeup() and F.solve_once(); P.trigger(solve=False)
+        compare(R, F, P, 5)
+        # kidnapped: keyframes of the dead zone arrive, a loop edge touching them is ignored, and nothing may trigger
+        for X in (R, F, M):
+            (X.kidnap if X is R else X.kidnap_indicator)(int(k0[0]), 1)
+        nodes(dead)
+        assert not R.wakeup() and not F.solve_once()
+        for X in (R, F, M):
+            (X.kidnap if X is R else X.kidnap_indicator)(int(k1[0]), 0)
+        # wake-up 2: world 1 and three loop edges back into world 0
+        nodes(w1); loops([(int(w1[10]), int(w0[20])), (int(w1[30]), int(w0[40])), (int(w1[-1]), int(w1[5]))])
+        assert [R.L.refslam_which_world(R.h, int(s)) for s in stamps[:n]] == [F.which_world(int(s)) for s in stamps[:n]] == [M.which_world_is_this(int(s)) for s in stamps[:n]]
+        assert R.wakeup() and F.solve_once(); P.trigger(solve=False)
+        B = compare(R, F, P, 5)
+        assert F.n_worlds() == 2 and F.world_setid(1) == F.world_setid(0) == 0
+        T = R.pose_between_worlds(0, 1)
+        assert T is not None and np.allclose(T, F.pose_between_worlds(0, 1), rtol=0, atol=1e-9) and np.allclose(T, M.worlds.getPoseBetweenWorlds(0, 1), rtol=0, atol=1e-9)
+        assert (B["type"] == 2).sum() == 1 and B["c1"][B["type"] == 2][0] == 0                # one set, one regulariser, on keyframe 0
+        no_dead = ~np.isin(B["c1"], dead) & ~np.isin(B["c2"], dead)
+        assert no_dead[B["type"] != 2].all()                                                  # no block touches a dead-zone keyframe
+    finally:
+        R.close(); F.close()
