@@ -15,6 +15,7 @@
 #include <array>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <functional>
@@ -58,6 +59,7 @@ struct Ref {
   bool started = false;
   std::vector<Snapshot> snaps;
   long arrivals_seen = 0;
+  double perturb = 0.0;          // > 0: the stand-in "solve" moves every variable of the problem by a known, index-dependent amount
 };
 Ref* g_ref = nullptr;
 
@@ -100,6 +102,27 @@ void on_solve(const ceres::Solver::Options&, ceres::Problem* P, ceres::Solver::S
   for (int e = 0; e < ns; ++e) S.s[e] = *R->slam->get_raw_ptr_to_opt_switch(e);
   sum->termination_type = ceres::NO_CONVERGENCE;
   R->snaps.push_back(S);
+  if (R->perturb > 0) {
+    // A stand-in for what a solve does to the state the NEXT wake-up starts from: every pose that appears in a residual
+    // block moves by Plus(q, a*eps_i), t += a*d_i, every switch of a block changes, all as closed forms of the index and
+    // the wake-up number so that tests/test_reference_frontend.py can apply the same to the other front ends.
+    const double a = R->perturb; const int k = (int)R->snaps.size();
+    std::vector<char> used(n, 0), sused(ns, 0);
+    for (const Block& B : S.blocks) { used[B.c1] = 1; if (B.c2 >= 0) used[B.c2] = 1; if (B.sw >= 0) sused[B.sw] = 1; }
+    for (int i = 0; i < n; ++i) {
+      if (!used[i]) continue;
+      double* q = R->slam->get_raw_ptr_to_opt_variable_q(i); double* t = R->slam->get_raw_ptr_to_opt_variable_t(i);
+      const double e[3] = {a * 0.1 * std::sin(i + k), a * 0.1 * std::cos(2 * i + k), a * 0.1 * std::sin(3 * i + 2 * k)};
+      const double nrm = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+      if (nrm > 0) {                                           // ceres::EigenQuaternionParameterization::Plus: [sin|e| e/|e| ; cos|e|] (x) q
+        const double sn = std::sin(nrm) / nrm, dx = sn * e[0], dy = sn * e[1], dz = sn * e[2], dw = std::cos(nrm);
+        const double x = q[0], y = q[1], z = q[2], w = q[3];
+        q[3] = dw * w - dx * x - dy * y - dz * z; q[0] = dw * x + dx * w + dy * z - dz * y; q[1] = dw * y + dy * w + dz * x - dx * z; q[2] = dw * z + dz * w + dx * y - dy * x;
+      }
+      t[0] += a * std::cos(i + k); t[1] += a * std::sin(2 * i + k); t[2] += a * std::cos(3 * i + k);
+    }
+    for (int e = 0; e < ns; ++e) if (sused[e]) *R->slam->get_raw_ptr_to_opt_switch(e) = 0.99 - 0.01 * ((7 * e + k) % 50);
+  }
 }
 
 void wait_arrival(Ref* R) {                      // until the solver thread is parked in loop_rate.sleep() again
@@ -161,6 +184,7 @@ void refslam_kidnap(void* h, long long stamp_ns, int kidnapped) {
   m->stamp = ros::Time::fromNSec(stamp_ns); m->frame_id = kidnapped ? "kidnapped" : "unkidnapped";
   R->manager->rcvd_kidnap_indicator_callback(std_msgs::HeaderConstPtr(m));
 }
+void refslam_set_perturb(void* h, double amplitude) { ((Ref*)h)->perturb = amplitude; }
 // One wake-up of PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF().  Returns 1 if it reached ceres::Solve.
 int refslam_wakeup(void* h) {
   Ref* R = (Ref*)h;
