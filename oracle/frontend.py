@@ -1,4 +1,6 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned to the reference's own front-end code by tests/test_reference_frontend.py
+(oracle/_ref/libref_frontend.so: the reference's NodeDataManager.cpp / Worlds.cpp / PoseGraphSLAM.cpp compiled unmodified
+over oracle/shim/ and single-stepped) and tests/test_reference_sets.py; the solve it calls (pgo) is Ceres restated.
 
 Python restatement of the reference's host-side graph-construction rules, i.e. everything
 `PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF` does before and after
