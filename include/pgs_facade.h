@@ -93,6 +93,11 @@ int pgs_io_string_to_mat(const char* s, double* T16);
  * EMPTY facade (before any keyframe): relative poses, world stamps, union-find op-log replayed. */
 int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* solved_posegraph_json);
 /* loads a solved_posegraph.json: n = number of keyframes (call with NULL outputs to size), poses [n][16], stamps, ids */
+/* Composer::loadStateFromDisk (src/Composer.cpp:1109-1177), what the reference node does for its `loadStateFromDisk` parameter:
+ * from <dir>/solved_posegraph.json restore the Worlds object ("WorldsData"), the kidnap stamps ("KidnapTimestamps"), every keyframe of
+ * "SolvedPoseGraph" (moved from its set root's frame back into its own world's frame) and then PoseGraphSLAM::load_state (the
+ * restored keyframes become constant optimisation variables, solvedUntil moves to the last one).  Into an empty handle. */
+int pgs_facade_load_state_from_disk(pgs_facade_handle h, const char* dir);
 int pgs_io_load_solved_posegraph(const char* json_file, double* T, int64_t* stamp_ns, int32_t* world_id, int32_t* set_id, int32_t cap);
 
 /* introspection of the graph-construction rules (parity tests against the oracle front-end).  The lists behind these

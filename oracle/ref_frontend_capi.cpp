@@ -173,7 +173,7 @@ int refslam_add_loop_edge(void* h, long long stamp0_ns, long long stamp1_ns, con
   m->timestamp0 = ros::Time::fromNSec(stamp0_ns); m->timestamp1 = ros::Time::fromNSec(stamp1_ns);
   m->pose_1T0.position.x = t[0]; m->pose_1T0.position.y = t[1]; m->pose_1T0.position.z = t[2];
   m->pose_1T0.orientation.x = q_xyzw[0]; m->pose_1T0.orientation.y = q_xyzw[1]; m->pose_1T0.orientation.z = q_xyzw[2]; m->pose_1T0.orientation.w = q_xyzw[3];
-  m->weight = weight; m->description = "test";
+  m->weight = weight; m->description = "";
   R->manager->loopclosure_pose_callback(solve_keyframe_pose_graph::LoopEdge::ConstPtr(m));
   return R->manager->getEdgeLen();
 }
@@ -230,6 +230,46 @@ int refslam_pose_between_worlds(void* h, int m, int n, double* T16) {      // di
   copy16(W->getPoseBetweenWorlds(m, n), T16);
   return 1;
 }
+// ---- the reference's own writers and reader of its state files
+// NodeDataManager::saveAsJSON (src/NodeDataManager.cpp:503-628) -> dir/log_posegraph.json, PoseGraphSLAM::saveAsJSON
+// (src/PoseGraphSLAM.cpp:1111-1207) -> dir/log_optimized_poses.json, Worlds::saveStateToDisk (src/Worlds.cpp:442-497) -> dir/worlds.json
+int refslam_save_json(void* h, const char* dir) {
+  Ref* R = (Ref*)h;
+  const bool a = R->manager->saveAsJSON(std::string(dir));
+  const bool b = R->slam->saveAsJSON(std::string(dir));
+  std::ofstream f(std::string(dir) + "/worlds.json");
+  f << R->manager->getWorldsPtr()->saveStateToDisk().dump(4);
+  return (a ? 1 : 0) | (b ? 2 : 0) | (f.good() ? 4 : 0);
+}
+// NodeDataManager::loadFromJSON (src/NodeDataManager.cpp:630-754) into this instance's manager (all edges)
+int refslam_load_posegraph_json(void* h, const char* dir) { return ((Ref*)h)->manager->loadFromJSON(std::string(dir), std::vector<bool>()) ? 1 : 0; }
+// Worlds::loadStateFromDisk (src/Worlds.cpp:499-640) from a file holding the "WorldsData" object
+int refslam_load_worlds_json(void* h, const char* file) {
+  std::ifstream f(file); if (!f.is_open()) return 0;
+  json obj; f >> obj;
+  return ((Ref*)h)->manager->getWorldsPtr()->loadStateFromDisk(obj) ? 1 : 0;
+}
+// The four calls of Composer::loadStateFromDisk (src/Composer.cpp:1137-1167; Composer.cpp itself is ROS visualisation and is not
+// compiled here), each of them the reference's own function: 0 on success, else the number of the step that failed.
+int refslam_load_state_from_disk(void* h, const char* dir) {
+  Ref* R = (Ref*)h;
+  std::ifstream f(std::string(dir) + "/solved_posegraph.json"); if (!f.is_open()) return -1;
+  json obj; f >> obj;
+  if (!R->manager->getWorldsPtr()->loadStateFromDisk(obj["WorldsData"])) return 1;
+  if (!R->manager->load_kidnap_data_from_json(obj["KidnapTimestamps"])) return 2;
+  if (!R->manager->load_solved_posegraph_data_from_json(obj)) return 3;
+  if (!R->slam->load_state()) return 4;
+  return 0;
+}
+int refslam_slam_n_nodes(void* h) { return ((Ref*)h)->slam->nNodes(); }
+int refslam_kidnap_status(void* h) { return ((Ref*)h)->manager->curr_kidnap_status() ? 1 : 0; }
+long long refslam_node_stamp(void* h, int i) { return (long long)((Ref*)h)->manager->getNodeTimestamp(i).toNSec(); }
+void refslam_manager_node_pose(void* h, int i, double* T16) { copy16(((Ref*)h)->manager->getNodePose(i), T16); }
+void refslam_edge(void* h, int e, int* a, int* b, double* T16, double* w) {
+  NodeDataManager* m = ((Ref*)h)->manager;
+  const std::pair<int, int> p = m->getEdgeIdxInfo(e); *a = p.first; *b = p.second; copy16(m->getEdgePose(e), T16); *w = m->getEdgeWeight(e);
+}
+int refslam_n_kidnaps(void* h) { return ((Ref*)h)->manager->n_kidnaps(); }
 void refslam_get_node_pose(void* h, int i, double* T16) { copy16(((Ref*)h)->slam->getNodePose(i), T16); }
 
 }  // extern "C"

@@ -94,7 +94,7 @@ bool saveAsJSON(const NodeDataManager& m, const std::string& base_path, std::str
     all["world_info"].push_back(w);
   }
   all["meta_data"]["n_worlds"] = Json(m.n_kidnaps());   // sic: the reference overwrites n_worlds with n_kidnaps (:599)
-  all["kidnap_info"] = Json::array();
+  all["kidnap_info"] = m.n_kidnaps() ? Json::array() : Json();   // never pushed to -> null in the reference's file
   for (int i = 0; i < m.n_kidnaps(); ++i) {
     Json k; k["idx"] = Json(i);
     k["stamp_of_kidnap_i_started"] = Json(to_sec(m.stamp_of_kidnap_i_started(i)));
@@ -103,7 +103,7 @@ bool saveAsJSON(const NodeDataManager& m, const std::string& base_path, std::str
     k["stampNSec_started"] = Json(m.stamp_of_kidnap_i_started(i)); k["stampNSec_ended"] = Json(m.stamp_of_kidnap_i_ended(i));
     all["kidnap_info"].push_back(k);
   }
-  all["disjoint_set_status"] = Json(m.getWorldsConstPtr()->disjoint_set_log());
+  all["disjoint_set_status"] = Json(m.getWorldsConstPtr()->disjoint_set_status());   // NodeDataManager.cpp:611
   return write_file(base_path + "/log_posegraph.json", all.dump(4), err);
 }
 

@@ -63,6 +63,33 @@ bool NodeDataManager::getNodePose(int i, Matrix4d& w_T_cam) const {
   w_T_cam = node_pose[i]; return true;
 }
 const Matrix4d& NodeDataManager::getNodePose(int i) const { std::lock_guard<std::mutex> lk(node_mutex); return node_pose[i]; }
+bool NodeDataManager::load_kidnap_data(const std::vector<int64_t>& starts_ns, const std::vector<int64_t>& ends_ns) {
+  if (!(starts_ns.size() == ends_ns.size() || starts_ns.size() == ends_ns.size() + 1)) return false;      // the reference exit(1)s (:944-948)
+  std::lock_guard<std::mutex> lk(mutex_kidnap);
+  kidnap_starts = starts_ns; kidnap_ends = ends_ns;
+  current_kidnap_status = starts_ns.size() != ends_ns.size();
+  return true;
+}
+
+bool NodeDataManager::load_solved_node(int64_t stamp_ns, const Matrix4d& ws_T_c, int world_id, int set_id, std::string* err) {
+  auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
+  Matrix4d w_T_c = ws_T_c;
+  if (world_id >= 0 && world_id != set_id) {                                                            // :1038-1050
+    bool ok = false;
+    const Matrix4d w_T_ws = worlds_handle_raw_ptr->is_exist(world_id, set_id) ? worlds_handle_raw_ptr->getPoseBetweenWorlds(world_id, set_id, &ok) : Matrix4d::Identity();
+    if (!ok) return fail("no relative pose between world " + std::to_string(world_id) + " and its saved set root " + std::to_string(set_id));
+    w_T_c = w_T_ws * ws_T_c;
+  }
+  if (world_id >= 0 && set_id >= 0) {                                                                   // :1061-1071
+    const int w = which_world_is_this(stamp_ns);
+    if (w != world_id) return fail("a saved keyframe falls into world " + std::to_string(w) + ", the file says " + std::to_string(world_id));
+    if (worlds_handle_raw_ptr->find_setID_of_world_i(w) != set_id) return fail("a saved keyframe's world is in another set than the file says");
+  }
+  std::lock_guard<std::mutex> lk(node_mutex);
+  node_timestamps.push_back(stamp_ns); node_pose.push_back(w_T_c); node_pose_covariance.push_back(std::array<double, 36>{});   // :1078-1081, no world_starts()
+  return true;
+}
+
 bool NodeDataManager::getNodeCov(int i, double* cov36) const {
   std::lock_guard<std::mutex> lk(node_mutex);
   if (i < 0 || i >= (int)node_pose_covariance.size() || !cov36) return false;

@@ -51,6 +51,15 @@ class NodeDataManager {
   double getEdgeWeight(int i) const;
   const std::string getEdgeDescriptionString(int i) const;
 
+  // ---- restoring a saved session (the two manager steps of Composer::loadStateFromDisk, reference src/Composer.cpp:1148-1163;
+  // the Worlds object must have been restored first).  load_kidnap_data: NodeDataManager::load_kidnap_data_from_json
+  // (NodeDataManager.cpp:912-950) — the stamp lists replace the current ones, the kidnap status follows from their lengths;
+  // false when they cannot belong together (the reference exits).  load_solved_node: one entry of "SolvedPoseGraph" as
+  // NodeDataManager::load_solved_posegraph_data_from_json treats it (:998-1090): the saved pose is in the frame of its world's
+  // set root and is moved back into the world's own frame, the stamp must fall into the saved world and set; no world is started.
+  bool load_kidnap_data(const std::vector<int64_t>& starts_ns, const std::vector<int64_t>& ends_ns);
+  bool load_solved_node(int64_t stamp_ns, const Matrix4d& ws_T_c, int world_id, int set_id_of_world, std::string* err = nullptr);
+
   // ---- kidnap / world queries
   bool curr_kidnap_status() const { return current_kidnap_status; }
   int n_kidnaps() const;

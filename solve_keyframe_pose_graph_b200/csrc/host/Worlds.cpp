@@ -66,6 +66,7 @@ bool Worlds::setPoseBetweenWorlds(int m, int n, const Matrix4d& m_T_n, const std
   // larger id first: on rank ties the smaller id stays the root (Worlds.cpp:168)
   disjoint_set.union_sets(std::max(m, n), std::min(m, n));
   log_ += "union_sets:" + std::to_string(std::max(m, n)) + "," + std::to_string(std::min(m, n)) + ";";
+  debug_ += "\t\t\tunion_sets( " + std::to_string(std::max(m, n)) + "," + std::to_string(std::min(m, n)) + ")\n";   // Worlds.cpp:169
   return true;
 }
 
@@ -96,6 +97,7 @@ void Worlds::world_starts(int64_t stamp_ns) {
   const int id = (int)vec_world_starts.size() - 1;
   disjoint_set.add_element(id);
   log_ += "add_element:" + std::to_string(id) + ";";
+  debug_ += "\t\t\tadd_element( " + std::to_string(id) + ")\n";                                                     // Worlds.cpp:238
 }
 
 void Worlds::world_ends(int64_t stamp_ns) {
@@ -111,6 +113,20 @@ int Worlds::find_setID_of_world_i(int i) const {
 int Worlds::n_worlds() const { std::lock_guard<std::mutex> lk(mutex_world); return disjoint_set.element_count(); }
 int Worlds::n_sets() const { std::lock_guard<std::mutex> lk(mutex_world); return disjoint_set.set_count(); }
 std::string Worlds::disjoint_set_log() const { std::lock_guard<std::mutex> lk(mutex_world); return log_; }
+// Worlds::disjoint_set_status (Worlds.cpp:333-363): what log_posegraph.json stores under "disjoint_set_status"
+std::string Worlds::disjoint_set_status() const {
+  std::lock_guard<std::mutex> lk(mutex_world);
+  std::map<int, std::string> ff;
+  std::string out = "element_count=" + std::to_string(disjoint_set.element_count()) + "   set_count=" + std::to_string(disjoint_set.set_count()) + ";";
+  for (int i = 0; i < disjoint_set.element_count(); ++i) {
+    const int setID = disjoint_set.find_set(i);
+    out += "world#" + std::to_string(i) + " is in setID=" + std::to_string(setID) + ";";
+    if (ff.count(setID)) ff[setID] += "," + std::to_string(i); else ff[setID] = std::to_string(i);
+  }
+  out += ";";
+  for (const auto& kv : ff) out += "set#" + std::to_string(kv.first) + " contains worlds: " + kv.second + ";";
+  return out;
+}
 
 // ---------------------------------------------------------------- state file (Worlds.cpp:442-640)
 static std::string mat_rows_string(const Matrix4d& M) {   // RawFileIO::eigen_matrix_to_json: ", " between coefficients, "\n" between rows
@@ -130,7 +146,8 @@ static bool parse_mat_rows(const std::string& s, Matrix4d& M) {
 Json Worlds::saveStateToDisk() const {
   std::lock_guard<std::mutex> lk(mutex_world);
   Json obb;
-  obb["rel_pose_between_worlds__wb_T_wa"] = Json::array();
+  // nlohmann leaves a key that was only ever indexed, never pushed to, as null: empty lists are written as null (Worlds.cpp:451-497)
+  obb["rel_pose_between_worlds__wb_T_wa"] = rel_pose.empty() ? Json() : Json::array();
   for (const auto& kv : rel_pose) {
     Json item;
     item["node_b"] = Json(kv.first.first); item["node_a"] = Json(kv.first.second);
@@ -146,8 +163,8 @@ Json Worlds::saveStateToDisk() const {
   Json A = Json::array(), B = Json::array();
   for (int64_t t : vec_world_starts) { Json a; a["stampNSec"] = Json(t); A.push_back(a); }
   for (int64_t t : vec_world_ends) { Json b; b["stampNSec"] = Json(t); B.push_back(b); }
-  obb["vec_world_starts"] = A; obb["vec_world_ends"] = B;
-  obb["disjoint_set"]["debug_string"] = Json(std::string());
+  obb["vec_world_starts"] = vec_world_starts.empty() ? Json() : A; obb["vec_world_ends"] = vec_world_ends.empty() ? Json() : B;
+  obb["disjoint_set"]["debug_string"] = Json(debug_);
   obb["disjoint_set"]["log_string"] = Json(log_);
   return obb;
 }
@@ -184,6 +201,7 @@ bool Worlds::loadStateFromDisk(const Json& o, std::string* err) {
     } catch (...) { return fail("Worlds::loadStateFromDisk: bad number in op-log"); }
   }
   log_ = log;
+  if (o.at("disjoint_set").contains("debug_string")) debug_ = o.at("disjoint_set").at("debug_string").as_string();   // Worlds.cpp:557
   const Json& ws = o.at("vec_world_starts"); const Json& we = o.at("vec_world_ends");
   for (size_t i = 0; i < ws.size(); ++i) vec_world_starts.push_back(ws[i].at("stampNSec").as_int());
   for (size_t i = 0; i < we.size(); ++i) vec_world_ends.push_back(we[i].at("stampNSec").as_int());

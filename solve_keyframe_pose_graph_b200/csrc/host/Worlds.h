@@ -30,6 +30,7 @@ class Worlds {
   int find_setID_of_world_i(int i) const;
   int n_worlds() const;
   int n_sets() const;
+  std::string disjoint_set_status() const;   // "element_count=2   set_count=1;world#0 is in setID=0;..." (Worlds.cpp:333-363)
   std::string disjoint_set_log() const;   // "add_element:0;union_sets:1,0;" op-log (Worlds.cpp:164-170,230-240)
   // The "WorldsData" object of solved_posegraph.json (Worlds.cpp:442-497): relative poses with their info strings,
   // world start / end stamps and the union-find op-log, which loadStateFromDisk replays (Worlds.cpp:499-640).
@@ -43,6 +44,7 @@ class Worlds {
   std::vector<int64_t> vec_world_starts, vec_world_ends;
   mutable DisjointSetForest disjoint_set;
   mutable std::string log_;
+  std::string debug_;                      // disjoint_set_debug of the reference (Worlds.cpp:169,238), saved as "debug_string"
 };
 
 }  // namespace pgs

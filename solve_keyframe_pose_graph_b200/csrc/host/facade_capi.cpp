@@ -213,6 +213,19 @@ int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* file) try {
   if (!pgs::Json::parse(text, &obj, &perr)) { h->err = perr; return PGS_ERR_STATE; }
   return h->manager.getWorldsPtr()->loadStateFromDisk(obj.at("WorldsData"), &h->err) ? PGS_OK : PGS_ERR_STATE;
 } CATCH_FACADE(h)
+int pgs_facade_load_state_from_disk(pgs_facade_handle h, const char* dir) try {
+  if (!h || !dir) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  if (h->manager.getNodeLen() != 0) { h->err = "load_state_from_disk: the session must be empty"; return PGS_ERR_STATE; }
+  const std::string file = std::string(dir) + "/solved_posegraph.json";
+  if (int rc = pgs_facade_load_worlds_state(h, file.c_str())) return rc;                                   // Composer.cpp:1137
+  pgs::SolvedPoseGraph pg;
+  if (!pgs::loadSolvedPoseGraph(file, &pg, &h->err)) return PGS_ERR_STATE;
+  if (!h->manager.load_kidnap_data(pg.kidnap_starts, pg.kidnap_ends)) { h->err = "load_state_from_disk: kidnap_starts / kidnap_ends do not belong together"; return PGS_ERR_STATE; }   // :1148
+  for (size_t i = 0; i < pg.w_T_c.size(); ++i)                                                            // :1158
+    if (!h->manager.load_solved_node(pg.stamp_ns[i], pg.w_T_c[i], pg.world_id[i], pg.set_id[i], &h->err)) { h->err = "SolvedPoseGraph[" + std::to_string(i) + "]: " + h->err; return PGS_ERR_STATE; }
+  return h->slam->load_state() ? PGS_OK : PGS_ERR_STATE;                                                  // :1167
+} CATCH_FACADE(h)
 static int copy_out(const std::string& s, char* out, int32_t cap) {
   if (out && cap > 0) { const size_t n = std::min((size_t)cap - 1, s.size()); std::memcpy(out, s.data(), n); out[n] = 0; }
   return (int)s.size();

@@ -181,6 +181,10 @@ class Facade:
     def load_worlds_state(self, solved_posegraph_json):
         self._ck(self.L.pgs_facade_load_worlds_state(self.h, str(solved_posegraph_json).encode()))
 
+    def load_state_from_disk(self, directory):
+        """Composer::loadStateFromDisk of the reference: restore a session from <directory>/solved_posegraph.json."""
+        self._ck(self.L.pgs_facade_load_state_from_disk(self.h, str(directory).encode()))
+
     def load_posegraph_json(self, directory):
         self._ck(self.L.pgs_facade_load_posegraph_json(self.h, str(directory).encode()))
 

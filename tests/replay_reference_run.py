@@ -38,12 +38,12 @@ def parse_mat(s):
 
 def read_posegraph(directory):
     J = json.load(open(os.path.join(directory, "log_posegraph.json")))
-    nodes, edges = J["nodes"], J["loopedges"]
+    nodes, edges = J["nodes"] or [], J["loopedges"] or []
     T = np.array([parse_mat(n["wTc"]) for n in nodes]).reshape(-1, 4, 4)
     stamps = np.array([int(round(float(n["timestamp"]) * 1e9)) for n in nodes], np.int64)
     qt = [pgo.mat4_to_pose(M) for M in T]
     k0, k1 = [], []
-    for k in J.get("kidnap_info", []):
+    for k in (J.get("kidnap_info") or []):          # the reference writes null when there was no kidnap
         k0.append(int(k["stampNSec_started"]) if "stampNSec_started" in k else int(round(float(k["stamp_of_kidnap_i_started"]) * 1e9)))
         k1.append(int(k["stampNSec_ended"]) if "stampNSec_ended" in k else int(round(float(k["stamp_of_kidnap_i_ended"]) * 1e9)))
     bTa = [pgo.mat4_to_pose(parse_mat(e["b_T_a"])) for e in edges]
@@ -57,7 +57,7 @@ def read_posegraph(directory):
 def read_optimized(directory):
     J = json.load(open(os.path.join(directory, "log_optimized_poses.json")))
     T = np.array([parse_mat(n["wTc_opt"]) for n in J["PoseGraphSLAM_nodes"]]).reshape(-1, 4, 4)
-    sw = {int(e["getEdge_i"]): float(e["switching_var_after_opt"]) for e in J.get("PoseGraphSLAM_loopedgeinfo", []) if "switching_var_after_opt" in e}
+    sw = {int(e["getEdge_i"]): float(e["switching_var_after_opt"]) for e in (J.get("PoseGraphSLAM_loopedgeinfo") or []) if "switching_var_after_opt" in e}
     return T, sw
 
 

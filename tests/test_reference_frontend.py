@@ -289,3 +289,154 @@ def test_warm_start_rules_after_the_state_has_moved_match_the_reference_front_en
         loops([(int(w1[50]), int(w0[50])), (int(w1[55]), int(w1[12]))]); wake(5)   # 5: further edges on the merged set
     finally:
         R.close()
+
+
+def _two_world_session(R, F, rng):
+    """World 0, a kidnap with dead-zone keyframes, world 1, loop edges inside and across the worlds; one wake-up at the end."""
+    g = synth.generate_config(4, n_nodes=40, n_interworld=6)
+    stamps, k0, k1 = g["stamps"], g["k0"], g["k1"]
+    w0 = np.nonzero(stamps <= k0[0])[0]; dead = np.nonzero((stamps > k0[0]) & (stamps <= k1[0]))[0]; w1 = np.nonzero((stamps > k1[0]) & (stamps <= k0[1]))[0]
+    for X in (R, F):
+        X.add_nodes(stamps[w0], g["q"][w0], g["t"][w0])
+        (X.kidnap if X is R else X.kidnap_indicator)(int(k0[0]), 1)
+        X.add_nodes(stamps[dead], g["q"][dead], g["t"][dead])
+        (X.kidnap if X is R else X.kidnap_indicator)(int(k1[0]), 0)
+        X.add_nodes(stamps[w1], g["q"][w1], g["t"][w1])
+    for a, b in [(int(w0[30]), int(w0[2])), (int(w1[10]), int(w0[20])), (int(w1[35]), int(w1[4])), (int(w1[20]), int(w0[5]))]:
+        T = pgo.inv4(pgo.pose_to_mat4(g["q"][b], g["t"][b])) @ pgo.pose_to_mat4(g["q"][a], g["t"][a])
+        q, t = pgo.mat4_to_pose(T); t = t + rng.normal(size=3) * 0.05
+        R.add_loop_edges(stamps, [a], [b], [q], [t], [1.0]); F.add_loop_edges([a], [b], [q], [t], [1.0])
+    assert R.wakeup() and F.solve_once()
+    return g, len(w0) + len(dead) + len(w1)
+
+
+def test_state_files_equal_the_files_the_reference_code_writes_and_its_loader_reads_ours(tmp_path):
+    """NodeDataManager::saveAsJSON, PoseGraphSLAM::saveAsJSON and Worlds::saveStateToDisk of the reference (real code) against
+    the product's writers for the same two-world session: log_posegraph.json and log_optimized_poses.json byte for byte
+    (the product adds two exact-nanosecond fields per kidnap, which the reference's loader ignores), the WorldsData object
+    value for value.  Then NodeDataManager::loadFromJSON and Worlds::loadStateFromDisk of the reference read the PRODUCT's
+    files into a fresh reference instance, which must end up in the same state."""
+    import json
+    rng = np.random.default_rng(12)
+    R = ReferenceNode(); F = facade.Facade(odom_fanout=5, dry_run=True)
+    R.L.refslam_save_json.argtypes = [C.c_void_p, C.c_char_p]
+    dR, dF = tmp_path / "ref", tmp_path / "ours"; dR.mkdir(); dF.mkdir()
+    try:
+        g, n = _two_world_session(R, F, rng)
+        assert R.L.refslam_save_json(R.h, str(dR).encode()) == 7
+        F.save_json(dF)
+        import re
+        number = re.compile(r"-?\d+\.?\d*(?:[eE][+-]?\d+)?")
+        for name in ("log_posegraph.json", "log_optimized_poses.json"):
+            ref_lines = open(dR / name).read().split("\n")
+            our_lines = [l for l in open(dF / name).read().split("\n") if '"stampNSec_started"' not in l and '"stampNSec_ended"' not in l]
+            assert len(ref_lines) == len(our_lines) and ref_lines[-1] == our_lines[-1] == "", name          # both end with one newline
+            identical = 0
+            for i, (a, b) in enumerate(zip(ref_lines, our_lines)):
+                if a == b:
+                    identical += 1; continue
+                # a line may differ only in the last digits of matrix entries: the arithmetic under the reference's code here is
+                # the stand-in's, not Eigen's, so products are not bit-equal; layout, keys, order and every other character are
+                assert number.sub("#", a) == number.sub("#", b), (name, i, a, b)
+                va, vb = [float(x) for x in number.findall(a)], [float(x) for x in number.findall(b)]
+                assert np.allclose(va, vb, rtol=1e-12, atol=1e-9), (name, i, a, b)
+            assert identical >= 0.9 * len(ref_lines), (name, identical, len(ref_lines))
+        wr = json.load(open(dR / "worlds.json")); wo = json.load(open(dF / "solved_posegraph.json"))["WorldsData"]
+        for a, b in zip(json.dumps(wr, indent=1, sort_keys=True).split("\n"), json.dumps(wo, indent=1, sort_keys=True).split("\n")):
+            assert number.sub("#", a) == number.sub("#", b), (a, b)                 # the matrix string differs in last digits only (see above)
+            assert np.allclose([float(x) for x in number.findall(a)], [float(x) for x in number.findall(b)], rtol=1e-12, atol=1e-9), (a, b)
+        assert wr["disjoint_set"] == wo["disjoint_set"] and wr["vec_world_starts"] == wo["vec_world_starts"] and wr["vec_world_ends"] == wo["vec_world_ends"]
+        assert wr["disjoint_set"]["log_string"] == "add_element:0;add_element:1;union_sets:1,0;" and len(wr["rel_pose_between_worlds__wb_T_wa"]) == 1
+    finally:
+        R.close()
+    # ---- the reference's loaders on the product's files
+    R2 = ReferenceNode()
+    for f, a in dict(refslam_load_posegraph_json=[C.c_char_p], refslam_load_worlds_json=[C.c_char_p], refslam_node_stamp=[C.c_int], refslam_manager_node_pose=[C.c_int, dp],
+                     refslam_edge=[C.c_int, ip, ip, dp, dp], refslam_n_kidnaps=[]).items():
+        getattr(R2.L, f).argtypes = [C.c_void_p] + a
+    R2.L.refslam_node_stamp.restype = C.c_longlong
+    try:
+        json.dump(json.load(open(dF / "solved_posegraph.json"))["WorldsData"], open(tmp_path / "worldsdata.json", "w"))
+        assert R2.L.refslam_load_worlds_json(R2.h, str(tmp_path / "worldsdata.json").encode()) == 1
+        assert R2.L.refslam_load_posegraph_json(R2.h, str(dF).encode()) == 1      # keyframes and loop edges; kidnap stamps are not part of what this loader restores
+        assert R2.L.refslam_n_nodes(R2.h) == n == F.n_keyframes() and R2.L.refslam_n_edges(R2.h) == 4
+        T = np.zeros((4, 4)); a = C.c_int(); b = C.c_int(); w = C.c_double()
+        for i in range(n):
+            assert abs(R2.L.refslam_node_stamp(R2.h, i) - int(g["stamps"][i])) < 1000    # stamps travel as seconds in a double
+            R2.L.refslam_manager_node_pose(R2.h, i, T.ctypes.data_as(dp))
+            assert np.allclose(T, pgo.pose_to_mat4(g["q"][i], g["t"][i]), rtol=0, atol=1e-12)
+        for e in range(4):
+            R2.L.refslam_edge(R2.h, e, C.byref(a), C.byref(b), T.ctypes.data_as(dp), C.byref(w))
+            assert w.value == 1.0 and 0 <= b.value < a.value < n
+        assert [R2.L.refslam_world_setid(R2.h, k) for k in range(2)] == [F.world_setid(k) for k in range(2)] == [0, 0]
+        P01 = R2.pose_between_worlds(0, 1)
+        assert P01 is not None and np.allclose(P01, F.pose_between_worlds(0, 1), rtol=1e-14, atol=1e-12)
+    finally:
+        R2.close(); F.close()
+
+
+def test_restoring_a_saved_session_matches_the_reference_restore_pipeline(tmp_path):
+    """Composer::loadStateFromDisk — what the reference node does for its `loadStateFromDisk` parameter — is four calls of
+    the reference's own functions (Worlds::loadStateFromDisk, NodeDataManager::load_kidnap_data_from_json,
+    NodeDataManager::load_solved_posegraph_data_from_json, PoseGraphSLAM::load_state).  They and the product's
+    pgs_facade_load_state_from_disk restore the same solved_posegraph.json; afterwards both sessions go on with new keyframes
+    and a loop edge into the restored (constant) part, and must build the same problem."""
+    import json
+    rng = np.random.default_rng(13)
+    R = ReferenceNode(); F = facade.Facade(odom_fanout=5, dry_run=True)
+    try:
+        g, n = _two_world_session(R, F, rng)
+        F.save_json(tmp_path)                                                # WorldsData + KidnapTimestamps; SolvedPoseGraph is filled below
+        q, t = F.poses()                                                     # every keyframe in the frame of its set root (dead-zone ones: placeholders)
+        world = [F.which_world(int(s)) for s in g["stamps"][:n]]
+    finally:
+        R.close(); F.close()
+    J = json.load(open(tmp_path / "solved_posegraph.json"))
+    assert J["SolvedPoseGraph"] in ([], None)                                # no Composer pass without a device: write what it would have written
+    J["SolvedPoseGraph"] = []
+    for i in range(n):
+        T = pgo.pose_to_mat4(q[i], t[i]) if world[i] >= 0 else pgo.pose_to_mat4(g["q"][i], g["t"][i])
+        J["SolvedPoseGraph"].append(dict(seq=i, stampNSec=int(g["stamps"][i]), worldID=world[i], setID_of_worldID=0 if world[i] >= 0 else -1,
+                                         w_T_c=dict(rows=4, cols=4, data=facade.io_mat_to_string(T, solved_layout=True), data_pretty=facade.io_prettyprint(T))))
+    d = tmp_path / "restore"; d.mkdir()
+    json.dump(J, open(d / "solved_posegraph.json", "w"), indent=4)
+
+    R = ReferenceNode(); F = facade.Facade(odom_fanout=5, dry_run=True)
+    for f, a in dict(refslam_load_state_from_disk=[C.c_char_p], refslam_slam_n_nodes=[], refslam_kidnap_status=[], refslam_n_kidnaps=[], refslam_node_stamp=[C.c_int],
+                     refslam_manager_node_pose=[C.c_int, dp]).items():
+        getattr(R.L, f).argtypes = [C.c_void_p] + a
+    R.L.refslam_node_stamp.restype = C.c_longlong
+    try:
+        assert R.L.refslam_load_state_from_disk(R.h, str(d).encode()) == 0
+        F.load_state_from_disk(d)
+        assert R.L.refslam_n_nodes(R.h) == F.n_keyframes() == n and R.L.refslam_slam_n_nodes(R.h) == F.n_nodes() == n
+        assert R.L.refslam_solved_until(R.h) == F.solved_until() == n - 1 and R.L.refslam_n_kidnaps(R.h) == 1 and R.L.refslam_kidnap_status(R.h) == 0
+        assert [R.L.refslam_world_setid(R.h, w) for w in range(2)] == [F.world_setid(w) for w in range(2)] == [0, 0]
+        T = np.zeros((4, 4)); Tm = np.zeros((4, 4)); fq, ft = F.poses()
+        for i in range(n):
+            assert R.L.refslam_node_stamp(R.h, i) == int(g["stamps"][i]) and R.L.refslam_which_world(R.h, int(g["stamps"][i])) == F.which_world(int(g["stamps"][i])) == world[i]
+            R.L.refslam_get_node_pose(R.h, i, T.ctypes.data_as(dp))          # the restored optimisation variable (ws_T_w * w_T_c again)
+            assert np.allclose(T, pgo.pose_to_mat4(fq[i], ft[i]), rtol=0, atol=1e-9)
+            R.L.refslam_manager_node_pose(R.h, i, Tm.ctypes.data_as(dp))     # the manager's pose: back in the keyframe's own world
+            if world[i] == 0:
+                assert np.allclose(Tm, T, rtol=0, atol=1e-9)
+        # ---- the restored sessions go on: new keyframes in world 1 and a loop edge into the restored part
+        last = int(g["stamps"][n - 1]); qn, tn = g["q"][n - 1], g["t"][n - 1]
+        new_stamps = [last + (k + 1) * 10**8 for k in range(6)]
+        new_q = np.array([pgo.quat_plus(qn, [0, 0, 0.01 * (k + 1)]) for k in range(6)]); new_t = np.array([tn + [0.5 * (k + 1), 0.1 * k, 0] for k in range(6)])
+        R.add_nodes(new_stamps, new_q, new_t); F.add_nodes(new_stamps, new_q, new_t)
+        all_stamps = np.r_[g["stamps"][:n], new_stamps]
+        lq, lt = pgo.mat4_to_pose(pgo.inv4(pgo.pose_to_mat4(g["q"][n - 20], g["t"][n - 20])) @ pgo.pose_to_mat4(new_q[4], new_t[4]))
+        R.add_loop_edges(all_stamps, [n + 4], [n - 20], [lq], [lt], [1.0]); F.add_loop_edges([n + 4], [n - 20], [lq], [lt], [1.0])
+        assert R.wakeup() and F.solve_once()
+        B = R.blocks(); od, lo, rg = B["type"] == 0, B["type"] == 1, B["type"] == 2
+        o, l, r = F.alternative_terms(0), F.alternative_terms(1), F.reg_terms()
+        assert np.array_equal(B["c1"][od], o["c1"]) and np.array_equal(B["c2"][od], o["c2"]) and np.allclose(B["w"][od], o["weight"], rtol=1e-9)
+        assert B["c1"][od].min() == n and np.allclose(B["obs"][od], mats(o["obs_rot"], o["obs_t"]), rtol=0, atol=1e-9)   # odometry only from solvedUntil+1 on (:1570)
+        assert np.array_equal(B["c1"][lo], l["c1"]) and np.array_equal(B["c2"][lo], l["c2"]) and len(l["c1"]) == 1
+        assert np.array_equal(B["c1"][rg], r["node"]) and np.allclose(B["w"][rg], r["w"]) and np.allclose(B["obs"][rg], mats(r["q"], r["t"]), rtol=0, atol=1e-9)
+        rq_, rt_, rs_, const = R.variables(); fq, ft = F.poses()
+        assert np.allclose(rt_, ft, rtol=0, atol=1e-8) and same_quats(rq_, fq)
+        assert const[:n].all() and not const[n:].any()                       # the restored keyframes are constant parameter blocks (:143-144), the new ones are free
+    finally:
+        R.close(); F.close()
