@@ -59,6 +59,7 @@ struct Ref {
   bool started = false;
   std::vector<Snapshot> snaps;
   long arrivals_seen = 0;
+  void (*solve_callback)() = nullptr;   // called inside the stand-in ceres::Solve, after the snapshot: the test's solver
   double perturb = 0.0;          // > 0: the stand-in "solve" moves every variable of the problem by a known, index-dependent amount
 };
 Ref* g_ref = nullptr;
@@ -102,6 +103,7 @@ void on_solve(const ceres::Solver::Options&, ceres::Problem* P, ceres::Solver::S
   for (int e = 0; e < ns; ++e) S.s[e] = *R->slam->get_raw_ptr_to_opt_switch(e);
   sum->termination_type = ceres::NO_CONVERGENCE;
   R->snaps.push_back(S);
+  if (R->solve_callback) R->solve_callback();   // may call refslam_write_vars(): that is "the solve"
   if (R->perturb > 0) {
     // A stand-in for what a solve does to the state the NEXT wake-up starts from: every pose that appears in a residual
     // block moves by Plus(q, a*eps_i), t += a*d_i, every switch of a block changes, all as closed forms of the index and
@@ -183,6 +185,16 @@ void refslam_kidnap(void* h, long long stamp_ns, int kidnapped) {
   std_msgs::Header* m = new std_msgs::Header();
   m->stamp = ros::Time::fromNSec(stamp_ns); m->frame_id = kidnapped ? "kidnapped" : "unkidnapped";
   R->manager->rcvd_kidnap_indicator_callback(std_msgs::HeaderConstPtr(m));
+}
+// A solver behind the reference's ceres::Solve call: the callback runs on the reference's solver thread, reads the problem with
+// refslam_get_blocks / refslam_get_vars, solves it with whatever it likes and writes the result into the reference's own
+// optimisation arrays with refslam_write_vars — which is all ceres::Solve does as far as PoseGraphSLAM.cpp can tell.
+void refslam_set_solve_callback(void* h, void (*cb)()) { ((Ref*)h)->solve_callback = cb; }
+void refslam_write_vars(void* h, const double* q, const double* t, const double* s) {
+  Ref* R = (Ref*)h;
+  const int n = R->slam->n_opt_variables(), ns = R->slam->n_opt_switch();
+  for (int i = 0; i < n; ++i) { std::memcpy(R->slam->get_raw_ptr_to_opt_variable_q(i), q + 4 * i, 32); std::memcpy(R->slam->get_raw_ptr_to_opt_variable_t(i), t + 3 * i, 24); }
+  for (int e = 0; e < ns; ++e) *R->slam->get_raw_ptr_to_opt_switch(e) = s[e];
 }
 void refslam_set_perturb(void* h, double amplitude) { ((Ref*)h)->perturb = amplitude; }
 // One wake-up of PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF().  Returns 1 if it reached ceres::Solve.

@@ -440,3 +440,57 @@ def test_restoring_a_saved_session_matches_the_reference_restore_pipeline(tmp_pa
         assert const[:n].all() and not const[n:].any()                       # the restored keyframes are constant parameter blocks (:143-144), the new ones are free
     finally:
         R.close(); F.close()
+
+
+def test_reference_node_with_a_solver_behind_its_ceres_solve_call_matches_the_python_front_end_session():
+    """The drop-in, on the CPU: the reference's PoseGraphSLAM.cpp runs unmodified and every ceres::Solve it issues is served
+    by a callback that reads the recorded problem, minimises it with the oracle's LM and writes the result into the
+    reference's own optimisation arrays.  Over three wake-ups of a growing session the reference node must then hold the
+    same poses and switches as the oracle's Python front-end driving the same LM — front-end rules, warm starts and
+    re-anchored regularisers under REAL solves.  (tools/reference_node_with_libpgs.py is the same with libpgs.so on a GPU.)"""
+    g = synth.generate_config(2, n_nodes=150, n_loop=24)
+    order = np.argsort(np.maximum(g["la"], g["lb"]), kind="stable")
+    R = ReferenceNode(); M = frontend.Manager(); P = frontend.ReferenceFrontEnd(M, odom_fanout=5)
+    R.L.refslam_set_solve_callback.argtypes = [C.c_void_p, C.c_void_p]; R.L.refslam_write_vars.argtypes = [C.c_void_p, dp, dp, dp]
+    solves = []
+
+    def serve_ceres_solve():
+        B = R.blocks(); q, t, s, _ = R.variables()
+        od, lo, rg = B["type"] == 0, B["type"] == 1, B["type"] == 2
+        pose = lambda Ms: (np.array([pgo.mat4_to_pose(X)[0] for X in Ms]).reshape(-1, 4), np.array([pgo.mat4_to_pose(X)[1] for X in Ms]).reshape(-1, 3))
+        S = pgo.Problem(); S.set_nodes(q, t)
+        oq, ot = pose(B["obs"][od]); S.add_odom_edges(B["c1"][od], B["c2"][od], oq, ot, B["w"][od])
+        lq, lt = pose(B["obs"][lo]); S.add_loop_edges(B["c1"][lo], B["c2"][lo], lq, lt, B["w"][lo], s_init=s[B["sw"][lo]])
+        rq, rt = pose(B["obs"][rg]); S.set_regularizers(B["c1"][rg], rq, rt, B["w"][rg])
+        solves.append(S.solve())
+        q2, t2 = S.poses(); s2 = s.copy(); s2[B["sw"][lo]] = S.switches()
+        q2, t2, s2 = (np.ascontiguousarray(x, dtype=np.float64) for x in (q2, t2, s2))
+        R.L.refslam_write_vars(R.h, q2.ctypes.data_as(dp), t2.ctypes.data_as(dp), s2.ctypes.data_as(dp))
+
+    cb = C.CFUNCTYPE(None)(serve_ceres_solve)
+    R.L.refslam_set_solve_callback(R.h, C.cast(cb, C.c_void_p))
+    try:
+        epos = 0; T = np.zeros((4, 4))
+        for lo_ in range(0, 150, 50):
+            sl = slice(lo_, lo_ + 50)
+            R.add_nodes(g["stamps"][sl], g["q"][sl], g["t"][sl])
+            for i in range(lo_, lo_ + 50):
+                M.add_node(int(g["stamps"][i]), g["q"][i], g["t"][i])
+            take = []
+            while epos < len(order) and max(g["la"][order[epos]], g["lb"][order[epos]]) < lo_ + 50:
+                take.append(order[epos]); epos += 1
+            take = np.array(take, dtype=int)
+            assert len(take)
+            R.add_loop_edges(g["stamps"], g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
+            for e in take:
+                M.add_loop_edge(int(g["la"][e]), int(g["lb"][e]), g["lq"][e], g["lt"][e], float(g["lw"][e]))
+            assert R.wakeup()
+            sp = P.trigger(solve=True)
+            assert len(solves[-1]["iterations"]) == len(sp["iterations"]) and abs(solves[-1]["final_cost"] - sp["final_cost"]) <= 1e-9 * sp["final_cost"]
+            for i in range(lo_ + 50):
+                R.L.refslam_get_node_pose(R.h, i, T.ctypes.data_as(dp))
+                assert np.allclose(T, pgo.pose_to_mat4(P.opt_q[i], P.opt_t[i]), rtol=0, atol=1e-8)
+            assert R.L.refslam_solved_until(R.h) == P.solved_until == lo_ + 49
+        assert len(solves) == 3 and solves[-1]["final_cost"] < solves[-1]["initial_cost"]
+    finally:
+        R.close()

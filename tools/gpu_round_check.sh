@@ -6,6 +6,8 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 # round 1 ended with an xdist worker crash that was traced to a buffer overrun in pgs_facade_compose: confirm the fix, full output kept
 python -m pytest tests -m gpu -q -n 4 --dist loadfile > gpurun_out/gpu_suite_xdist.txt 2>&1; tail -3 gpurun_out/gpu_suite_xdist.txt
 python tools/facade_alternative_check.py 2>&1 | tail -4
+# the reference's own PoseGraphSLAM.cpp with libpgs.so serving its ceres::Solve calls, against the same served by the oracle
+python tests/reference_node_with_libpgs.py 2>/dev/null | grep 'wake-up' 
 python tools/fourdof_bench.py > gpurun_out/fourdof_bench.txt 2>&1; cat gpurun_out/fourdof_bench.txt
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err; cut -c1-3000 gpurun_out/bench.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>&1; cut -c1-400 gpurun_out/bench_ref.json
