@@ -494,3 +494,60 @@ def test_reference_node_with_a_solver_behind_its_ceres_solve_call_matches_the_py
         assert len(solves) == 3 and solves[-1]["final_cost"] < solves[-1]["initial_cost"]
     finally:
         R.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_sessions_match_the_reference_front_end(seed):
+    """Differential test over random sessions: random chunk sizes, loop edges between random keyframes (inside a world,
+    across the two worlds in both directions, and touching dead-zone keyframes, which every implementation must ignore),
+    an optional kidnap at a random place, wake-ups after every chunk whether or not anything new arrived.  Even seeds keep
+    the variables where the front end put them (the facade takes part); odd seeds move them after every wake-up with the
+    stand-in solve (reference vs Python front-end)."""
+    rng = np.random.default_rng(1000 + seed)
+    moved = seed % 2 == 1
+    g = synth.generate_config(4, n_nodes=int(rng.integers(30, 70)), n_interworld=4)
+    stamps, k0, k1 = g["stamps"], g["k0"], g["k1"]
+    two_worlds = rng.random() < 0.75
+    last = int(np.nonzero(stamps <= (k0[1] if two_worlds else k0[0]))[0][-1])          # keyframes 0..last: world 0 [, dead zone, world 1]
+    R = ReferenceNode(); M = frontend.Manager(); P = frontend.ReferenceFrontEnd(M, odom_fanout=5)
+    F = None if moved else facade.Facade(odom_fanout=5, dry_run=True)
+    if moved:
+        R.L.refslam_set_perturb(R.h, 0.2)
+    try:
+        pos, kidnapped_sent, unkidnapped_sent, wake = 0, False, False, 0
+        have = []                                                                      # keyframes ingested so far
+        while pos <= last:
+            hi = min(last + 1, pos + int(rng.integers(5, 40)))
+            for i in range(pos, hi):
+                if two_worlds and not kidnapped_sent and stamps[i] > k0[0]:
+                    R.kidnap(int(k0[0]), 1); M.kidnap_indicator(int(k0[0]), 1); F and F.kidnap_indicator(int(k0[0]), 1); kidnapped_sent = True
+                if two_worlds and kidnapped_sent and not unkidnapped_sent and stamps[i] > k1[0]:
+                    R.kidnap(int(k1[0]), 0); M.kidnap_indicator(int(k1[0]), 0); F and F.kidnap_indicator(int(k1[0]), 0); unkidnapped_sent = True
+                R.add_nodes(stamps[i:i + 1], g["q"][i:i + 1], g["t"][i:i + 1]); M.add_node(int(stamps[i]), g["q"][i], g["t"][i])
+                F and F.add_nodes(stamps[i:i + 1], g["q"][i:i + 1], g["t"][i:i + 1])
+                have.append(i)
+            pos = hi
+            for _ in range(int(rng.integers(0, 4))):
+                a, b = (int(x) for x in rng.choice(have, size=2, replace=False)) if len(have) > 1 else (0, 0)
+                if a == b:
+                    continue
+                wa, wb = M.which_world_is_this(int(stamps[a])), M.which_world_is_this(int(stamps[b]))
+                if wa >= 0 and wb >= 0 and wa != wb and (wb, wa) != (0, 1) and not M.worlds.is_exist(wa, wb):
+                    a, b = b, a                                                        # the first cross edge fixes key (0,1): later look-ups stay direct (no BFS branch)
+                T = pgo.inv4(pgo.pose_to_mat4(g["q"][b], g["t"][b])) @ pgo.pose_to_mat4(g["q"][a], g["t"][a])
+                q, t = pgo.mat4_to_pose(T); t = t + rng.normal(size=3) * 0.05
+                R.add_loop_edges(stamps, [a], [b], [q], [t], [1.0]); M.add_loop_edge(a, b, q, t, 1.0); F and F.add_loop_edges([a], [b], [q], [t], [1.0])
+            expect = P.prev_loopedge_len != len(M.edges) and not M.kidnapped          # the trigger condition (:1306-1319)
+            fired = R.wakeup()
+            P.trigger(solve=False)
+            assert fired == expect
+            if F is not None:
+                assert F.solve_once() == fired
+            if fired:
+                wake += 1
+                compare(R, F, P, 5)
+                if moved:
+                    stand_in_solve(P, 0.2, wake)
+    finally:
+        R.close(); F and F.close()
+
