@@ -551,3 +551,36 @@ def test_random_sessions_match_the_reference_front_end(seed):
     finally:
         R.close(); F and F.close()
 
+
+
+def test_loop_edge_time_stamp_lookup_matches_the_reference_callback():
+    """loopclosure_pose_callback finds the two keyframes of a LoopEdge message by time stamp (src/NodeDataManager.cpp:107-189,
+    find_indexof_node :274-299): stamps that are a little off still match, stamps further off drop the edge.  Random offsets
+    around that tolerance, between keyframes 0.1 s apart, through the reference's callback and the product's."""
+    rng = np.random.default_rng(21)
+    n = 40
+    stamps = 10**9 + np.arange(n, dtype=np.int64) * 10**8
+    q = np.tile([0, 0, 0, 1.0], (n, 1)); t = np.c_[np.arange(n, dtype=float), np.zeros(n), np.zeros(n)]
+    R = ReferenceNode(); F = facade.Facade(dry_run=True)
+    R.L.refslam_edge.argtypes = [C.c_void_p, C.c_int, ip, ip, dp, dp]
+    try:
+        R.add_nodes(stamps, q, t); F.add_nodes(stamps, q, t)
+        kept = 0
+        for k in range(120):
+            a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+            off = [int(x) for x in rng.choice([0, 1, -1, 400_000, -400_000, 999_000, -999_000, 1_000_000, -1_000_000, 1_001_000, -1_001_000, 3_000_000, 49_000_000, -60_000_000], size=2)]
+            sa, sb = int(stamps[a]) + off[0], int(stamps[b]) + off[1]
+            lq = np.array([0, 0, 0, 1.0]); lt = np.array([float(k), 0.0, 0.0])
+            before = R.L.refslam_n_edges(R.h)
+            after = R.L.refslam_add_loop_edge(R.h, sa, sb, lq.ctypes.data_as(dp), lt.ctypes.data_as(dp), 1.0)
+            got = F.add_loop_edge_stamped(sa, sb, lq, lt, 1.0)
+            assert (after - before) == (1 if got else 0), (k, off, after - before, got)
+            if got:
+                ia, ib = C.c_int(), C.c_int(); T = np.zeros((4, 4)); w = C.c_double()
+                R.L.refslam_edge(R.h, after - 1, C.byref(ia), C.byref(ib), T.ctypes.data_as(dp), C.byref(w))
+                assert (ia.value, ib.value) == (a, b) and T[0, 3] == float(k)
+                kept += 1
+        assert 10 < kept < 110                                                 # both outcomes occurred
+        assert F.n_loop == kept
+    finally:
+        R.close(); F.close()
