@@ -584,3 +584,40 @@ def test_loop_edge_time_stamp_lookup_matches_the_reference_callback():
         assert F.n_loop == kept
     finally:
         R.close(); F.close()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_world_indexing_with_several_kidnaps_matches_the_reference_manager(seed):
+    """which_world_is_this / n_worlds / nodeidx_of_world_i_started / _ended (src/NodeDataManager.cpp:1127-1304) with up to four
+    kidnaps, queried for stamps before, inside and after every world and dead zone, also while still kidnapped."""
+    rng = np.random.default_rng(300 + seed)
+    R = ReferenceNode(); F = facade.Facade(dry_run=True); M = frontend.Manager()
+    try:
+        t = 10**9; all_stamps = []; marks = []
+        n_kid = int(rng.integers(2, 5)); end_kidnapped = seed == 2
+        for w in range(n_kid + 1):
+            for _ in range(int(rng.integers(3, 9))):                             # keyframes of world w
+                t += int(rng.integers(5, 20)) * 10**7
+                R.add_nodes([t], [[0, 0, 0, 1.0]], [[float(len(all_stamps)), 0, 0]]); F.add_nodes([t], [[0, 0, 0, 1.0]], [[float(len(all_stamps)), 0, 0]])
+                M.add_node(t, np.array([0, 0, 0, 1.0]), np.array([float(len(all_stamps)), 0, 0])); all_stamps.append(t)
+            if w == n_kid:
+                break
+            t += 3 * 10**7; k0 = t; marks.append(k0)
+            R.kidnap(k0, 1); F.kidnap_indicator(k0, 1); M.kidnap_indicator(k0, 1)
+            for _ in range(int(rng.integers(0, 4))):                             # keyframes that arrive while kidnapped
+                t += int(rng.integers(5, 20)) * 10**7
+                R.add_nodes([t], [[0, 0, 0, 1.0]], [[0.0, 1.0, 0]]); F.add_nodes([t], [[0, 0, 0, 1.0]], [[0.0, 1.0, 0]]); M.add_node(t, np.array([0, 0, 0, 1.0]), np.array([0, 1.0, 0])); all_stamps.append(t)
+            if end_kidnapped and w == n_kid - 1:
+                break
+            t += 3 * 10**7; marks.append(t)
+            R.kidnap(t, 0); F.kidnap_indicator(t, 0); M.kidnap_indicator(t, 0)
+        probes = sorted(set(all_stamps + marks + [m + d for m in marks for d in (-1, 1, 10**6)] + [all_stamps[0] - 10**8, t + 10**9]
+                            + [int(x) for x in rng.integers(all_stamps[0] - 10**8, t + 10**8, size=60)]))
+        assert [R.L.refslam_which_world(R.h, s) for s in probes] == [F.which_world(s) for s in probes] == [M.which_world_is_this(s) for s in probes]
+        nw = R.L.refslam_n_worlds(R.h)
+        assert nw == F.n_worlds() == M.n_worlds()
+        for w in range(-1, nw + 2):
+            assert R.L.refslam_world_start(R.h, w) == F.world_start(w) == M.nodeidx_of_world_i_started(w), w
+            assert R.L.refslam_world_end(R.h, w) == F.world_end(w) == M.nodeidx_of_world_i_ended(w), w
+    finally:
+        R.close(); F.close()
