@@ -3,8 +3,9 @@ body of the reference's Composer::pose_assember_thread (reference src/Composer.c
 the other with 4x4 numpy matrices and the generic inverse, exactly as the reference walks it — including the
 `jmb[world].rbegin()` look-ups that make dead-zone keyframes depend on what was assembled before them.
 
-Parity unpinned: the reference holds no test or golden vector for this function; the restatement is
-checked by known-answer cases in tests/test_composer.py."""
+Pinned to the reference's own Composer::pose_assember_thread (compiled unmodified into oracle/_ref/libref_frontend.so and
+single-stepped) by tests/test_reference_frontend.py::test_pose_assembly_matches_the_reference_composer_thread, over the
+states a session goes through; known-answer cases in tests/test_composer.py."""
 import numpy as np
 
 

@@ -43,6 +43,7 @@
 #define private public          // the functors keep their observation and weight private; this translation unit only reads them
 #define protected public
 #include "PoseGraphSLAM.h"      // -I /root/reference/src
+#include "Composer.h"
 #undef private
 #undef protected
 
@@ -55,10 +56,11 @@ struct Ref {
   ros::NodeHandle nh;
   NodeDataManager* manager = nullptr;
   PoseGraphSLAM* slam = nullptr;
-  std::thread th;
-  bool started = false;
+  Composer* composer = nullptr;
+  std::thread th, th_composer;
+  bool started = false, composer_started = false;
   std::vector<Snapshot> snaps;
-  long arrivals_seen = 0;
+  long arrivals_seen = 0, composer_arrivals_seen = 0;
   void (*solve_callback)() = nullptr;   // called inside the stand-in ceres::Solve, after the snapshot: the test's solver
   double perturb = 0.0;          // > 0: the stand-in "solve" moves every variable of the problem by a known, index-dependent amount
 };
@@ -127,12 +129,14 @@ void on_solve(const ceres::Solver::Options&, ceres::Problem* P, ceres::Solver::S
   }
 }
 
-void wait_arrival(Ref* R) {                      // until the solver thread is parked in loop_rate.sleep() again
+void wait_arrival(std::thread& th, long& seen) {   // until that thread is parked in its rate.sleep() again
   ros::Gate& g = ros::gate();
   std::unique_lock<std::mutex> lk(g.m);
-  g.cv.wait(lk, [&] { return g.arrivals > R->arrivals_seen; });
-  R->arrivals_seen = g.arrivals;
+  ros::GateState& st = g.per_thread[th.get_id()];
+  g.cv.wait(lk, [&] { return st.arrivals > seen; });
+  seen = st.arrivals;
 }
+void give_token(std::thread& th) { ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); ++g.per_thread[th.get_id()].tokens; g.cv.notify_all(); }
 
 }  // namespace
 
@@ -144,17 +148,18 @@ void* refslam_create() {
   R->manager = new NodeDataManager(R->nh);
   R->slam = new PoseGraphSLAM(R->manager);
   ceres::solve_hook() = on_solve;
-  { ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); g.tokens = 0; g.arrivals = 0; g.free_run = false; }
+  R->composer = new Composer(R->manager, R->slam, nullptr, R->nh);   // no VizPoseGraph: only the assembler thread is run
+  { ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); g.per_thread.clear(); g.free_run = false; }
   g_ref = R;
   return R;
 }
 void refslam_destroy(void* h) {
   Ref* R = (Ref*)h;
-  if (R->started) {
-    R->slam->reinit_ceres_problem_onnewloopedge_optimize6DOF_disable();
-    { ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); g.free_run = true; g.cv.notify_all(); }
-    R->th.join();
-  }
+  R->slam->reinit_ceres_problem_onnewloopedge_optimize6DOF_disable();
+  R->composer->pose_assember_disable();
+  { ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); g.free_run = true; g.cv.notify_all(); }
+  if (R->started) R->th.join();
+  if (R->composer_started) R->th_composer.join();
   ceres::solve_hook() = nullptr;
   g_ref = nullptr;                                // the reference's destructors free fixed arrays; the objects are leaked on purpose (test process)
   delete R;
@@ -205,11 +210,24 @@ int refslam_wakeup(void* h) {
     R->slam->reinit_ceres_problem_onnewloopedge_optimize6DOF_enable();
     R->th = std::thread(&PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF, R->slam);
     R->started = true;
-  } else {
-    ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); ++g.tokens; g.cv.notify_all();
-  }
-  wait_arrival(R);
+  } else give_token(R->th);
+  wait_arrival(R->th, R->arrivals_seen);
   return R->snaps.size() > before ? 1 : 0;
+}
+// One pass of Composer::pose_assember_thread (src/Composer.cpp:10-263), the reference's own, on its own thread; then
+// global_lmb — the assembled pose of every keyframe — is copied out.  Returns the number of poses.
+int refslam_compose_once(void* h, double* T16, int cap) {
+  Ref* R = (Ref*)h;
+  if (!R->composer_started) {
+    R->composer->pose_assember_enable();
+    R->th_composer = std::thread(&Composer::pose_assember_thread, R->composer, 30);
+    R->composer_started = true;
+  } else give_token(R->th_composer);
+  wait_arrival(R->th_composer, R->composer_arrivals_seen);
+  std::lock_guard<std::mutex> lk(R->composer->mx);
+  const int n = (int)R->composer->global_lmb.size();
+  for (int i = 0; i < n && i < cap; ++i) copy16(R->composer->global_lmb[i], T16 + 16 * i);
+  return n;
 }
 // ---- what the reference built, as of the last ceres::Solve
 int refslam_n_blocks(void* h) { Ref* R = (Ref*)h; return R->snaps.empty() ? 0 : (int)R->snaps.back().blocks.size(); }

@@ -60,6 +60,7 @@ struct Dyn {
   Dyn col(int j) const { Dyn o(r, 1); for (int i = 0; i < r; ++i) o(i, 0) = (*this)(i, j); return o; }
   Dyn topLeftCorner(int rr, int cc) const { Dyn o(rr, cc); for (int i = 0; i < rr; ++i) for (int j = 0; j < cc; ++j) o(i, j) = (*this)(i, j); return o; }
   Dyn topRows(int n) const { return topLeftCorner(n, c); }
+  Dyn head(int n) const { Dyn o(n, 1); for (int i = 0; i < n; ++i) o.a[i] = a[i]; return o; }
   Dyn& operator*=(const T& s) { for (int i = 0; i < r * c; ++i) a[i] = a[i] * s; return *this; }
   inline Dyn& operator*=(const Dyn& o);
   CommaInit<T> operator<<(const T& v) { a[0] = v; return CommaInit<T>{this, 1}; }

@@ -6,6 +6,7 @@
 #include <mutex>
 #include <cmath>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <ostream>
 #include <string>
@@ -50,10 +51,11 @@ struct Time {
 };
 inline std::ostream& operator<<(std::ostream& os, const Time& t) { char b[40]; snprintf(b, sizeof(b), "%u.%09u", t.sec, t.nsec); return os << b; }
 inline std::ostream& operator<<(std::ostream& os, const Duration& t) { return os << t.toSec(); }
-// Rate::sleep() is where the reference's polling loops yield.  Here it is a GATE: the thread reports that it arrived
-// (one loop iteration is over) and waits for the test driver to hand it a token, so the driver single-steps the
-// reference's `while (enabled) { ... loop_rate.sleep(); }` loops deterministically; free_run lets them drain at shutdown.
-struct Gate { std::mutex m; std::condition_variable cv; long tokens = 0, arrivals = 0; bool free_run = false; };
+// Rate::sleep() is where the reference's polling loops yield.  Here it is a GATE, one per thread: the thread reports that it
+// arrived (one loop iteration is over) and waits for the test driver to hand it a token, so the driver single-steps each of the
+// reference's `while (enabled) { ... rate.sleep(); }` loops deterministically; free_run lets them drain at shutdown.
+struct GateState { long tokens = 0, arrivals = 0; };
+struct Gate { std::mutex m; std::condition_variable cv; std::map<std::thread::id, GateState> per_thread; bool free_run = false; };
 inline Gate& gate() { static Gate g; return g; }
 struct Rate {
   double hz;
@@ -61,9 +63,10 @@ struct Rate {
   bool sleep() {
     Gate& g = gate();
     std::unique_lock<std::mutex> lk(g.m);
-    ++g.arrivals; g.cv.notify_all();
-    g.cv.wait(lk, [&] { return g.tokens > 0 || g.free_run; });
-    if (!g.free_run) --g.tokens;
+    GateState& st = g.per_thread[std::this_thread::get_id()];
+    ++st.arrivals; g.cv.notify_all();
+    g.cv.wait(lk, [&] { return st.tokens > 0 || g.free_run; });
+    if (!g.free_run) --st.tokens;
     return true;
   }
 };

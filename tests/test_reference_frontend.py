@@ -621,3 +621,56 @@ def test_world_indexing_with_several_kidnaps_matches_the_reference_manager(seed)
             assert R.L.refslam_world_end(R.h, w) == F.world_end(w) == M.nodeidx_of_world_i_ended(w), w
     finally:
         R.close(); F.close()
+
+
+def test_pose_assembly_matches_the_reference_composer_thread():
+    """Composer::pose_assember_thread (src/Composer.cpp:10-263), the reference's own code on its own thread, against the
+    oracle's restatement (oracle/composer.py — which the device kernel of include/pgs_compose.h is held to in
+    tests/test_composer.py): before any solve, after a solve that moved the keyframes of world 0, with keyframes that
+    arrived after it, through a dead zone, in a second world before and after it is merged into the first."""
+    from oracle import composer
+    rng = np.random.default_rng(15)
+    g = synth.generate_config(4, n_nodes=50, n_interworld=6)
+    stamps, k0, k1 = g["stamps"], g["k0"], g["k1"]
+    w0 = np.nonzero(stamps <= k0[0])[0]; dead = np.nonzero((stamps > k0[0]) & (stamps <= k1[0]))[0]; w1 = np.nonzero((stamps > k1[0]) & (stamps <= k0[1]))[0]
+    R = ReferenceNode(); M = frontend.Manager(); P = frontend.ReferenceFrontEnd(M, odom_fanout=5)
+    R.L.refslam_compose_once.argtypes = [C.c_void_p, dp, C.c_int]
+    R.L.refslam_set_perturb(R.h, 0.3)
+    checked = [0]
+
+    def nodes(idx):
+        R.add_nodes(stamps[idx], g["q"][idx], g["t"][idx])
+        for i in idx:
+            M.add_node(int(stamps[i]), g["q"][i], g["t"][i])
+
+    def loops(pairs):
+        for a, b in pairs:
+            T = pgo.inv4(pgo.pose_to_mat4(g["q"][b], g["t"][b])) @ pgo.pose_to_mat4(g["q"][a], g["t"][a])
+            q, t = pgo.mat4_to_pose(T); t = t + rng.normal(size=3) * 0.05
+            R.add_loop_edges(stamps, [a], [b], [q], [t], [1.0]); M.add_loop_edge(a, b, q, t, 1.0)
+
+    def wake(k):
+        assert R.wakeup(); P.trigger(solve=False); stand_in_solve(P, 0.3, k)
+
+    def check():
+        n = len(M.poses)
+        buf = np.zeros((n + 8, 4, 4))
+        got = R.L.refslam_compose_once(R.h, buf.ctypes.data_as(dp), n + 8)
+        slam = [pgo.pose_to_mat4(P.opt_q[i], P.opt_t[i]) for i in range(len(P.opt_q))]
+        want, wid, _ = composer.assemble(M, slam, P.solved_until)
+        assert got == n == len(want)
+        assert np.allclose(buf[:n], want, rtol=0, atol=1e-8), int(np.abs(buf[:n] - want).reshape(n, -1).max(axis=1).argmax())
+        checked[0] += 1
+
+    try:
+        nodes(w0[:30]); check()                                               # nothing solved: odometry
+        loops([(int(w0[25]), int(w0[3]))]); wake(1); check()                  # world 0 solved and moved
+        nodes(w0[30:]); check()                                               # keyframes after the solve: carried forward
+        R.kidnap(int(k0[0]), 1); M.kidnap_indicator(int(k0[0]), 1); nodes(dead); check()          # dead zone hangs off the last pose of world 0
+        R.kidnap(int(k1[0]), 0); M.kidnap_indicator(int(k1[0]), 0); nodes(w1[:25]); check()       # a new world, not solved, not connected
+        loops([(int(w1[20]), int(w1[2]))]); wake(2); check()                  # world 1 solved on its own
+        nodes(w1[25:]); loops([(int(w1[30]), int(w0[10]))]); wake(3); check() # merged into world 0's set
+        nodes(np.arange(int(w1[-1]) + 1, int(w1[-1]) + 1)); check()
+        assert checked[0] == 8
+    finally:
+        R.close()
