@@ -93,6 +93,11 @@ int pgs_io_string_to_mat(const char* s, double* T16);
  * EMPTY facade (before any keyframe): relative poses, world stamps, union-find op-log replayed. */
 int pgs_facade_load_worlds_state(pgs_facade_handle h, const char* solved_posegraph_json);
 /* loads a solved_posegraph.json: n = number of keyframes (call with NULL outputs to size), poses [n][16], stamps, ids */
+/* Composer::saveStateToDisk (src/Composer.cpp:955-1105), what the reference node does at shutdown for its `saveStateToDisk` parameter:
+ * if the session is not kidnapped the current world is ended at the stamp of the last keyframe (mark_as_kidnapped_and_signal_end_of_world,
+ * :967-974 — the session is left in the kidnapped state, as the reference's is), then <dir>/solved_posegraph.json is written.
+ * pgs_facade_save_json above writes the same file without touching the session. */
+int pgs_facade_save_state_to_disk(pgs_facade_handle h, const char* dir);
 /* Composer::loadStateFromDisk (src/Composer.cpp:1109-1177), what the reference node does for its `loadStateFromDisk` parameter:
  * from <dir>/solved_posegraph.json restore the Worlds object ("WorldsData"), the kidnap stamps ("KidnapTimestamps"), every keyframe of
  * "SolvedPoseGraph" (moved from its set root's frame back into its own world's frame) and then PoseGraphSLAM::load_state (the

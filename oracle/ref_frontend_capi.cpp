@@ -291,6 +291,9 @@ int refslam_load_state_from_disk(void* h, const char* dir) {
   if (!R->slam->load_state()) return 4;
   return 0;
 }
+// Composer::saveStateToDisk (src/Composer.cpp:990-1105) and Composer::loadStateFromDisk (:1109-1177), the reference's own
+int refslam_composer_save(void* h, const char* dir) { return ((Ref*)h)->composer->saveStateToDisk(std::string(dir)) ? 1 : 0; }
+int refslam_composer_load(void* h, const char* dir) { return ((Ref*)h)->composer->loadStateFromDisk(std::string(dir)) ? 1 : 0; }
 int refslam_slam_n_nodes(void* h) { return ((Ref*)h)->slam->nNodes(); }
 int refslam_kidnap_status(void* h) { return ((Ref*)h)->manager->curr_kidnap_status() ? 1 : 0; }
 long long refslam_node_stamp(void* h, int i) { return (long long)((Ref*)h)->manager->getNodeTimestamp(i).toNSec(); }

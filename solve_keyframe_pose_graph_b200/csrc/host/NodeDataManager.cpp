@@ -63,6 +63,12 @@ bool NodeDataManager::getNodePose(int i, Matrix4d& w_T_cam) const {
   w_T_cam = node_pose[i]; return true;
 }
 const Matrix4d& NodeDataManager::getNodePose(int i) const { std::lock_guard<std::mutex> lk(node_mutex); return node_pose[i]; }
+bool NodeDataManager::mark_as_kidnapped_and_signal_end_of_world() {
+  int64_t last;
+  { std::lock_guard<std::mutex> lk(node_mutex); if (node_timestamps.empty()) return false; last = node_timestamps.back(); }
+  return rcvd_kidnap_indicator(last, true);
+}
+
 bool NodeDataManager::load_kidnap_data(const std::vector<int64_t>& starts_ns, const std::vector<int64_t>& ends_ns) {
   if (!(starts_ns.size() == ends_ns.size() || starts_ns.size() == ends_ns.size() + 1)) return false;      // the reference exit(1)s (:944-948)
   std::lock_guard<std::mutex> lk(mutex_kidnap);

@@ -58,6 +58,9 @@ class NodeDataManager {
   // NodeDataManager::load_solved_posegraph_data_from_json treats it (:998-1090): the saved pose is in the frame of its world's
   // set root and is moved back into the world's own frame, the stamp must fall into the saved world and set; no world is started.
   bool load_kidnap_data(const std::vector<int64_t>& starts_ns, const std::vector<int64_t>& ends_ns);
+  // NodeDataManager::mark_as_kidnapped_and_signal_end_of_world (NodeDataManager.cpp:838-844): what Composer::saveStateToDisk does before it
+  // writes when the session is not kidnapped — the current world ends at the stamp of the last keyframe.  false: no keyframes / already kidnapped.
+  bool mark_as_kidnapped_and_signal_end_of_world();
   bool load_solved_node(int64_t stamp_ns, const Matrix4d& ws_T_c, int world_id, int set_id_of_world, std::string* err = nullptr);
 
   // ---- kidnap / world queries

@@ -196,6 +196,12 @@ int pgs_facade_save_json(pgs_facade_handle h, const char* dir) try {
   if (h->composer && !h->composer->get_global_lmb().empty()) mask |= 4;                          // ... with the assembled poses when a pass has run
   return mask;
 } CATCH_FACADE(h)
+int pgs_facade_save_state_to_disk(pgs_facade_handle h, const char* dir) try {
+  if (!h || !dir) return PGS_ERR_INVALID_ARGUMENT;
+  h->err.clear();
+  if (!h->manager.curr_kidnap_status()) h->manager.mark_as_kidnapped_and_signal_end_of_world();          // Composer.cpp:969-971
+  return pgs::saveSolvedPoseGraph(h->composer, h->manager, dir, &h->err) ? PGS_OK : PGS_ERR_STATE;
+} CATCH_FACADE(h)
 int pgs_facade_load_posegraph_json(pgs_facade_handle h, const char* dir) try {
   if (!h || !dir) return PGS_ERR_INVALID_ARGUMENT;
   h->err.clear();

@@ -181,6 +181,10 @@ class Facade:
     def load_worlds_state(self, solved_posegraph_json):
         self._ck(self.L.pgs_facade_load_worlds_state(self.h, str(solved_posegraph_json).encode()))
 
+    def save_state_to_disk(self, directory):
+        """Composer::saveStateToDisk of the reference: end the current world at the last keyframe, write <directory>/solved_posegraph.json."""
+        self._ck(self.L.pgs_facade_save_state_to_disk(self.h, str(directory).encode()))
+
     def load_state_from_disk(self, directory):
         """Composer::loadStateFromDisk of the reference: restore a session from <directory>/solved_posegraph.json."""
         self._ck(self.L.pgs_facade_load_state_from_disk(self.h, str(directory).encode()))

@@ -674,3 +674,58 @@ def test_pose_assembly_matches_the_reference_composer_thread():
         assert checked[0] == 8
     finally:
         R.close()
+
+
+def test_solved_posegraph_json_written_and_restored_by_the_reference_composer(tmp_path):
+    """Composer::saveStateToDisk of the reference writes solved_posegraph.json for a two-world session (its own assembler
+    filled global_lmb); the product writes the same session.  KidnapTimestamps and WorldsData must agree, the reference's
+    SolvedPoseGraph must be readable by the product's reader, and — the other way round — Composer::loadStateFromDisk of the
+    reference itself (not a restatement of its call sequence) must restore a session from the file the PRODUCT restores from."""
+    import json
+    rng = np.random.default_rng(16)
+    R = ReferenceNode(); F = facade.Facade(odom_fanout=5, dry_run=True)
+    for f, a in dict(refslam_compose_once=[dp, C.c_int], refslam_composer_save=[C.c_char_p], refslam_composer_load=[C.c_char_p], refslam_slam_n_nodes=[],
+                     refslam_n_kidnaps=[], refslam_kidnap_status=[]).items():
+        getattr(R.L, f).argtypes = [C.c_void_p] + a
+    dR, dF = tmp_path / "ref", tmp_path / "ours"; dR.mkdir(); dF.mkdir()
+    try:
+        g, n = _two_world_session(R, F, rng)
+        lmb = np.zeros((n, 4, 4))
+        assert R.L.refslam_compose_once(R.h, lmb.ctypes.data_as(dp), n) == n
+        assert R.L.refslam_composer_save(R.h, str(dR).encode()) == 1
+        F.save_state_to_disk(dF)                                             # both end the current world at the last keyframe first (Composer.cpp:967-974)
+        assert R.L.refslam_kidnap_status(R.h) == 1 and R.L.refslam_n_kidnaps(R.h) == 1
+        Jr = json.load(open(dR / "solved_posegraph.json")); Jo = json.load(open(dF / "solved_posegraph.json"))
+        assert sorted(Jr) == sorted(Jo) == ["KidnapTimestamps", "SolvedPoseGraph", "WorldsData"]
+        assert Jr["KidnapTimestamps"] == Jo["KidnapTimestamps"] and len(Jr["KidnapTimestamps"]["kidnap_starts"]) == 2 and len(Jr["KidnapTimestamps"]["kidnap_ends"]) == 1
+        assert Jr["WorldsData"]["disjoint_set"] == Jo["WorldsData"]["disjoint_set"] and Jr["WorldsData"]["vec_world_starts"] == Jo["WorldsData"]["vec_world_starts"]
+        assert Jr["WorldsData"]["vec_world_ends"] == Jo["WorldsData"]["vec_world_ends"]
+        assert [sorted(x) for x in Jr["WorldsData"]["rel_pose_between_worlds__wb_T_wa"]] == [sorted(x) for x in Jo["WorldsData"]["rel_pose_between_worlds__wb_T_wa"]]
+        # the reference-written SolvedPoseGraph through the product's reader
+        T, st, wid, sid = facade.io_load_solved_posegraph(dR / "solved_posegraph.json")
+        assert len(T) == n and np.allclose(T, lmb, rtol=1e-15, atol=1e-300)
+        assert list(st) == [int(s) for s in g["stamps"][:n]] and list(wid) == [F.which_world(int(s)) for s in g["stamps"][:n]]
+        assert [int(x) for x in sid] == [F.world_setid(int(w)) if w >= 0 else -1 for w in wid]
+        entry = Jr["SolvedPoseGraph"][3]
+        assert sorted(entry) == ["seq", "setID_of_worldID", "stampNSec", "w_T_c", "worldID"] and sorted(entry["w_T_c"]) == ["cols", "data", "data_pretty", "rows"]
+        assert entry["w_T_c"]["data_pretty"] == facade.io_prettyprint(lmb[3]) and entry["w_T_c"]["data"] == facade.io_mat_to_string(lmb[3], solved_layout=True)
+    finally:
+        R.close(); F.close()
+    # ---- Composer::loadStateFromDisk itself, on the reference-written file and on the same file with the product's WorldsData / KidnapTimestamps
+    Jmix = dict(Jr); Jmix["WorldsData"] = Jo["WorldsData"]; Jmix["KidnapTimestamps"] = Jo["KidnapTimestamps"]
+    dM = tmp_path / "mixed"; dM.mkdir(); json.dump(Jmix, open(dM / "solved_posegraph.json", "w"), indent=4)
+    for d in (dR, dM):
+        R2 = ReferenceNode(); F2 = facade.Facade(odom_fanout=5, dry_run=True)
+        for f, a in dict(refslam_composer_load=[C.c_char_p], refslam_slam_n_nodes=[], refslam_n_kidnaps=[], refslam_kidnap_status=[]).items():
+            getattr(R2.L, f).argtypes = [C.c_void_p] + a
+        try:
+            assert R2.L.refslam_composer_load(R2.h, str(d).encode()) == 1
+            F2.load_state_from_disk(d)
+            assert R2.L.refslam_n_nodes(R2.h) == F2.n_keyframes() == n and R2.L.refslam_slam_n_nodes(R2.h) == F2.n_nodes() == n
+            assert R2.L.refslam_solved_until(R2.h) == F2.solved_until() == n - 1 and R2.L.refslam_n_kidnaps(R2.h) == 1 and R2.L.refslam_kidnap_status(R2.h) == 1
+            fq, ft = F2.poses(); T = np.zeros((4, 4))
+            for i in range(n):
+                R2.L.refslam_get_node_pose(R2.h, i, T.ctypes.data_as(dp))
+                assert np.allclose(T, pgo.pose_to_mat4(fq[i], ft[i]), rtol=0, atol=1e-9)
+        finally:
+            R2.close(); F2.close()
