@@ -14,7 +14,17 @@ void NodeDataManager::add_node(int64_t stamp_ns, const Matrix4d& w_T_cam, const 
   std::array<double, 36> cov{};                                                 // NodeDataManager.cpp:55-63
   if (cov36) for (int k = 0; k < 36; ++k) cov[k] = cov36[k];
   node_pose_covariance.push_back(cov);
-  if (node_pose.size() == 1) worlds_handle_raw_ptr->world_starts(stamp_ns);   // fresh start: world 0 (NodeDataManager.cpp:80-84)
+  // the first keyframe this manager RECEIVES (NodeDataManager.cpp:74-92; the reference keeps the flag in a function-local static):
+  // on a fresh start world 0 begins; after a restore from disk — the file was saved with the world ended, the session is kidnapped —
+  // the kidnap ends and a new world begins at this keyframe (mark_as_unkidnapped_and_signal_start_of_world)
+  if (!first_keyframe_received) {
+    first_keyframe_received = true;
+    if (node_pose.size() == 1) worlds_handle_raw_ptr->world_starts(stamp_ns);
+    else if (current_kidnap_status) {
+      { std::lock_guard<std::mutex> lk2(mutex_kidnap); current_kidnap_status = false; kidnap_ends.push_back(stamp_ns); }
+      worlds_handle_raw_ptr->world_starts(stamp_ns);
+    }
+  }
 }
 
 // First node whose stamp is strictly within 1 ms of `stamp` (the reference scans linearly and returns

@@ -96,6 +96,7 @@ class NodeDataManager {
   mutable std::mutex mutex_kidnap;
   std::vector<int64_t> kidnap_starts, kidnap_ends;
   std::atomic<bool> current_kidnap_status;
+  bool first_keyframe_received = false;   // guarded by node_mutex
   Worlds* worlds_handle_raw_ptr = nullptr;
 };
 

@@ -727,5 +727,27 @@ def test_solved_posegraph_json_written_and_restored_by_the_reference_composer(tm
             for i in range(n):
                 R2.L.refslam_get_node_pose(R2.h, i, T.ctypes.data_as(dp))
                 assert np.allclose(T, pgo.pose_to_mat4(fq[i], ft[i]), rtol=0, atol=1e-9)
+            # the restored session receives its first keyframe: the kidnap that the save started ends there and a NEW world begins
+            # (NodeDataManager.cpp:74-92); a loop edge from it into restored world 0 merges that world into the old set
+            last = int(g["stamps"][n - 1])
+            new_stamps = [last + (k + 1) * 10**8 for k in range(8)]
+            new_q = np.tile([0, 0, 0, 1.0], (8, 1)); new_t = np.c_[np.arange(8) * 0.7, np.zeros(8), np.zeros(8)]
+            R2.add_nodes(new_stamps, new_q, new_t); F2.add_nodes(new_stamps, new_q, new_t)
+            assert R2.L.refslam_kidnap_status(R2.h) == 0 and R2.L.refslam_n_kidnaps(R2.h) == 2 and R2.L.refslam_n_worlds(R2.h) == F2.n_worlds() == 3
+            wr_, wf_ = [R2.L.refslam_which_world(R2.h, int(s_)) for s_ in new_stamps], [F2.which_world(int(s_)) for s_ in new_stamps]
+            assert wr_ == wf_, (wr_, wf_)
+            assert wr_ == [-2] + [2] * 7        # the keyframe AT the un-kidnap stamp still counts as dead zone (<=, NodeDataManager.cpp:1127-1198)
+            all_stamps = np.r_[g["stamps"][:n], new_stamps]
+            lq, lt = np.array([0, 0, 0, 1.0]), np.array([0.3, -0.2, 0.1])
+            R2.add_loop_edges(all_stamps, [n + 5], [7], [lq], [lt], [1.0]); F2.add_loop_edges([n + 5], [7], [lq], [lt], [1.0])
+            assert R2.wakeup() and F2.solve_once()
+            B = R2.blocks(); od, lo, rg = B["type"] == 0, B["type"] == 1, B["type"] == 2
+            o, l, r = F2.alternative_terms(0), F2.alternative_terms(1), F2.reg_terms()
+            assert np.array_equal(B["c1"][od], o["c1"]) and np.array_equal(B["c2"][od], o["c2"]) and np.allclose(B["w"][od], o["weight"], rtol=1e-9)
+            assert np.array_equal(B["c1"][lo], l["c1"]) and np.array_equal(B["c2"][lo], l["c2"]) and np.allclose(B["obs"][lo], mats(l["obs_rot"], l["obs_t"]), rtol=0, atol=1e-9)
+            assert np.array_equal(B["c1"][rg], r["node"]) and np.allclose(B["w"][rg], r["w"]) and np.allclose(B["obs"][rg], mats(r["q"], r["t"]), rtol=0, atol=1e-9)
+            rq_, rt_, rs_, const = R2.variables(); fq, ft = F2.poses()
+            assert np.allclose(rt_, ft, rtol=0, atol=1e-8) and same_quats(rq_, fq) and const[:n].all() and not const[n:].any()
+            assert [R2.L.refslam_world_setid(R2.h, w) for w in range(3)] == [F2.world_setid(w) for w in range(3)]
         finally:
             R2.close(); F2.close()
