@@ -1,7 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
 //
-// THE REFERENCE'S OWN FRONT END, single-stepped.  src/NodeDataManager.cpp, src/Worlds.cpp, src/PoseGraphSLAM.cpp and
-// src/utils/PoseManipUtils.cpp are compiled unmodified, from where they lie under /root/reference, over oracle/shim/
+// THE REFERENCE'S OWN FRONT END, single-stepped.  src/NodeDataManager.cpp, src/Worlds.cpp, src/PoseGraphSLAM.cpp, src/Composer.cpp
+// (with src/VizPoseGraph.cpp, whose publishers are inert), src/utils/PoseManipUtils.cpp, src/utils/RawFileIO.cpp and
+// src/utils/RosMarkerUtils.cpp are compiled unmodified, from where they lie under /root/reference, over oracle/shim/
 // (stand-ins for the Eigen / Ceres / roscpp / message / OpenCV names they use) into oracle/_ref/libref_frontend.so.
 // The ROS callbacks are fed messages built from plain arrays; PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_
 // optimize6DOF() runs on its own thread exactly as in keyframe_pose_graph_slam_node.cpp:475-477, with ros::Rate::sleep
