@@ -286,3 +286,11 @@ def test_explicit_graph_api_add_odometry_edge_and_add_loop_edge():
     F.add_loop_edges(g["la"], g["lb"], g["lq"], g["lt"], g["lw"])  # addLoopEdge: stored in the manager, bound as (b, a, switch)
     assert F.solve_once() and len(F.odom_terms()["u"]) == len(added)   # no derived odometry was added behind our back
     F.close()
+
+
+def test_c_abi_headers_compile_as_plain_c(tmp_path):
+    # the drop-in boundary is a C ABI: every header under include/ must be valid C99 on its own (no C++, no torch types)
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text("".join(f'#include "{os.path.basename(h)}"\n' for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))) + "int main(void) { return 0; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "hdr.o")])
