@@ -130,12 +130,13 @@ void on_solve(const ceres::Solver::Options&, ceres::Problem* P, ceres::Solver::S
   }
 }
 
-void wait_arrival(std::thread& th, long& seen) {   // until that thread is parked in its rate.sleep() again
+bool wait_arrival(std::thread& th, long& seen) {   // until that thread is parked in its rate.sleep() again; false after 120 s (a test must fail, not hang)
   ros::Gate& g = ros::gate();
   std::unique_lock<std::mutex> lk(g.m);
   ros::GateState& st = g.per_thread[th.get_id()];
-  g.cv.wait(lk, [&] { return st.arrivals > seen; });
+  if (!g.cv.wait_for(lk, std::chrono::seconds(120), [&] { return st.arrivals > seen; })) return false;
   seen = st.arrivals;
+  return true;
 }
 void give_token(std::thread& th) { ros::Gate& g = ros::gate(); std::lock_guard<std::mutex> lk(g.m); ++g.per_thread[th.get_id()].tokens; g.cv.notify_all(); }
 
@@ -212,7 +213,7 @@ int refslam_wakeup(void* h) {
     R->th = std::thread(&PoseGraphSLAM::reinit_ceres_problem_onnewloopedge_optimize6DOF, R->slam);
     R->started = true;
   } else give_token(R->th);
-  wait_arrival(R->th, R->arrivals_seen);
+  if (!wait_arrival(R->th, R->arrivals_seen)) return -1;
   return R->snaps.size() > before ? 1 : 0;
 }
 // One pass of Composer::pose_assember_thread (src/Composer.cpp:10-263), the reference's own, on its own thread; then
@@ -224,7 +225,7 @@ int refslam_compose_once(void* h, double* T16, int cap) {
     R->th_composer = std::thread(&Composer::pose_assember_thread, R->composer, 30);
     R->composer_started = true;
   } else give_token(R->th_composer);
-  wait_arrival(R->th_composer, R->composer_arrivals_seen);
+  if (!wait_arrival(R->th_composer, R->composer_arrivals_seen)) return -1;
   std::lock_guard<std::mutex> lk(R->composer->mx);
   const int n = (int)R->composer->global_lmb.size();
   for (int i = 0; i < n && i < cap; ++i) copy16(R->composer->global_lmb[i], T16 + 16 * i);

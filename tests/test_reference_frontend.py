@@ -67,7 +67,9 @@ class ReferenceNode:
         self.L.refslam_kidnap(self.h, int(stamp), int(kidnapped))
 
     def wakeup(self):
-        return self.L.refslam_wakeup(self.h) == 1
+        rc = self.L.refslam_wakeup(self.h)
+        assert rc >= 0, "the reference's solver thread did not come back to its sleep within 120 s"
+        return rc == 1
 
     def blocks(self):
         n = self.L.refslam_n_blocks(self.h)
