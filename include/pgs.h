@@ -73,6 +73,13 @@ typedef struct pgs_options {
   int32_t linear_solver;                    /* pgs_linear_solver */
   int32_t pcg_max_iterations;               /* per linear solve */
   double pcg_tolerance;                     /* relative residual ||b-Ax|| / ||b|| */
+  int32_t chains;                           /* elimination chains of the skyline solver on ONE GPU: 0 = automatic (two chains
+                                               burning from both ends of the keyframe chain from 4096 nodes on), 1 = one
+                                               natural-order chain, 2.. = that many; with pgs_dist_init: chains per rank (0 = 1) */
+  int32_t check_linear_solves;              /* != 0: measure the backward error ||b - A y|| / ||b|| of every linear solve
+                                               (one block SpMV each; pgs_get_linear_backward_errors) */
+  double max_factor_bytes;                  /* skyline factor larger than this (0 = 80 % of the free device memory) or ... */
+  double max_factor_flops;                  /* ... costlier than this per factorisation (0 = no limit): fall back to PGS_BLOCK_PCG */
 } pgs_options;
 
 /* One row of Ceres' minimizer_progress_to_stdout table. */
@@ -88,7 +95,13 @@ typedef struct pgs_summary {
   int32_t num_successful_steps, num_unsuccessful_steps, num_iterations;
   int32_t linear_solver_iterations;         /* total PCG iterations (0 for the direct solver) */
   double ms_sweep, ms_assemble, ms_linear_solve, ms_total; /* device time by phase (CUDA events) */
-  int64_t factor_nnz;                       /* scalars stored by the skyline factor (0 for PCG) */
+  int64_t factor_nnz;                       /* scalars stored by the skyline factor(s) (0 for PCG) */
+  int32_t linear_solver_used;               /* pgs_linear_solver actually used (PGS_BLOCK_PCG when the skyline estimate exceeded the budget) */
+  int32_t n_chains;                         /* elimination chains on this GPU (1 = plain natural order) */
+  double factor_flops;                      /* estimated flops of one factorisation (sum over rows of width^2) */
+  double max_linear_backward_error;         /* max over the linear solves of ||b - A y|| / ||b||; -1 when not measured */
+  double fixed_cost;                        /* Ceres Summary::fixed_cost: cost of the residual blocks whose parameter blocks are all constant */
+  double ms_comm;                           /* device time spent in collectives incl. waiting for other ranks (multi-GPU) */
 } pgs_summary;
 
 /* Sizes of the residual/Jacobian outputs of pgs_evaluate. */
@@ -159,15 +172,29 @@ typedef struct pgs_dist_stats {
   int32_t n_odom_owned, n_loop_owned, n_reg_owned;
   int64_t border_buffer_bytes;                      /* size of the per-iteration all-reduce */
   int64_t n_collectives, bytes_reduced;             /* over the last solve */
+  int32_t n_chains, n_local_border_nodes;           /* chains this rank eliminates; border nodes its factors hold */
+  int64_t factor_nnz;                               /* this rank's chain factors + its copy of the border factor */
+  double ms_comm;                                   /* this rank's time in collectives over the last solve (waiting included) */
 } pgs_dist_stats;
 int pgs_dist_unique_id(void* id128);                /* rank 0: ncclGetUniqueId; distribute the 128 bytes yourself */
 int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128);
-int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out);
+/* The same sharded solve over an in-process transport: `world` handles of ONE process (same or different devices), each
+ * driven by its own host thread, that name the same `group`.  Every collective is a host barrier plus device copies —
+ * for hosts that drive several GPUs from one process, and for running any number of ranks on a single GPU. */
+int pgs_dist_init_local(pgs_handle h, int32_t rank, int32_t world, const char* group);
+int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out);   /* also valid after a single-GPU solve that used several chains */
+/* Backward errors ||b - A y|| / ||b|| of the linear solves of the last pgs_solve (pgs_options.check_linear_solves),
+ * in the order they were done; at most cap values are written, *n gets the number available. */
+int pgs_get_linear_backward_errors(pgs_handle h, double* out, int32_t cap, int32_t* n);
 /* The partition rule on its own (host only, no device needed): node_owner[N] = owning rank or -1 for a border
- * node; *_owner = rank that evaluates each residual block.  Loop edge e couples (a[e], b[e]). */
+ * node; *_owner = rank that evaluates each residual block; cut[world+1] = the node ranges of the ranks (ranges that
+ * carry a separator through their elimination get fewer nodes); node_chain[N] = chain that eliminates the node (-1 =
+ * border), chain_down[world*chains_per_rank] = 1 where a chain runs in descending keyframe order.  Any output may be
+ * NULL.  chains_per_rank = 0: the default of pgs_options.chains.  Loop edge e couples (a[e], b[e]). */
 int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t* c1, const int32_t* c2, int32_t n_loop,
                   const int32_t* a, const int32_t* b, int32_t n_reg, const int32_t* reg_node, int32_t* node_owner,
-                  int32_t* odom_owner, int32_t* loop_owner, int32_t* reg_owner, int32_t* n_border);
+                  int32_t* odom_owner, int32_t* loop_owner, int32_t* reg_owner, int32_t* n_border,
+                  int32_t chains_per_rank, int32_t* cut, int32_t* node_chain, int32_t* chain_down, int32_t* n_chains);
 
 /* ---- measurement hooks used by bench.py ---- */
 /* Runs the residual+Jacobian sweep `reps` times with every input already resident in HBM and

@@ -38,6 +38,10 @@ class Options(C.Structure):
         ("linear_solver", C.c_int32),
         ("pcg_max_iterations", C.c_int32),
         ("pcg_tolerance", C.c_double),
+        ("chains", C.c_int32),
+        ("check_linear_solves", C.c_int32),
+        ("max_factor_bytes", C.c_double),
+        ("max_factor_flops", C.c_double),
     ]
 
 
@@ -57,6 +61,8 @@ class Summary(C.Structure):
         ("num_iterations", C.c_int32), ("linear_solver_iterations", C.c_int32),
         ("ms_sweep", C.c_double), ("ms_assemble", C.c_double), ("ms_linear_solve", C.c_double), ("ms_total", C.c_double),
         ("factor_nnz", C.c_int64),
+        ("linear_solver_used", C.c_int32), ("n_chains", C.c_int32), ("factor_flops", C.c_double),
+        ("max_linear_backward_error", C.c_double), ("fixed_cost", C.c_double), ("ms_comm", C.c_double),
     ]
 
 
@@ -67,7 +73,8 @@ class Sizes(C.Structure):
 class DistStats(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_interior_nodes", C.c_int32), ("n_border_nodes", C.c_int32),
                 ("n_odom_owned", C.c_int32), ("n_loop_owned", C.c_int32), ("n_reg_owned", C.c_int32),
-                ("border_buffer_bytes", C.c_int64), ("n_collectives", C.c_int64), ("bytes_reduced", C.c_int64)]
+                ("border_buffer_bytes", C.c_int64), ("n_collectives", C.c_int64), ("bytes_reduced", C.c_int64),
+                ("n_chains", C.c_int32), ("n_local_border_nodes", C.c_int32), ("factor_nnz", C.c_int64), ("ms_comm", C.c_double)]
 
 
 SKYLINE_CHOLESKY, BLOCK_PCG = 0, 1
@@ -122,16 +129,20 @@ def dist_unique_id():
     return bytes(buf.raw)
 
 
-def partition(n_nodes, world, oc1, oc2, la, lb, rn):
-    """Host-only view of the node-range partition rule (include/pgs.h pgs_partition)."""
+def partition(n_nodes, world, oc1, oc2, la, lb, rn, chains_per_rank=0):
+    """Host-only view of the node-range plan (include/pgs.h pgs_partition)."""
     oc1, p1 = _i(oc1); oc2, p2 = _i(oc2); la, pa = _i(la); lb, pb = _i(lb); rn, pr = _i(rn)
     node_owner = np.zeros(max(n_nodes, 1), np.int32); oo = np.zeros(max(len(oc1), 1), np.int32)
     lo = np.zeros(max(len(la), 1), np.int32); ro = np.zeros(max(len(rn), 1), np.int32); nb = C.c_int32(0)
+    cut = np.zeros(world + 1, np.int32); node_chain = np.zeros(max(n_nodes, 1), np.int32)
+    down = np.zeros(world * max(chains_per_rank, 2), np.int32); nc = C.c_int32(0)
     rc = lib().pgs_partition(C.c_int32(n_nodes), C.c_int32(world), C.c_int32(len(oc1)), p1, p2, C.c_int32(len(la)), pa, pb, C.c_int32(len(rn)), pr,
-                             node_owner.ctypes.data_as(c_ip), oo.ctypes.data_as(c_ip), lo.ctypes.data_as(c_ip), ro.ctypes.data_as(c_ip), C.byref(nb))
+                             node_owner.ctypes.data_as(c_ip), oo.ctypes.data_as(c_ip), lo.ctypes.data_as(c_ip), ro.ctypes.data_as(c_ip), C.byref(nb),
+                             C.c_int32(chains_per_rank), cut.ctypes.data_as(c_ip), node_chain.ctypes.data_as(c_ip), down.ctypes.data_as(c_ip), C.byref(nc))
     if rc != 0:
         raise PgsError(f"pgs_partition failed ({rc})")
-    return dict(node_owner=node_owner[:n_nodes], odom_owner=oo[:len(oc1)], loop_owner=lo[:len(la)], reg_owner=ro[:len(rn)], n_border=nb.value)
+    return dict(node_owner=node_owner[:n_nodes], odom_owner=oo[:len(oc1)], loop_owner=lo[:len(la)], reg_owner=ro[:len(rn)], n_border=nb.value,
+                cut=cut, node_chain=node_chain[:n_nodes], chain_down=down[:nc.value], n_chains=nc.value)
 
 
 class ComposeInput(C.Structure):
@@ -331,6 +342,15 @@ class PoseGraphSolver:
     # ---- multi-GPU
     def dist_init(self, rank, world, unique_id):
         self._ck(self.L.pgs_dist_init(self.h, C.c_int32(rank), C.c_int32(world), C.c_char_p(unique_id)))
+
+    def dist_init_local(self, rank, world, group):
+        """In-process transport: `world` handles of this process, one thread each, naming the same group."""
+        self._ck(self.L.pgs_dist_init_local(self.h, C.c_int32(rank), C.c_int32(world), C.c_char_p(group.encode())))
+
+    def linear_backward_errors(self):
+        n = C.c_int32(0); out = np.zeros(256)
+        self._ck(self.L.pgs_get_linear_backward_errors(self.h, out.ctypes.data_as(c_dp), C.c_int32(len(out)), C.byref(n)))
+        return out[: min(n.value, len(out))].copy()
 
     def dist_stats(self):
         s = DistStats(); self._ck(self.L.pgs_dist_get_stats(self.h, C.byref(s)))

@@ -29,6 +29,7 @@ int pgs_default_options(pgs_options* o) {
   o->max_num_consecutive_invalid_steps = 5; o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
   o->jacobi_scaling = 1; o->switch_init = 0.99;  // reference PoseGraphSLAM.cpp:353
   o->device = 0; o->linear_solver = PGS_SKYLINE_CHOLESKY; o->pcg_max_iterations = 20000; o->pcg_tolerance = 1e-10;
+  o->chains = 0; o->check_linear_solves = 0; o->max_factor_bytes = 0.0; o->max_factor_flops = 0.0;
   return PGS_OK;
 }
 
@@ -82,17 +83,24 @@ int pgs_dist_unique_id(void* id128) {
   return pgs::Comm::unique_id(id128, &g_create_error);
 }
 int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128) { H(h); GUARDED(h, h->s->dist_init(rank, world, id128)); }
+int pgs_dist_init_local(pgs_handle h, int32_t rank, int32_t world, const char* group) { H(h); GUARDED(h, h->s->dist_init_local(rank, world, group)); }
 int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out) { H(h); if (!out) return PGS_ERR_INVALID_ARGUMENT; return h->s->dist_stats(out); }
+int pgs_get_linear_backward_errors(pgs_handle h, double* out, int32_t cap, int32_t* n) { H(h); return h->s->get_backward_errors(out, cap, n); }
 int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t* c1, const int32_t* c2, int32_t n_loop, const int32_t* a,
                   const int32_t* b, int32_t n_reg, const int32_t* reg_node, int32_t* node_owner, int32_t* odom_owner, int32_t* loop_owner,
-                  int32_t* reg_owner, int32_t* n_border) {
+                  int32_t* reg_owner, int32_t* n_border, int32_t chains_per_rank, int32_t* cut, int32_t* node_chain, int32_t* chain_down,
+                  int32_t* n_chains) {
   if (n_nodes < 0 || world < 1 || n_odom < 0 || n_loop < 0 || n_reg < 0) return PGS_ERR_INVALID_ARGUMENT;
   if ((n_odom && (!c1 || !c2)) || (n_loop && (!a || !b)) || (n_reg && !reg_node)) return PGS_ERR_INVALID_ARGUMENT;
   for (int e = 0; e < n_odom; ++e) if (c1[e] < 0 || c1[e] >= n_nodes || c2[e] < 0 || c2[e] >= n_nodes) return PGS_ERR_INVALID_ARGUMENT;
   for (int e = 0; e < n_loop; ++e) if (a[e] < 0 || a[e] >= n_nodes || b[e] < 0 || b[e] >= n_nodes) return PGS_ERR_INVALID_ARGUMENT;
   for (int k = 0; k < n_reg; ++k) if (reg_node[k] < 0 || reg_node[k] >= n_nodes) return PGS_ERR_INVALID_ARGUMENT;
   pgs::Partition P;
-  pgs::make_partition(n_nodes, world, n_odom, c1, c2, n_loop, a, b, n_reg, reg_node, &P);
+  pgs::make_partition(n_nodes, world, n_odom, c1, c2, n_loop, a, b, n_reg, reg_node, &P, chains_per_rank);
+  if (cut) for (int k = 0; k <= world; ++k) cut[k] = P.cut[k];
+  if (node_chain) for (int i = 0; i < n_nodes; ++i) node_chain[i] = P.node_chain[i];
+  if (chain_down) for (size_t c = 0; c < P.ranges.size(); ++c) chain_down[c] = P.ranges[c].down ? 1 : 0;
+  if (n_chains) *n_chains = (int)P.ranges.size();
   if (node_owner) for (int i = 0; i < n_nodes; ++i) node_owner[i] = P.node_owner[i];
   if (odom_owner) for (int e = 0; e < n_odom; ++e) odom_owner[e] = P.odom_owner[e];
   if (loop_owner) for (int e = 0; e < n_loop; ++e) loop_owner[e] = P.loop_owner[e];

@@ -646,8 +646,8 @@ __global__ void __launch_bounds__(256) model_cost_kernel(MccArgs A) {
 
 // ------------------------------------------------------------------ K5: retraction + norms
 // cand = Plus(x, sign*d) per used node / switch.  Partials: [0]=sum (x-cand)^2, [1]=sum x^2, [2]=max |x-cand|
-// Nodes >= count_until are retracted but left out of the norms (border nodes are counted by one rank only).
-__global__ void __launch_bounds__(256) retract_kernel(int N, int count_until, int n_loop, const char* __restrict__ node_used, const double* __restrict__ pose,
+// Nodes with node_counted == 0 are retracted but left out of the norms (a border node is counted by one rank only).
+__global__ void __launch_bounds__(256) retract_kernel(int N, const char* __restrict__ node_counted, int n_loop, const char* __restrict__ node_used, const double* __restrict__ pose,
                                                       const double* __restrict__ sw, const double* __restrict__ dp, const double* __restrict__ ds,
                                                       double sign, double* __restrict__ cpose, double* __restrict__ csw,
                                                       double* __restrict__ p_diff2, double* __restrict__ p_x2, double* __restrict__ p_max) {
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(256) retract_kernel(int N, int count_until, in
       o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
     } else { o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3]; }
     o[4] = x[4] + sign * dp[6 * (size_t)i + 3]; o[5] = x[5] + sign * dp[6 * (size_t)i + 4]; o[6] = x[6] + sign * dp[6 * (size_t)i + 5];
-    const bool counted = i < count_until;
+    const bool counted = node_counted[i] != 0;
 #pragma unroll
     for (int k = 0; k < 7; ++k) { const double df = x[k] - o[k]; if (counted) { d2 += df * df; x2 += x[k] * x[k]; mx = fmax(mx, fabs(df)); } c[k] = o[k]; }
     c[7] = x[7];

@@ -65,6 +65,8 @@ struct SkylineFactor {
   double* xacc = nullptr;          // [n] backward-solve accumulator
   int* fail = nullptr; int* h_fail = nullptr;
   int* pair_hi = nullptr; int* pair_lo = nullptr; int n_pairs = 0;
+  int* node_src = nullptr; int* pair_src = nullptr;   // optional: factor node -> row of Ad / b (-1 = none), factor pair -> row of Ao
+  long long tail = 0;              // extra doubles behind the envelope (travel with it in the border all-reduce)
 };
 
 #define SK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { if (err) *err = std::string("skyline: ") + cudaGetErrorString(e__) + " at " #x; return e__ == cudaErrorMemoryAllocation ? PGS_ERR_OUT_OF_MEMORY : PGS_ERR_CUDA; } } while (0)
@@ -72,7 +74,7 @@ struct SkylineFactor {
 void skyline_destroy(SkylineFactor* f) {
   if (!f) return;
   cudaFree(f->val); cudaFree(f->ptr); cudaFree(f->start); cudaFree(f->rows_ptr); cudaFree(f->rows_idx); cudaFree(f->dinv);
-  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched);
+  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched); cudaFree(f->node_src); cudaFree(f->pair_src);
   if (f->h_fail) cudaFreeHost(f->h_fail);
   for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); if (f->ev_c[i]) cudaEventDestroy(f->ev_c[i]); }
   if (f->ev_fork) cudaEventDestroy(f->ev_fork);
@@ -86,10 +88,10 @@ int64_t skyline_nnz(const SkylineFactor* f) { return f ? f->nnz : 0; }
 int skyline_panel_width() { return PW; }
 
 SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
-                              int n_border_nodes, bool dense) {
+                              int n_border_nodes, bool dense, const int* node_src, const int* pair_src, long long tail) {
   SkylineFactor* f = new SkylineFactor();
   for (int i = 0; i < NEV; ++i) { f->ev_trsm[i] = nullptr; f->ev_rest[i] = nullptr; f->ev_c[i] = nullptr; }
-  f->N = N; f->n = 6 * N; f->D = (f->n + PW - 1) / PW; f->stream = stream; f->n_pairs = n_pairs;
+  f->N = N; f->n = 6 * N; f->D = (f->n + PW - 1) / PW; f->stream = stream; f->n_pairs = n_pairs; f->tail = tail;
   const int n = f->n, D = f->D;
   const int N_int = dense ? 0 : N - n_border_nodes;           // interior nodes come first, border nodes last
   f->D_elim = (!dense && n_border_nodes > 0) ? (6 * N_int) / PW : D;   // the caller pads the interior to a whole number of panels
@@ -124,7 +126,11 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
 
   auto bad = [&](cudaError_t e, const char* what) { if (err) *err = std::string("skyline_create: ") + cudaGetErrorString(e) + " (" + what + ", factor needs " + std::to_string((double)f->nnz * 8 / 1e9) + " GB)"; skyline_destroy(f); return (SkylineFactor*)nullptr; };
   cudaError_t e;
-  if ((e = cudaMalloc((void**)&f->val, sizeof(double) * (size_t)f->nnz)) != cudaSuccess) return bad(e, "val");
+  if ((e = cudaMalloc((void**)&f->val, sizeof(double) * (size_t)(f->nnz + f->tail))) != cudaSuccess) return bad(e, "val");
+  if (node_src) { if ((e = cudaMalloc((void**)&f->node_src, sizeof(int) * std::max(N, 1))) != cudaSuccess) return bad(e, "node_src");
+                  cudaMemcpyAsync(f->node_src, node_src, sizeof(int) * N, cudaMemcpyHostToDevice, stream); }
+  if (pair_src) { if ((e = cudaMalloc((void**)&f->pair_src, sizeof(int) * std::max(n_pairs, 1))) != cudaSuccess) return bad(e, "pair_src");
+                  cudaMemcpyAsync(f->pair_src, pair_src, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream); }
   if ((e = cudaMalloc((void**)&f->ptr, sizeof(long long) * (n + 2))) != cudaSuccess) return bad(e, "ptr");
   if ((e = cudaMalloc((void**)&f->start, sizeof(int) * (n + 1))) != cudaSuccess) return bad(e, "start");
   if ((e = cudaMalloc((void**)&f->rows_ptr, sizeof(int) * (D + 1))) != cudaSuccess) return bad(e, "rows_ptr");
@@ -160,21 +166,26 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
 
 // ------------------------------------------------------------------------------------------------ kernels
 // scatter the block system into the (zeroed) envelope: diagonal blocks (lower triangle), off-diagonal blocks, rhs row
+// node_src / pair_src (may be null = identity): the factor holds a sub-system — node i takes its diagonal block and
+// right-hand side from row node_src[i] of Ad / b (-1: none, the entries stay zero), pair p its block from row pair_src[p] of Ao.
 __global__ void sky_scatter_kernel(int N, int n_pairs, const double* __restrict__ Ad, const double* __restrict__ Ao, const double* __restrict__ b,
-                                   const int* __restrict__ pair_hi, const int* __restrict__ pair_lo, const long long* __restrict__ ptr,
+                                   const int* __restrict__ pair_hi, const int* __restrict__ pair_lo, const int* __restrict__ node_src,
+                                   const int* __restrict__ pair_src, const long long* __restrict__ ptr,
                                    const int* __restrict__ start, double* __restrict__ val) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = 6 * N;
   if (t < 36 * N) {
     const int i = t / 36, a = (t % 36) / 6, c = t % 6;
-    if (c <= a) { const int r = 6 * i + a; val[ptr[r] + (6 * i + c - start[r])] = Ad[t]; }
+    const int src = node_src ? node_src[i] : i;
+    if (c <= a && src >= 0) { const int r = 6 * i + a; val[ptr[r] + (6 * i + c - start[r])] = Ad[36 * (size_t)src + 6 * a + c]; }
   }
   if (t < 36 * n_pairs) {
     const int p = t / 36, a = (t % 36) / 6, c = t % 6;
     const int r = 6 * pair_hi[p] + a;
-    val[ptr[r] + (6 * pair_lo[p] + c - start[r])] = Ao[t];
+    const int src = pair_src ? pair_src[p] : p;
+    val[ptr[r] + (6 * pair_lo[p] + c - start[r])] = Ao[36 * (size_t)src + 6 * a + c];
   }
-  if (t < n) val[ptr[n] + t] = b[t];
+  if (t < n) { const int src = node_src ? node_src[t / 6] : t / 6; if (src >= 0) val[ptr[n] + t] = b[6 * (size_t)src + t % 6]; }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -780,37 +791,22 @@ static int set_attrs(std::string* err) {
 
 static int skyline_begin(SkylineFactor* f, std::string* err) {
   if (int rc = set_attrs(err)) return rc;
-  SK(cudaMemsetAsync(f->val, 0, sizeof(double) * (size_t)f->nnz, f->stream));
+  SK(cudaMemsetAsync(f->val, 0, sizeof(double) * (size_t)(f->nnz + f->tail), f->stream));
   SK(cudaMemsetAsync(f->xacc, 0, sizeof(double) * (size_t)std::max(f->D, 1) * PW, f->stream));
   SK(cudaMemsetAsync(f->fail, 0, sizeof(int), f->stream));
   return PGS_OK;
 }
 
-// dense (border) system given as a packed lower triangle + rhs; every row of a dense factor starts at column 0
-__global__ void sky_load_packed_kernel(int n, const long long* __restrict__ ptr, const double* __restrict__ S, const double* __restrict__ rhs,
-                                       double* __restrict__ val) {
-  const long long tot = (long long)n * (n + 1) / 2;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
-    int i = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-    while ((long long)(i + 1) * (i + 2) / 2 <= e) ++i;
-    while ((long long)i * (i + 1) / 2 > e) --i;
-    const int j = (int)(e - (long long)i * (i + 1) / 2);
-    val[ptr[i] + j] = S[e];
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) val[ptr[n] + i] = rhs[i];
-}
-int skyline_load_packed(SkylineFactor* f, const double* S_packed, const double* rhs, std::string* err) {
-  if (int rc = skyline_begin(f, err)) return rc;
-  sky_load_packed_kernel<<<592, 256, 0, f->stream>>>(f->n, f->ptr, S_packed, rhs, f->val);
-  SK(cudaGetLastError());
-  return PGS_OK;
-}
+int skyline_begin_border(SkylineFactor* f, std::string* err) { return skyline_begin(f, err); }
+double* skyline_values(SkylineFactor* f) { return f->val; }
+long long skyline_values_count(const SkylineFactor* f) { return f->nnz + f->tail; }
+double* skyline_tail(SkylineFactor* f) { return f->val + f->nnz; }
 
 // Numeric factorisation of the first D_elim panels (all of them for a single-GPU solve).
 int skyline_factor(SkylineFactor* f, const double* Ad, const double* Ao, const double* b, std::string* err) {
   if (int rc = skyline_begin(f, err)) return rc;
   const int tot = std::max(36 * std::max(f->N, f->n_pairs), f->n);
-  sky_scatter_kernel<<<(tot + 255) / 256, 256, 0, f->stream>>>(f->N, f->n_pairs, Ad, Ao, b, f->pair_hi, f->pair_lo, f->ptr, f->start, f->val);
+  sky_scatter_kernel<<<(tot + 255) / 256, 256, 0, f->stream>>>(f->N, f->n_pairs, Ad, Ao, b, f->pair_hi, f->pair_lo, f->node_src, f->pair_src, f->ptr, f->start, f->val);
   return skyline_factor_numeric(f, err);
 }
 
@@ -888,10 +884,13 @@ int skyline_factor_solve(SkylineFactor* f, const double* Ad, const double* Ao, c
   return skyline_check(f, err);
 }
 
-// ---- border access for the multi-GPU Schur scheme: the trailing (border) rows after a partial factorisation
-// out[(i*(i+1))/2 + j] = S[i][j] (packed lower triangle over the nb = n - 6*N_int border scalars), rhs[i] = forward-substituted b.
-__global__ void sky_border_get_kernel(int n, int nint, const long long* __restrict__ ptr, const int* __restrict__ start, const double* __restrict__ val,
-                                      double* __restrict__ S, double* __restrict__ rhs) {
+// ---- border access for the Schur scheme: after a partial factorisation the trailing rows of a chain factor hold
+// its contribution to the border system (dense over the nbc border scalars it holds) and to the border right-hand side.
+// They are ADDED into the border factor `dst`, whose node order is the global border order: chain border node j sits at
+// border node bmap[j] (ascending, so lower triangles map onto lower triangles).
+__global__ void sky_border_accumulate_kernel(int n, int nint, const long long* __restrict__ ptr, const int* __restrict__ start, const double* __restrict__ val,
+                                             const int* __restrict__ bmap, int dn, const long long* __restrict__ dptr, const int* __restrict__ dstart,
+                                             double* __restrict__ dval) {
   const int nb = n - nint;
   const long long tot = (long long)nb * (nb + 1) / 2;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
@@ -900,13 +899,24 @@ __global__ void sky_border_get_kernel(int n, int nint, const long long* __restri
     while ((long long)i * (i + 1) / 2 > e) --i;
     const int j = (int)(e - (long long)i * (i + 1) / 2);
     const int r = nint + i;
-    S[e] = val[ptr[r] + (nint + j - start[r])];
+    const int R = 6 * bmap[i / 6] + i % 6, Cc = 6 * bmap[j / 6] + j % 6;
+    dval[dptr[R] + (Cc - dstart[R])] += val[ptr[r] + (nint + j - start[r])];
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) rhs[i] = val[ptr[n] + nint + i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) dval[dptr[dn] + 6 * bmap[i / 6] + i % 6] += val[ptr[n] + nint + i];
 }
-int skyline_border_get(SkylineFactor* f, double* S_packed, double* rhs, std::string* err) {
+int skyline_border_accumulate(SkylineFactor* f, SkylineFactor* dst, const int* bmap_dev, cudaStream_t st, std::string* err) {
   const int nint = f->D_elim * PW;
-  sky_border_get_kernel<<<592, 256, 0, f->stream>>>(f->n, nint, f->ptr, f->start, f->val, S_packed, rhs);
+  if (f->n == nint) return PGS_OK;
+  sky_border_accumulate_kernel<<<592, 256, 0, st>>>(f->n, nint, f->ptr, f->start, f->val, bmap_dev, dst->n, dst->ptr, dst->start, dst->val);
+  SK(cudaGetLastError());
+  return PGS_OK;
+}
+__global__ void sky_add_diagonal_kernel(int n, const long long* __restrict__ ptr, const int* __restrict__ start, const double* __restrict__ add, double* __restrict__ val) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) val[ptr[r] + (r - start[r])] += add[r];
+}
+int skyline_add_diagonal(SkylineFactor* f, const double* add, std::string* err) {
+  if (f->n) sky_add_diagonal_kernel<<<(f->n + 255) / 256, 256, 0, f->stream>>>(f->n, f->ptr, f->start, add, f->val);
   SK(cudaGetLastError());
   return PGS_OK;
 }

@@ -62,8 +62,9 @@ Solver::Solver(const pgs_options& o) : opt(o) {}
 
 Solver::~Solver() {
   inner.reset();
+  release_chains();
+  if (ev_fork) cudaEventDestroy(ev_fork);
   if (sky) skyline_destroy(sky);
-  if (sky_border) skyline_destroy(sky_border);
   if (h_scal) cudaFreeHost(h_scal);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -108,7 +109,7 @@ int Solver::set_nodes(int n, const double* q, const double* t, bool append) {
   h_q.insert(h_q.end(), q, q + 4 * (size_t)n);
   h_t.insert(h_t.end(), t, t + 3 * (size_t)n);
   N = (int)(h_t.size() / 3);
-  structure_dirty = true; host_params_newer = true;
+  structure_dirty = true; inner_dirty = true; host_params_newer = true;
   return PGS_OK;
 }
 int Solver::update_nodes(int first, int n, const double* q, const double* t) {
@@ -128,11 +129,10 @@ int Solver::get_poses(int first, int n, double* q, double* t) {
 }
 int Solver::set_constant(int first, int n, int constant) {
   if (first < 0 || n < 0 || first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "set_constant_nodes: range out of bounds");
-  if (comm_owned) return fail(PGS_ERR_STATE, "set_constant_nodes: not supported on a multi-GPU handle");
   if (int rc = sync_params_to_host()) return rc;
   if ((int)h_node_const.size() < N) h_node_const.resize(N, 0);
   for (int i = first; i < first + n; ++i) h_node_const[i] = constant ? 1 : 0;
-  structure_dirty = true; host_params_newer = true;   // node_used and the pose records' flag slot are rebuilt
+  structure_dirty = true; inner_dirty = true; host_params_newer = true;   // node_used and the pose records' flag slot are rebuilt
   return PGS_OK;
 }
 int Solver::set_switches(int first, int n, const double* s) {
@@ -154,7 +154,7 @@ int Solver::add_odom(int m, const int* c1, const int* c2, const double* q, const
     if (c1[i] < 0 || c2[i] < 0 || c1[i] >= N || c2[i] >= N || c1[i] == c2[i]) return fail(PGS_ERR_INVALID_ARGUMENT, "add_odom_edges: node index out of range or c1 == c2");
   o_c1.insert(o_c1.end(), c1, c1 + m); o_c2.insert(o_c2.end(), c2, c2 + m);
   o_q.insert(o_q.end(), q, q + 4 * (size_t)m); o_t.insert(o_t.end(), t, t + 3 * (size_t)m); o_w.insert(o_w.end(), w, w + m);
-  structure_dirty = true;
+  structure_dirty = true; inner_dirty = true;
   return PGS_OK;
 }
 int Solver::add_loop(int m, const int* a, const int* b, const double* q, const double* t, const double* w) {
@@ -165,14 +165,14 @@ int Solver::add_loop(int m, const int* a, const int* b, const double* q, const d
   l_a.insert(l_a.end(), a, a + m); l_b.insert(l_b.end(), b, b + m);
   l_q.insert(l_q.end(), q, q + 4 * (size_t)m); l_t.insert(l_t.end(), t, t + 3 * (size_t)m);
   for (int i = 0; i < m; ++i) { l_w.push_back(w ? w[i] : 1.0); h_sw.push_back(opt.switch_init); }
-  structure_dirty = true; host_params_newer = true;
+  structure_dirty = true; inner_dirty = true; host_params_newer = true;
   return PGS_OK;
 }
 int Solver::set_regs(int k, const int* node, const double* q, const double* t, const double* w) {
   if (k < 0 || (k > 0 && (!node || !q || !t || !w))) return fail(PGS_ERR_INVALID_ARGUMENT, "set_regularizers: null input");
   for (int i = 0; i < k; ++i) if (node[i] < 0 || node[i] >= N) return fail(PGS_ERR_INVALID_ARGUMENT, "set_regularizers: node index out of range");
   r_node.assign(node, node + k); r_q.assign(q, q + 4 * (size_t)k); r_t.assign(t, t + 3 * (size_t)k); r_w.assign(w, w + k);
-  structure_dirty = true;   // incidence lists contain the regulariser blocks
+  structure_dirty = true; inner_dirty = true;   // incidence lists contain the regulariser blocks
   return PGS_OK;
 }
 void Solver::sizes(pgs_sizes* s) {
@@ -237,7 +237,7 @@ int Solver::finalize() {
   h_node_const.resize(std::max(N, 1), 0);
   // a block is updated (and counted in the step / gradient norms) if some residual block uses it and it is not constant:
   // Ceres' reduced program drops unused and constant parameter blocks alike
-  for (int i = 0; i < N; ++i) h_node_used[i] = inc_ptr[i + 1] > inc_ptr[i] && !h_node_const[i];
+  for (int i = 0; i < N; ++i) h_node_used[i] = (inc_ptr[i + 1] > inc_ptr[i] || (i < (int)forced_used.size() && forced_used[i])) && !h_node_const[i];
   // 3. distinct node pairs (hi, lo) and their edges (edge<<2 | kind<<1 | c1_is_hi)
   std::vector<std::pair<uint64_t, int>> keyed; keyed.reserve((size_t)Eo + El);
   auto key_of = [](int c1, int c2) { const uint64_t hi = (uint64_t)std::max(c1, c2), lo = (uint64_t)std::min(c1, c2); return (hi << 32) | lo; };
@@ -291,7 +291,17 @@ int Solver::finalize() {
   CU(d_Ad.resize((size_t)std::max(N, 1) * 36, true)); CU(d_Ao.resize((size_t)std::max(n_pairs, 1) * 36, true)); CU(d_b.resize((size_t)std::max(N, 1) * 6, true));
   CU(d_y.resize((size_t)std::max(N, 1) * 6, true)); CU(d_dp.resize((size_t)std::max(N, 1) * 6, true)); CU(d_ds.resize(std::max(El, 1), true));
   if (sky) { skyline_destroy(sky); sky = nullptr; }
-  if (sky_border) { skyline_destroy(sky_border); sky_border = nullptr; }
+  release_chains();
+  flag_ptrs_ready = false;
+  {
+    // which nodes this rank counts in the step / gradient / x norms: everything but the border nodes another rank counts
+    std::vector<char> counted(std::max(N, 1), 1);
+    const int fb = first_border >= 0 ? first_border : N;
+    for (int i = fb; i < N; ++i) counted[i] = (i - fb) < (int)border_counted.size() ? border_counted[i - fb] : 1;
+    CU(d_node_counted.upload(counted, stream));
+    std::vector<int> gp(border_gpos); if (gp.empty()) gp.push_back(0);
+    CU(d_border_gpos.upload(gp, stream));
+  }
   CU(cudaStreamSynchronize(stream));
   structure_dirty = false; host_params_newer = true; device_params_newer = false;
   return PGS_OK;
@@ -428,25 +438,143 @@ int Solver::solve_pcg(int* iters) {
   return PGS_OK;
 }
 
-int Solver::solve_skyline() {
-  const int nb_nodes = first_border >= 0 ? N - first_border : 0;
+int Solver::prepare_linear() {
+  if (use_pcg()) return PGS_OK;
+  if (!chains.empty()) return prepare_chains();
   if (!sky) {
-    sky = skyline_create(N, n_pairs, h_pair_hi.data(), h_pair_lo.data(), stream, &err, nb_nodes);
+    sky = skyline_create(N, n_pairs, h_pair_hi.data(), h_pair_lo.data(), stream, &err);
     if (!sky) return PGS_ERR_OUT_OF_MEMORY;
     factor_nnz = skyline_nnz(sky);
   }
-  if (!comm || nb_nodes == 0) return skyline_factor_solve(sky, d_Ad.p, d_Ao.p, d_b.p, d_y.p, &err);
-  // multi-GPU: eliminate the interior, exchange + solve the border system, back-substitute the interior.
-  // Pivot failures are not checked here: the flag travels with the scalar all-reduce so every rank takes the same branch.
-  if (int rc = skyline_factor(sky, d_Ad.p, d_Ao.p, d_b.p, &err)) return rc;
-  if (int rc = border_solve()) return rc;
-  return skyline_backward(sky, d_y.p, &err);
+  return PGS_OK;
+}
+
+int Solver::solve_skyline() {
+  if (int rc = prepare_linear()) return rc;
+  if (!chains.empty()) return solve_chains();
+  return skyline_factor_solve(sky, d_Ad.p, d_Ao.p, d_b.p, d_y.p, &err);
 }
 
 int Solver::solve_linear(int* iters) {
   if (iters) *iters = 0;
-  if (opt.linear_solver == PGS_BLOCK_PCG) return solve_pcg(iters);
+  if (use_pcg()) return solve_pcg(iters);
   return solve_skyline();
+}
+
+int Solver::get_backward_errors(double* out, int cap, int* n) {
+  const std::vector<double>& v = inner ? inner->backward_error : backward_error;
+  if (n) *n = (int)v.size();
+  for (int i = 0; out && i < cap && i < (int)v.size(); ++i) out[i] = v[i];
+  return PGS_OK;
+}
+
+// Envelope size and factorisation cost of the natural-order skyline, straight from the edge lists (host only):
+// row i spans [min neighbour, i], nnz = sum of the widths, flops ~ sum of the squared widths (scalars).
+void Solver::estimate_skyline(double* bytes, double* flops) const {
+  std::vector<int> nstart(std::max(N, 1));
+  for (int i = 0; i < N; ++i) nstart[i] = i;
+  auto edge = [&](int i, int j) { const int hi = std::max(i, j), lo = std::min(i, j); nstart[hi] = std::min(nstart[hi], lo); };
+  for (size_t e = 0; e < o_c1.size(); ++e) edge(o_c1[e], o_c2[e]);
+  for (size_t e = 0; e < l_a.size(); ++e) edge(l_a[e], l_b[e]);
+  const int PW = skyline_panel_width(), PN = PW / 6;
+  double nnz = 0.0, fl = 0.0;
+  for (int i = 0; i < N; ++i) {
+    const double w = (double)(((6 * i) / PW + 1) * PW - (nstart[i] / PN) * PW);
+    nnz += 6.0 * w; fl += 6.0 * w * w;
+  }
+  *bytes = nnz * sizeof(double); *flops = fl;
+}
+
+// The skyline factor is dense inside the row envelope: loop closures that reach far back make it large.  Past the
+// memory or flop budget the iterative solver takes over for this problem (pgs_summary.linear_solver_used says so).
+int Solver::choose_linear_solver() {
+  pcg_fallback = false; est_flops = 0.0;
+  if (opt.linear_solver != PGS_SKYLINE_CHOLESKY || is_inner) return PGS_OK;
+  double bytes = 0.0;
+  estimate_skyline(&bytes, &est_flops);
+  if (comm_owned) return PGS_OK;   // sharded across GPUs: every rank holds a part; no fallback there
+  double limit = opt.max_factor_bytes;
+  if (limit <= 0.0) { size_t fr = 0, tot = 0; CU(cudaMemGetInfo(&fr, &tot)); limit = 0.8 * (double)fr; }
+  if (bytes > limit || (opt.max_factor_flops > 0.0 && est_flops > opt.max_factor_flops)) pcg_fallback = true;
+  return PGS_OK;
+}
+
+// r = b - A y of the reduced block system (Ad, Ao); one thread per scalar row
+__global__ void lin_residual_kernel(int N, const double* __restrict__ Ad, const double* __restrict__ Ao, const int2* __restrict__ pair,
+                                    const int* __restrict__ adj_ptr, const int* __restrict__ adj_item, const double* __restrict__ b,
+                                    const double* __restrict__ y, double* __restrict__ r) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 6 * N) return;
+  const int i = t / 6, a = t % 6;
+  double s = b[t];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) s -= Ad[36 * (size_t)i + 6 * a + c] * y[6 * (size_t)i + c];
+  for (int q = adj_ptr[i]; q < adj_ptr[i + 1]; ++q) {
+    const int code = adj_item[q], p = code >> 1;
+    const int2 hl = pair[p];
+    if (code & 1) {   // this node is the pair's hi: block (row hi, col lo)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s -= Ao[36 * (size_t)p + 6 * a + c] * y[6 * (size_t)hl.y + c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s -= Ao[36 * (size_t)p + 6 * c + a] * y[6 * (size_t)hl.x + c];
+    }
+  }
+  r[t] = s;
+}
+// partial[blk] = sum r^2, partial[grid + blk] = sum b^2 over [0, n)
+__global__ void sumsq2_kernel(int n, const double* __restrict__ r, const double* __restrict__ b, double* __restrict__ partial) {
+  __shared__ double sm[32];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { s0 += r[i] * r[i]; s1 += b[i] * b[i]; }
+  const double t0 = block_sum(s0, sm), t1 = block_sum(s1, sm);
+  if (threadIdx.x == 0) { partial[blockIdx.x] = t0; partial[gridDim.x + blockIdx.x] = t1; }
+}
+// buf[gpos] <- r of the local border rows, buf[ng6 + gpos] <- b of the local border rows
+__global__ void border_pack_res_kernel(int nb6, int first6, const int* __restrict__ gpos, const double* __restrict__ r, const double* __restrict__ b, int ng6,
+                                       double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb6) { const int g = 6 * gpos[i / 6] + i % 6; buf[g] = r[first6 + i]; buf[ng6 + g] = b[first6 + i]; }
+}
+// the summed border rows lack the damping term: r_b -= damp * z_b
+__global__ void border_fix_res_kernel(int ng6, const double* __restrict__ damp, const double* __restrict__ zb, double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ng6) buf[i] -= damp[i] * zb[i];
+}
+
+// Backward error of the linear solve just done: ||b - A y|| / ||b|| on the reduced pose system (scaled, damped,
+// switches eliminated).  Sharded: interior rows are local; border rows are summed over the ranks first.
+int Solver::linear_residual(double* rel) {
+  const int n6 = 6 * N;
+  *rel = 0.0;
+  if (n6 == 0) return PGS_OK;
+  CU(d_pr.resize((size_t)n6));
+  lin_residual_kernel<<<cdiv(n6, 128), 128, 0, stream>>>(N, d_Ad.p, d_Ao.p, d_pair.p, d_adj_ptr.p, d_adj_item.p, d_b.p, d_y.p, d_pr.p);
+  const int fb = (!chains.empty() && first_border >= 0) ? first_border : N, int6 = 6 * fb, b6 = n6 - int6, ng6 = 6 * n_gborder;
+  const int grid = std::max(1, std::min(MAX_GRID / 2, cdiv(std::max(int6, 1), 256)));
+  double* P = d_partial.p + 2 * MAX_GRID;   // [2][grid]
+  sumsq2_kernel<<<grid, 256, 0, stream>>>(int6, d_pr.p, d_b.p, P);
+  reduce_sum_kernel<<<1, 256, 0, stream>>>(P, grid, 1.0, d_scal.p + L_RES);
+  reduce_sum_kernel<<<1, 256, 0, stream>>>(P + grid, grid, 1.0, d_scal.p + L_RES + 1);
+  if (comm) if (int rc = comm->allreduce_sum(d_scal.p + L_RES, 2, stream, &err)) return rc;
+  double rb = 0.0, bb = 0.0;
+  if (!chains.empty() && ng6 > 0) {
+    CU(d_xbuf.resize(2 * (size_t)ng6));
+    CU(cudaMemsetAsync(d_xbuf.p, 0, sizeof(double) * 2 * (size_t)ng6, stream));
+    if (b6) border_pack_res_kernel<<<cdiv(b6, 256), 256, 0, stream>>>(b6, int6, d_border_gpos.p, d_pr.p, d_b.p, ng6, d_xbuf.p);
+    if (comm) if (int rc = comm->allreduce_sum(d_xbuf.p, 2 * (size_t)ng6, stream, &err)) return rc;
+    border_fix_res_kernel<<<cdiv(ng6, 256), 256, 0, stream>>>(ng6, d_dampb.p, d_zb.p, d_xbuf.p);
+    const int g2 = std::max(1, std::min(MAX_GRID / 2, cdiv(ng6, 256)));
+    sumsq2_kernel<<<g2, 256, 0, stream>>>(ng6, d_xbuf.p, d_xbuf.p + ng6, P);
+    reduce_sum_kernel<<<1, 256, 0, stream>>>(P, g2, 1.0, d_scal.p + L_RES + 2);
+    reduce_sum_kernel<<<1, 256, 0, stream>>>(P + g2, g2, 1.0, d_scal.p + L_RES + 3);
+  }
+  CU(cudaGetLastError());
+  if (int rc = read_scalars(L_NSCAL)) return rc;
+  if (!chains.empty() && ng6 > 0) { rb = h_scal[L_RES + 2]; bb = h_scal[L_RES + 3]; }
+  const double r2 = h_scal[L_RES] + rb, b2 = h_scal[L_RES + 1] + bb;
+  *rel = b2 > 0.0 ? std::sqrt(r2 / b2) : 0.0;
+  return PGS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ public ops
@@ -629,12 +757,23 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
 // Follows Ceres 1.12-1.14 TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy.
 int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
   CU(cudaSetDevice(dev));
-  if (comm_owned) return solve_dist(sum, iters, cap);   // outer solver of a multi-GPU run
-  if (comm && opt.linear_solver != PGS_SKYLINE_CHOLESKY) return fail(PGS_ERR_INVALID_ARGUMENT, "multi-GPU solve needs the skyline Cholesky solver");
+  if (comm_owned && opt.linear_solver != PGS_SKYLINE_CHOLESKY) return fail(PGS_ERR_INVALID_ARGUMENT, "multi-GPU solve needs the skyline Cholesky solver");
+  if (!is_inner) if (int rc = choose_linear_solver()) return rc;
+  if (comm_owned || (want_chains() && !pcg_fallback)) {   // outer solver of a sharded run (several GPUs, or two chains on this one)
+    if (inner_dirty) plain_chain = false;
+    if (!plain_chain) { const int rc = solve_dist(sum, iters, cap); if (rc != PGS_PLAIN_CHAIN) return rc; }
+  }
   if (int rc = sync_params_to_device()) return rc;
-  const int count_until = (comm && !count_border && first_border >= 0) ? first_border : N;
+  const bool sharded = !chains.empty();
   border_scale_ready = false;
-  ms_sweep = ms_asm = ms_lin = 0.0;
+  ms_sweep = ms_asm = ms_lin = ms_comm = 0.0;
+  backward_error.clear();
+  {
+    // the factors are allocated up front: a rank that cannot hold its share says so before anyone waits for it
+    int prc = prepare_linear();
+    if (comm) { const int a = comm->agree(prc, stream, &err); if (a) return prc ? prc : a; }
+    else if (prc) return prc;
+  }
   cudaEvent_t t_begin, t_end; CU(cudaEventCreate(&t_begin)); CU(cudaEventCreate(&t_end));
   CU(cudaEventRecord(t_begin, stream));
   const int El = (int)l_a.size(), Eo = (int)o_c1.size(), K = (int)r_node.size();
@@ -657,9 +796,13 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     tic();
     if (int r = run_assemble()) return r;
     if (iteration == 0) if (int r = compute_scaling(true)) return r;
-    if (comm) if (int r = border_gradient_exchange()) return r;   // summed border gradient -> d_gfull, summed cost -> L_COST
+    ms_asm += toc();
+    tic();
+    if (sharded) if (int r = border_gradient_exchange()) return r;   // summed border gradient -> d_gfull, summed cost -> L_COST
+    if (comm) ms_comm += toc(); else ms_asm += toc();
+    tic();
     // |Plus(x, -g) - x| in the ambient space (Ceres' projected-gradient norms)
-    retract_kernel<<<rgrid, 256, 0, stream>>>(N, count_until, El, d_node_used.p, d_pose.p, d_sw.p, comm ? d_gfull.p : d_g.p, d_lg.p, -1.0, d_cpose.p, d_csw.p, P0, P1, P2);
+    retract_kernel<<<rgrid, 256, 0, stream>>>(N, d_node_counted.p, El, d_node_used.p, d_pose.p, d_sw.p, sharded ? d_gfull.p : d_g.p, d_lg.p, -1.0, d_cpose.p, d_csw.p, P0, P1, P2);
     reduce_sum_kernel<<<1, 256, 0, stream>>>(P0, rgrid, 1.0, d_scal.p + L_DIFF2);
     reduce_max_kernel<<<1, 256, 0, stream>>>(P2, rgrid, d_scal.p + L_MAX);
     if (cudaGetLastError() != cudaSuccess) return cuda_fail(cudaPeekAtLastError(), "eval_grad_jac");
@@ -699,6 +842,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     const int lrc = solve_linear(&lin_it);
     ms_lin += toc();
     if (lrc != PGS_OK && lrc != PGS_ERR_LINEAR_SOLVER) return lrc;
+    if (lrc == PGS_OK && opt.check_linear_solves) { double rel = 0.0; if ((rc = linear_residual(&rel))) return rc; backward_error.push_back(rel); }
     it.linear_solver_iterations = lin_it; lin_total += lin_it;
     reuse_diagonal = true;
     bool step_ok = (lrc == PGS_OK);
@@ -712,20 +856,19 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
       model_cost_kernel<<<mg, 256, 0, stream>>>(M);
       reduce_sum_kernel<<<1, 256, 0, stream>>>(P0, mg, -1.0, d_scal.p + L_MCC);
       // candidate point + its cost, queued speculatively so one read-back serves all the tests
-      retract_kernel<<<rgrid, 256, 0, stream>>>(N, count_until, El, d_node_used.p, d_pose.p, d_sw.p, d_dp.p, d_ds.p, 1.0, d_cpose.p, d_csw.p, P0, P1, P2);
+      retract_kernel<<<rgrid, 256, 0, stream>>>(N, d_node_counted.p, El, d_node_used.p, d_pose.p, d_sw.p, d_dp.p, d_ds.p, 1.0, d_cpose.p, d_csw.p, P0, P1, P2);
       reduce_sum_kernel<<<1, 256, 0, stream>>>(P0, rgrid, 1.0, d_scal.p + L_DIFF2);
       reduce_sum_kernel<<<1, 256, 0, stream>>>(P1, rgrid, 1.0, d_scal.p + L_X2);
       tic();
       if ((rc = launch_sweep(1, d_cpose.p, d_csw.p, d_scal.p + L_CCOST))) return rc;
       ms_sweep += toc();
-      if (comm) {   // model change, candidate cost, step norms and the pivot flags, summed over the ranks
-        if ((rc = dist_fail_flag())) return rc;
-        if ((rc = comm->allreduce_sum(d_scal.p + L_MCC, L_FAIL - L_MCC + 1, stream, &err))) return rc;
-      }
+      if (sharded) if ((rc = dist_fail_flag())) return rc;
+      // model change, candidate cost, step norms and the pivot flags, summed over the ranks
+      if (comm) if ((rc = comm->allreduce_sum(d_scal.p + L_MCC, L_FAIL - L_MCC + 1, stream, &err))) return rc;
       if ((rc = read_scalars(L_NSCAL))) return rc;
       mcc = h_scal[L_MCC]; cand_cost = h_scal[L_CCOST]; diff2 = h_scal[L_DIFF2]; x2 = h_scal[L_X2];
       step_ok = std::isfinite(mcc) && std::isfinite(diff2) && mcc > 0.0;
-      if (comm && h_scal[L_FAIL] != 0.0) step_ok = false;   // some rank hit a non-positive pivot
+      if (sharded && h_scal[L_FAIL] != 0.0) step_ok = false;   // some chain (of some rank) hit a non-positive pivot
     }
     it.step_is_valid = step_ok ? 1 : 0;
     if (!step_ok) {
@@ -766,7 +909,14 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     sum->initial_cost = initial_cost; sum->final_cost = x_cost; sum->termination = termination;
     sum->num_successful_steps = n_succ; sum->num_unsuccessful_steps = n_unsucc; sum->num_iterations = (int)rows.size();
     sum->linear_solver_iterations = lin_total; sum->ms_sweep = ms_sweep; sum->ms_assemble = ms_asm; sum->ms_linear_solve = ms_lin; sum->ms_total = total_ms;
-    sum->factor_nnz = factor_nnz;
+    sum->factor_nnz = use_pcg() ? 0 : factor_nnz;
+    sum->linear_solver_used = use_pcg() ? PGS_BLOCK_PCG : PGS_SKYLINE_CHOLESKY;
+    sum->n_chains = use_pcg() ? 0 : std::max<int>(1, (int)chains.size());
+    sum->factor_flops = use_pcg() ? 0.0 : est_flops;
+    sum->max_linear_backward_error = -1.0;
+    for (double e : backward_error) sum->max_linear_backward_error = std::max(sum->max_linear_backward_error, e);
+    sum->fixed_cost = 0.0;
+    sum->ms_comm = ms_comm;
   }
   for (int i = 0; iters && i < (int)rows.size() && i < cap; ++i) iters[i] = rows[i];
   return PGS_OK;

@@ -42,7 +42,8 @@ struct SkylineFactor;  // pgs_skyline.cu
 static constexpr int MAX_GRID = 2048;
 // slots of the small device/pinned scalar array.  L_MCC..L_FAIL are contiguous: the multi-GPU loop sums them
 // over the ranks with one small all-reduce
-enum { L_COST = 8, L_MCC = 9, L_DIFF2 = 10, L_X2 = 11, L_CCOST = 12, L_FAIL = 13, L_MAX = 14, L_NSCAL = 32 };
+enum { PGS_PLAIN_CHAIN = 1 };   // internal: solve_dist found nothing to split, the caller solves on its own handle
+enum { L_COST = 8, L_MCC = 9, L_DIFF2 = 10, L_X2 = 11, L_CCOST = 12, L_FAIL = 13, L_MAX = 14, L_RES = 16, L_NSCAL = 32 };
 
 class Solver {
  public:
@@ -78,10 +79,19 @@ class Solver {
   // range, loads this rank's interior + the border into an inner Solver and runs the sharded LM in it.
   int dist_init(int rank, int world, const void* nccl_id128);
   int dist_stats(pgs_dist_stats* out);
+  int get_backward_errors(double* out, int cap, int* n);
+  int dist_init_local(int rank, int world, const char* group);   // the same over the in-process transport (pgs_comm.h)
   // On the inner (per-rank) solver: set by the outer one before the first solve.
-  Comm* comm = nullptr;          // not owned; non-null switches solve() to the collective variant
+  struct ChainSpec { int off = 0, len = 0; std::vector<int> border; };   // interior = local nodes [off, off+len) in elimination order (padded to whole panels); border = local indices, ascending
+  Comm* comm = nullptr;          // not owned; non-null adds the collectives
+  bool is_inner = false;
   int first_border = -1;         // local index of the first border node (they come last); -1 = no border
-  bool count_border = true;      // exactly one rank counts the (replicated) border nodes in norms
+  std::vector<ChainSpec> chains; // the chains this rank eliminates
+  std::vector<int> border_gpos;  // per local border node: its position in the global border order
+  std::vector<char> border_counted;   // per local border node: this rank counts it in the norms and publishes its pose
+  std::vector<char> forced_used; // per local node: used by some residual block of SOME rank (Ceres' reduced program is global)
+  int n_gborder = 0;             // border nodes of the whole graph
+  std::vector<int> gborder_env;  // per global border position: first position of its row envelope in the border system
 
   std::string err;
   pgs_options opt;
@@ -100,10 +110,17 @@ class Solver {
   int solve_pcg(int* iters);
   int solve_skyline();
   int solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap);   // outer: partition, inner solve, gather
-  int border_gradient_exchange();        // inner: all-reduce of the border gradient + cost, norms of Plus(x,-g)-x
-  int border_solve();                    // inner: Schur complement exchange + redundant border solve
-  int dist_fail_flag();                  // inner: pivot flags of both factors -> d_scal[L_FAIL]
+  int solve_chains();                    // inner: concurrent chain eliminations, border system, back-substitution
+  int prepare_linear();                  // allocate the factor(s) before the LM loop (so that a failure is known up front)
+  int prepare_chains();
+  int border_gradient_exchange();        // inner: all-reduce of the border gradient + cost
+  int dist_fail_flag();                  // inner: pivot flags of all factors -> d_scal[L_FAIL]
+  bool want_chains() const;
+  bool use_pcg() const { return opt.linear_solver == PGS_BLOCK_PCG || pcg_fallback; }
+  void estimate_skyline(double* bytes, double* flops) const;
+  int choose_linear_solver();              // single GPU: split the elimination into two chains burning from both ends
   int nb6() const { return first_border >= 0 ? 6 * (N - first_border) : 0; }
+  int linear_residual(double* rel);      // ||b - A y|| / ||b|| of the reduced system just solved (backward error of the step)
   int flush_l2_now();                    // evict everything from L2 and leave no dirty lines behind
   int read_scalars(int n);               // d_scal -> h_scal (pinned), synchronises the stream
 
@@ -114,6 +131,10 @@ class Solver {
   std::vector<int> l_a, l_b; std::vector<double> l_q, l_t, l_w;
   std::vector<int> r_node; std::vector<double> r_q, r_t, r_w;
   bool structure_dirty = true, regs_dirty = true, host_params_newer = true, device_params_newer = false;
+  bool inner_dirty = true;               // outer: the inner solver of a sharded solve has to be rebuilt
+  bool pcg_fallback = false;             // the skyline estimate exceeded the budget: this problem is solved with PGS_BLOCK_PCG
+  double est_flops = 0.0;
+  bool plain_chain = false;              // outer, one GPU: the plan found nothing to split (no crossing edge / separator too large)
 
   // sorted structure (host)
   std::vector<int> perm_o, perm_l;       // sorted index -> caller index
@@ -149,7 +170,15 @@ class Solver {
   std::unique_ptr<Solver> inner;         // outer: this rank's local problem
   std::vector<int> loc2glob, loop2glob;  // outer: local node -> global node (-1 = padding), local loop -> global loop
   pgs_dist_stats dstats{};
-  DBuf<double> d_xbuf, d_gfull, d_sb, d_diagb, d_zb;   // inner: border exchange buffer, summed gradient, border scale / LM diagonal / solution
+  DBuf<double> d_xbuf, d_gfull, d_sb, d_diagb, d_zb, d_dampb;   // inner: border exchange buffer, summed gradient, border scale / LM diagonal / solution / damping
+  struct ChainState { SkylineFactor* f = nullptr; cudaStream_t st = nullptr; cudaEvent_t done = nullptr; DBuf<double> y; DBuf<int> bmap; int nb = 0, nf = 0; };
+  std::vector<ChainState> cstate;
+  cudaEvent_t ev_fork = nullptr;
+  DBuf<int> d_border_gpos; DBuf<char> d_node_counted;
+  DBuf<const int*> d_flag_ptrs; bool flag_ptrs_ready = false;
+  std::vector<double> backward_error;    // per linear solve of the last LM run: ||b - A y|| / ||b||
+  void release_chains();
+  double ms_comm = 0;
   double cur_radius = 0.0; bool cur_reuse_diag = false, border_scale_ready = false;
 
   // phase timers (ms, accumulated per solve)

@@ -1,5 +1,4 @@
-"""The drop-in demonstrated with the reference's own code (needs a GPU and oracle/_ref/libref_frontend.so; not yet run on a
-device — round 1 ended without GPU time): the reference's NodeDataManager / Worlds / PoseGraphSLAM sources run unmodified
+"""The drop-in demonstrated with the reference's own code (needs a GPU and oracle/_ref/libref_frontend.so): the reference's NodeDataManager / Worlds / PoseGraphSLAM sources run unmodified
 (tests/test_reference_frontend.py explains how) and every ceres::Solve they issue is served by libpgs.so — the product's
 raw solver C-ABI — instead of Ceres.  A second reference instance gets the same session served by the CPU oracle; after every
 wake-up the two must agree within north_star's tolerances (1e-5 m, 1e-4 rad, same switch states, cost 1e-5 relative).
@@ -47,37 +46,54 @@ def server(R, backend, log):
     return serve
 
 
-def main():
+def run_backend(backend, out_path):
+    """One reference instance per process (two in one process share the C++ runtime's unique symbols and trip over each other)."""
     g = synth.generate_config(2, n_nodes=600, n_loop=90)
     order = np.argsort(np.maximum(g["la"], g["lb"]), kind="stable")
-    nodes, logs, keep = {}, {}, []
-    for backend in ("libpgs", "oracle"):
-        R = nodes[backend] = ReferenceNode(); logs[backend] = []
-        R.L.refslam_set_solve_callback.argtypes = [C.c_void_p, C.c_void_p]; R.L.refslam_write_vars.argtypes = [C.c_void_p, dp, dp, dp]
-        cb = C.CFUNCTYPE(None)(server(R, backend, logs[backend])); keep.append(cb)
-        R.L.refslam_set_solve_callback(R.h, C.cast(cb, C.c_void_p))
-    bad = 0; epos = 0
+    R = ReferenceNode(); log = []
+    R.L.refslam_set_solve_callback.argtypes = [C.c_void_p, C.c_void_p]; R.L.refslam_write_vars.argtypes = [C.c_void_p, dp, dp, dp]
+    cb = C.CFUNCTYPE(None)(server(R, backend, log))
+    R.L.refslam_set_solve_callback(R.h, C.cast(cb, C.c_void_p))
+    res = {}; epos = 0
     try:
-        for lo in range(0, 600, 200):
+        for k, lo in enumerate(range(0, 600, 200)):
             take = []
             while epos < len(order) and max(g["la"][order[epos]], g["lb"][order[epos]]) < lo + 200:
                 take.append(order[epos]); epos += 1
             take = np.array(take, dtype=int)
-            for R in nodes.values():
-                R.add_nodes(g["stamps"][lo:lo + 200], g["q"][lo:lo + 200], g["t"][lo:lo + 200])
-                R.add_loop_edges(g["stamps"], g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
-                assert R.wakeup()
-            (qa, ta, sa, _), (qb, tb, sb, _) = nodes["libpgs"].variables(), nodes["oracle"].variables()
-            dt = np.abs(ta - tb).max(); dr = (2 * np.arccos(np.abs(np.sum(qa * qb, axis=1)).clip(0, 1))).max()
-            a, b = logs["libpgs"][-1], logs["oracle"][-1]
-            dc = abs(a["final_cost"] - b["final_cost"]) / b["final_cost"]
-            ok = dt < 1e-5 and dr < 1e-4 and np.array_equal(sa > 0.5, sb > 0.5) and dc < 1e-5 and len(a["iterations"]) == len(b["iterations"])
-            bad += not ok
-            print(f"wake-up at {lo + 200} keyframes / {epos} loop edges: dt {dt:.2e} m  drot {dr:.2e} rad  cost {a['final_cost']:.6g} vs {b['final_cost']:.6g} ({dc:.1e})  "
-                  f"iterations {len(a['iterations']) - 1}/{len(b['iterations']) - 1}  {'ok' if ok else 'MISMATCH'}")
+            R.add_nodes(g["stamps"][lo:lo + 200], g["q"][lo:lo + 200], g["t"][lo:lo + 200])
+            R.add_loop_edges(g["stamps"], g["la"][take], g["lb"][take], g["lq"][take], g["lt"][take], g["lw"][take])
+            assert R.wakeup()
+            q, t, s, _ = R.variables()
+            res.update({f"q{k}": q, f"t{k}": t, f"s{k}": s, f"cost{k}": log[-1]["final_cost"], f"iters{k}": len(log[-1]["iterations"]), f"edges{k}": epos})
     finally:
-        for R in nodes.values():
-            R.close()
+        R.close()
+    np.savez(out_path, **res)
+
+
+def main():
+    import subprocess
+    import tempfile
+    if len(sys.argv) == 3:
+        return run_backend(sys.argv[1], sys.argv[2])
+    d = tempfile.mkdtemp(prefix="refnode_")
+    out = {}
+    for backend in ("libpgs", "oracle"):
+        path = os.path.join(d, backend + ".npz")
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), backend, path], capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            print(r.stdout[-1500:] + r.stderr[-3000:]); sys.exit(2)
+        out[backend] = np.load(path)
+    a, b = out["libpgs"], out["oracle"]
+    bad = 0
+    for k in range(3):
+        dt = np.abs(a[f"t{k}"] - b[f"t{k}"]).max(); dr = (2 * np.arccos(np.abs(np.sum(a[f"q{k}"] * b[f"q{k}"], axis=1)).clip(0, 1))).max()
+        ca, cb_ = float(a[f"cost{k}"]), float(b[f"cost{k}"])
+        dc = abs(ca - cb_) / cb_
+        ok = dt < 1e-5 and dr < 1e-4 and np.array_equal(a[f"s{k}"] > 0.5, b[f"s{k}"] > 0.5) and dc < 1e-5 and int(a[f"iters{k}"]) == int(b[f"iters{k}"])
+        bad += not ok
+        print(f"wake-up at {200 * (k + 1)} keyframes / {int(a[f'edges{k}'])} loop edges: dt {dt:.2e} m  drot {dr:.2e} rad  cost {ca:.6g} vs {cb_:.6g} ({dc:.1e})  "
+              f"iterations {int(a[f'iters{k}']) - 1}/{int(b[f'iters{k}']) - 1}  {'ok' if ok else 'MISMATCH'}")
     sys.exit(1 if bad else 0)
 
 

@@ -20,7 +20,13 @@ def test_partition_rule_properties(world):
     N = g["N"]
     P = pgs.partition(N, world, g["oc1"], g["oc2"], g["la"], g["lb"], g["rn"])
     own = P["node_owner"]
-    cut = [k * N // world for k in range(world + 1)]
+    cut = list(P["cut"])
+    assert cut[0] == 0 and cut[-1] == N and all(a < b for a, b in zip(cut, cut[1:]))
+    if world >= 3:
+        # ranges between the two free ends carry a separator through their elimination: a third of the nodes (kCarryCost = 3)
+        sizes = np.diff(cut)
+        assert abs(sizes[0] - sizes[-1]) <= 1 and all(abs(3 * m - sizes[0]) <= 3 for m in sizes[1:-1])
+        assert list(P["chain_down"]) == [0] * (world - 1) + [1]      # the last range burns downwards from the free top end
     rng = np.searchsorted(cut, np.arange(N), side="right") - 1
     # interior nodes stay in their range; removing the border disconnects the ranges
     assert np.array_equal(own[own >= 0], rng[own >= 0])
@@ -45,15 +51,36 @@ def test_partition_rule_properties(world):
     assert np.array_equal(P["reg_owner"], rng[g["rn"]])
 
 
+@pytest.mark.parametrize("chains", [2, 4])
+def test_single_gpu_chain_plan(chains):
+    """One GPU, several chains: the same rule over `chains` ranges that all belong to rank 0."""
+    g = random_graph(600, 3, 150, seed=5)
+    N = g["N"]
+    P = pgs.partition(N, 1, g["oc1"], g["oc2"], g["la"], g["lb"], g["rn"], chains_per_rank=chains)
+    assert P["n_chains"] == chains and list(P["cut"]) == [0, N]
+    ch = P["node_chain"]
+    assert set(ch[ch >= 0]) == set(range(chains)) and P["n_border"] == int((ch < 0).sum()) > 0
+    assert list(P["chain_down"]) == [0] * (chains - 1) + [1]
+    # interiors of different chains are never adjacent
+    for i, j in list(zip(g["oc1"], g["oc2"])) + list(zip(g["la"], g["lb"])):
+        if ch[i] >= 0 and ch[j] >= 0:
+            assert ch[i] == ch[j]
+    assert (P["node_owner"][ch >= 0] == 0).all() and (P["odom_owner"] == 0).all()
+    if chains == 2:     # burn at both ends: two halves, nothing carried
+        first = np.nonzero(ch == 1)[0].min()
+        assert abs(first - N // 2) < 60
+
+
 def test_partition_rejects_bad_indices():
     with pytest.raises(pgs.PgsError):
         pgs.partition(10, 2, [0, 11], [1, 2], [], [], [])
 
 
-def test_border_schur_scheme_world2_gloo():
+@pytest.mark.parametrize("world,port", [(2, 29533), (3, 29534)])
+def test_border_schur_scheme_gloo(world, port):
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_cpu_worker.py")]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_cpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("dist-cpu seed") == 2, r.stdout
