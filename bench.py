@@ -11,6 +11,16 @@ loop edges, 10% outliers) — the configuration the metric is quoted on.  `value
 with all inputs resident in HBM; `e2e` = the same through the C-ABI with host buffers (poses/switches
 host->device from pinned memory, cost device->host inside the timed region).  N > 1: node-range shards, one
 process per GPU, no data-path collective (weak scaling: N x 100k nodes).  Prints ONE JSON line on rank 0.
+
+The second half of BASELINE.json's metric — LM iterations per second and the final cost — rides on the same line:
+  lm          config 3 on one GPU, reference options (10 iterations), per-phase device times, backward errors
+  lm_c2       config 2 on one GPU: the configuration the reference arm can solve on a CPU (same-box LM ratio)
+  lm_sharded  config 5 (1M nodes / 3M + 500k edges) solved by ALL N GPUs together: node-range shards, interior
+              elimination per GPU, ONE NCCL all-reduce of the border system per LM iteration (strong scaling: the
+              same graph at N = 1, 2, 4, 8; at N = 1 two elimination chains on the one GPU), with the difference to
+              the single-GPU solution at N > 1
+  e2e_trigger the plugin call a host makes: keyframes + loop edges in host memory -> pgs_facade_solve_once -> poses
+The reference arm prints the matching `lm` (oracle LM, config 2) and `e2e_trigger` (oracle front end + LM, config 2).
 """
 import argparse
 import json
@@ -166,12 +176,35 @@ def run_reference(args):
         P.time_sweep(autodiff=True, threads=threads, reps=1)
     dt = (time.perf_counter() - t0) / args.steps
     v = E / dt
+    lm = trig = None
+    if not args.no_lm:
+        # the LM half of the metric: the oracle's restatement of ceres::Solve (TrustRegionMinimizer + LM strategy +
+        # sparse Cholesky as a natural-order skyline LDL^T, scalar code, 1 thread) on config 2 — config 3 is out of a
+        # CPU port's reach in a bench run.  NOT Ceres + CHOLMOD: a supernodal CHOLMOD would be several times faster.
+        from oracle import frontend
+        from solve_keyframe_pose_graph_b200 import synth
+        g2 = synth.generate_config(2)
+        t1 = time.perf_counter()
+        M = frontend.Manager(); M.ingest(g2)
+        R = frontend.ReferenceFrontEnd(M, odom_fanout=3)
+        R.trigger(solve=False)
+        P2 = R.problem()
+        t_front = time.perf_counter() - t1
+        t1 = time.perf_counter(); s2 = P2.solve(); t_lm = time.perf_counter() - t1
+        n_it = max(1, len(s2["iterations"]) - 1)
+        lm = {"config": 2, "what": "oracle LM (Ceres 1.12-1.14 trust-region semantics restated; natural-order skyline LDL^T, scalar, 1 thread)",
+              "iterations": n_it, "termination": s2["termination"], "initial_cost": s2["initial_cost"], "final_cost": s2["final_cost"],
+              "ms_total": t_lm * 1e3, "ms_per_iter": t_lm * 1e3 / n_it, "lm_iters_per_s": n_it / t_lm, "cores": 1}
+        trig = {"config": 2, "what": "oracle front end (graph construction rules in Python) + oracle LM: host graph in -> poses out",
+                "ms_total": (t_front + t_lm) * 1e3, "ms_front_end": t_front * 1e3, "ms_solve": t_lm * 1e3}
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(args.config, p, 1), "sample": "one full sweep of the workload per step"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                             "sample": "full config-3 sweep (Jet autodiff functors) per step, all host threads"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if lm:
+        out["lm"] = lm; out["e2e_trigger"] = trig
     print(json.dumps(out), flush=True)
 
 
@@ -186,6 +219,83 @@ def cpu_model():
     return "unknown"
 
 
+def run_sharded(args, rank, local_rank, world, dist, torch, barrier, lm_record):
+    """The north-star multi-GPU path: BASELINE config 5 solved by all N GPUs together (strong scaling).  Every rank loads the
+    same graph through the C-ABI, attaches the NCCL communicator (pgs_dist_init) and calls pgs_solve: node-range shards,
+    interior elimination per GPU, one all-reduce of the border system per LM iteration.  N = 1: the same graph on one GPU
+    (two elimination chains).  Also times the sweep at this size (2.57 GB per launch, 20x the L2) for the roofline."""
+    import solve_keyframe_pose_graph_b200 as pgs
+    from solve_keyframe_pose_graph_b200 import problems
+    out = {}
+    try:
+        over = {}
+        if args.sharded_nodes:
+            over = dict(n_nodes=args.sharded_nodes, n_loop=args.sharded_nodes // 2)
+        p = problems.build_problem(5, **over)
+        out["workload"] = workload_name(5, p, world)
+        S = problems.load_into_solver(p, device=local_rank)
+        if world > 1:
+            ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                ident = torch.frombuffer(bytearray(pgs.dist_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(ident, 0)
+            S.dist_init(rank, world, bytes(ident.cpu().numpy().tobytes()))
+        barrier()
+        t0 = time.perf_counter(); s = S.solve(); wall = time.perf_counter() - t0
+        st = S.dist_stats() if (world > 1 or s["n_chains"] > 1) else {}
+        mine = dict(rank=rank, ms_total=s["ms_total"], ms_linear_solve=s["ms_linear_solve"], ms_sweep=s["ms_sweep"], ms_assemble=s["ms_assemble"], ms_comm=s["ms_comm"],
+                    factor_nnz=int(st.get("factor_nnz", s["factor_nnz"])), n_interior_nodes=int(st.get("n_interior_nodes", p["N"])),
+                    n_local_border_nodes=int(st.get("n_local_border_nodes", 0)), n_collectives=int(st.get("n_collectives", 0)), bytes_reduced=int(st.get("bytes_reduced", 0)))
+        per_rank = [mine]
+        tmax = torch.tensor([s["ms_total"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, mine)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        qd, td = S.poses(); swd = S.switches()
+        rec = lm_record(p, S, s)
+        n_it = rec["iterations"]
+        rec.update({"scaling": "strong", "n_gpus": world, "ms_total": float(tmax.item()), "ms_per_iter": float(tmax.item()) / n_it,
+                    "lm_iters_per_s": n_it / (float(tmax.item()) * 1e-3), "wall_s_rank0": wall,
+                    "border_nodes": int(st.get("n_border_nodes", 0)), "border_buffer_bytes": int(st.get("border_buffer_bytes", 0)),
+                    "n_collectives": int(st.get("n_collectives", 0)), "collective": ("ncclAllReduce(sum, f64) of the border system, once per linear solve" if world > 1 else "none (one GPU)"),
+                    "ranks": per_rank})
+        out.update(rec)
+        S.close()
+        if world == 1:
+            # roofline of the sweep at a working set far beyond the L2
+            S = problems.load_into_solver(p, device=local_rank)
+            bytes5 = S.sweep_bytes()
+            S.time_sweep(mode=0, reps=3, flush_l2=False)
+            _, msk, _ = S.time_sweep(mode=0, reps=max(5, min(args.steps, 20)), flush_l2=False)
+            peak, peak_src = measured_peak_gbs()
+            out["roofline_large"] = {"bound": "hbm", "kernel": "sweep_kernel<0>", "workload": out["workload"], "achieved": bytes5 / (msk * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": bytes5 / (msk * 1e-3) / 1e9 / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes5), "kernel_ms": msk,
+                                     "l2": "no flush needed: one launch moves 20x the L2 capacity", "traffic": None}
+            prof = os.path.join(ROOT, "profiles", "r02_sweep_traffic_c5.json")
+            if os.path.exists(prof):
+                tr = json.load(open(prof))
+                if int(tr.get("algorithmic_bytes_per_launch", -1)) == int(bytes5):
+                    out["roofline_large"]["traffic"] = tr.get("dram_bytes_per_launch")
+                    out["roofline_large"]["traffic_source"] = "profiles/r02_sweep_traffic_c5.json (ncu --set full capture, not measured in this run)"
+            S.close()
+        if world > 1 and rank == 0 and not args.no_single:
+            T = problems.load_into_solver(p, device=local_rank)
+            s1 = T.solve(); q1, t1 = T.poses(); sw1 = T.switches(); T.close()
+            out["single_gpu"] = {"ms_total": s1["ms_total"], "final_cost": s1["final_cost"], "n_chains": s1["n_chains"], "factor_nnz": s1["factor_nnz"]}
+            out["dist_vs_single"] = {"max_dt_m": float(np.abs(td - t1).max()),
+                                     "max_drot_rad": float((2 * np.arccos(np.abs(np.sum(qd * q1, axis=1)).clip(0, 1))).max()),
+                                     "max_dswitch": float(np.abs(swd - sw1).max()), "switch_states_equal": bool(np.array_equal(swd > 0.5, sw1 > 0.5)),
+                                     "rel_cost": abs(s["final_cost"] - s1["final_cost"]) / max(s1["final_cost"], 1e-300),
+                                     "same_trajectory": [r["step_is_successful"] for r in s["iterations"]] == [r["step_is_successful"] for r in s1["iterations"]],
+                                     "speedup_vs_single_gpu": s1["ms_total"] / float(tmax.item())}
+        if world > 1:
+            barrier()
+    except Exception as ex:
+        out["error"] = repr(ex)[:400]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +305,9 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-lm", action="store_true", help="skip the (reported, untimed-in-value) LM solve section")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the config-5 LM solve over all GPUs")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: do not solve config 5 on one GPU as well for the comparison")
+    ap.add_argument("--sharded-nodes", type=int, default=0, help="override config 5's node count (loop edges scale along); for quick runs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,21 +364,60 @@ def main():
     ms_step_max, ms_kernel_max, e2e_ms_max, ms_warm_max = [float(x) for x in tt.tolist()]
 
     extra = {}
+    S.close(); S = None   # the sections below need the memory (config 5 on one GPU holds a 130 GB factor)
+
+    def lm_record(p, T, s, t_wall=None):
+        n_it = max(1, len(s["iterations"]) - 1)
+        be = T.linear_backward_errors()
+        return {"workload": workload_name(p["config"], p, 1), "linear_solver": "skyline_cholesky" if s["linear_solver_used"] == 0 else "block_pcg",
+                "options": "reference (max_num_iterations=10, Ceres defaults)", "iterations": n_it, "termination": s["termination"],
+                "initial_cost": s["initial_cost"], "final_cost": s["final_cost"], "lm_iters_per_s": n_it / (s["ms_total"] * 1e-3), "ms_total": s["ms_total"],
+                "ms_per_iter": s["ms_total"] / n_it, "ms_sweep": s["ms_sweep"], "ms_assemble": s["ms_assemble"], "ms_linear_solve": s["ms_linear_solve"],
+                "ms_comm": s["ms_comm"], "factor_nnz": s["factor_nnz"], "factor_flops_est": s["factor_flops"], "n_chains": s["n_chains"],
+                "linear_backward_error": {"max": float(be.max()) if len(be) else None, "per_solve": [float(x) for x in be], "what": "||b - A y|| / ||b|| of every linear solve (reduced, scaled, damped pose system)"},
+                "costs": [r["cost"] for r in s["iterations"]], "accepted": [int(r["step_is_successful"]) for r in s["iterations"]],
+                "switches_off": int((T.switches() < 0.5).sum()), "outliers": int(p["lout"].sum())}
+
     if rank == 0 and not args.no_lm and world == 1:
         # LM iterations/s and final cost (second half of BASELINE.json's metric), reference options
         try:
-            T = problems.load_into_solver(shard, device=local_rank, linear_solver=pgs.capi.SKYLINE_CHOLESKY)
+            T = problems.load_into_solver(shard, device=local_rank)
+            T.solve()                                                 # warm-up: allocations, first-touch of the factor
+            q0, t0 = shard["q"], shard["t"]
+            T.update_nodes(0, q0, t0); T.set_switches(np.full(len(shard["la"]), 0.99))
             s = T.solve()
-            n_it = max(1, len(s["iterations"]) - 1)
-            extra["lm"] = {"linear_solver": "skyline_cholesky", "options": "reference (max_num_iterations=10, Ceres defaults)", "iterations": n_it,
-                           "termination": s["termination"], "initial_cost": s["initial_cost"],
-                           "final_cost": s["final_cost"], "lm_iters_per_s": n_it / (s["ms_total"] * 1e-3), "ms_total": s["ms_total"],
-                           "ms_sweep": s["ms_sweep"], "ms_assemble": s["ms_assemble"], "ms_linear_solve": s["ms_linear_solve"],
-                           "factor_nnz": s["factor_nnz"],
-                           "switches_off": int((T.switches() < 0.5).sum()), "outliers": int(shard["lout"].sum())}
+            extra["lm"] = lm_record(shard, T, s)
+            T.close()
+            p2 = problems.build_problem(2)
+            T = problems.load_into_solver(p2, device=local_rank)
+            T.solve(); T.update_nodes(0, p2["q"], p2["t"]); T.set_switches(np.full(len(p2["la"]), 0.99))
+            extra["lm_c2"] = lm_record(p2, T, T.solve())
             T.close()
         except Exception as ex:   # the headline number must not die with the extra section
-            extra["lm"] = {"error": str(ex)[:200]}
+            extra["lm"] = {"error": str(ex)[:300]}
+        try:
+            extra["e2e_trigger"] = {}
+            from solve_keyframe_pose_graph_b200 import facade, synth
+            for cfg in (2, 3):
+                g = synth.generate_config(cfg)
+                ms = []
+                for rep in range(2):   # second repetition: allocations warm, as in a long-running node
+                    F = facade.Facade(odom_fanout=3, device=local_rank)
+                    F.ingest(g)
+                    t1 = time.perf_counter(); ok = F.solve_once(); qf, tf = F.poses(); ms.append((time.perf_counter() - t1) * 1e3)
+                    summ = F.summary(); F.close()
+                extra["e2e_trigger"][f"config{cfg}"] = {"ms_total": ms[-1], "ms_first_call": ms[0], "ms_solve_device": summ["ms_total"], "triggered": bool(ok),
+                                                         "final_cost": summ["final_cost"], "iterations": max(1, summ["num_iterations"] - 1),
+                                                         "h2d_bytes": int(56 * g["N"]), "d2h_bytes": int(56 * g["N"] + 8 * len(g["la"]))}
+            extra["e2e_trigger"]["api"] = ("pgs_facade_add_nodes / add_loop_edges (host graph) -> pgs_facade_solve_once (graph-construction rules on the host, "
+                                           "problem upload, LM on the device) -> pgs_facade_get_poses; wall clock around solve_once + get_poses")
+        except Exception as ex:
+            extra["e2e_trigger"] = {"error": str(ex)[:300]}
+
+    if not args.no_lm and not args.no_sharded:
+        extra_sh = run_sharded(args, rank, local_rank, world, dist if world > 1 else None, torch, barrier, lm_record)
+        if rank == 0:
+            extra["lm_sharded"] = extra_sh
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -301,15 +453,19 @@ def main():
             "value_warm_l2": E_total / (ms_warm_max * 1e-3), "cost": cost,
             "clocks": clocks, "cpu_baseline": cpu,
         }
-        prof = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
+        # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of THIS
+        # kernel on THIS workload; it is not measured in the run, so it is only attached where the capture applies
+        prof = os.path.join(ROOT, "profiles", "r02_sweep_traffic.json")
         if os.path.exists(prof):
             try:
-                out["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                tr = json.load(open(prof))
+                if int(tr.get("algorithmic_bytes_per_launch", -1)) == int(bytes_local):
+                    out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+                    out["roofline"]["traffic_source"] = "profiles/r02_sweep_traffic.json (ncu --set full capture of this kernel on this workload, not measured in this run)"
             except Exception:
                 pass
         out.update(extra)
         print(json.dumps(out), flush=True)
-    S.close()
     if world > 1:
         dist.destroy_process_group()
 

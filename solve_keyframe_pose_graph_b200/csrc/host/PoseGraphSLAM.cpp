@@ -155,7 +155,7 @@ bool PoseGraphSLAM::solve_once(bool force) {
   // trigger only on new loop edges, never while kidnapped (PoseGraphSLAM.cpp:1306-1319)
   bool explicit_pending;
   { std::lock_guard<std::mutex> lk(mutex_pending_); explicit_pending = !pending_explicit_odom_.empty(); }
-  if (!force && prev_loopedge_len == loopedge_len && !explicit_pending) { status = 0; return false; }
+  if (!force && prev_loopedge_len == loopedge_len && !explicit_pending && !retry_pending_) { status = 0; return false; }
   if (manager->curr_kidnap_status()) { status = 0; return false; }
   if (node_len == 0) { status = 0; return false; }
   status = 1;
@@ -166,13 +166,13 @@ bool PoseGraphSLAM::solve_once(bool force) {
   for (int yp = n_opt_switch(); yp < loopedge_len; ++yp) allocate_and_append_new_edge_switch_var();
 
   // -1/2- loop edges, intra and inter world   [:1381-1559]
-  std::vector<int> new_la, new_lb; std::vector<double> new_lq, new_lt, new_lw;
   loop_slot_.resize(loopedge_len, -1);
-  for (int e = prev_loopedge_len; e < loopedge_len; ++e) {
+  for (int e = loops_taken_until_; e < loopedge_len; ++e) {
     const Matrix4d bTa = manager->getEdgePose(e);
     const double weight = manager->getEdgeWeight(e);
     const std::pair<int, int> paur = manager->getEdgeIdxInfo(e);
     const int _a = paur.first, _b = paur.second;
+    if (_a == _b) continue;                     // both stamps resolved to the same keyframe: no constraint, no block
     const int a_world = manager->which_world_is_this(manager->getNodeTimestamp(_a));
     const int b_world = manager->which_world_is_this(manager->getNodeTimestamp(_b));
     if (a_world < 0 || b_world < 0) continue;   // an endpoint lies in a dead zone; its switch slot stays unused
@@ -193,16 +193,18 @@ bool PoseGraphSLAM::solve_once(bool force) {
     }
     double q[4], t[3];
     mat_to_raw_xyzw(bTa, q, t);
-    loop_slot_[e] = n_device_loops_ + (int)new_la.size();
-    new_la.push_back(_a); new_lb.push_back(_b);
-    new_lq.insert(new_lq.end(), q, q + 4); new_lt.insert(new_lt.end(), t, t + 3); new_lw.push_back(weight);
+    loop_slot_[e] = (int)loop_a_.size();
+    loop_a_.push_back(_a); loop_b_.push_back(_b);
+    loop_q_.insert(loop_q_.end(), q, q + 4); loop_t_.insert(loop_t_.end(), t, t + 3); loop_w_.push_back(weight);
     { std::lock_guard<std::mutex> lk(mutex_residue_info); loop_edges_terms.push_back(std::make_tuple(_a, _b, (float)weight, std::string(""), std::string(""))); }
   }
+
+  loops_taken_until_ = loopedge_len;
 
   // -3- odometry edges u <-> u-f for u in (solvedUntil, node_len)   [:1570-1639]
   std::vector<OdomTerm> new_odom;
   if (opt_.derive_odometry) {
-    for (int u = solvedUntil() + 1; u < node_len; ++u) {
+    for (int u = std::max(solvedUntil(), odom_added_until_) + 1; u < node_len; ++u) {
       const int world_of_u = manager->which_world_is_this(manager->getNodeTimestamp(u));
       const int set_u = worlds->find_setID_of_world_i(world_of_u);
       for (int f = 1; f <= opt_.odom_fanout; ++f) {
@@ -231,6 +233,8 @@ bool PoseGraphSLAM::solve_once(bool force) {
     for (const OdomTerm& o : new_odom) odometry_edges_terms.push_back(std::make_tuple(o.u, o.umf, (float)o.weight, std::string("")));
   }
   odom_terms_.insert(odom_terms_.end(), new_odom.begin(), new_odom.end());
+  if (opt_.derive_odometry) odom_added_until_ = std::max(odom_added_until_, node_len - 1);
+  retry_pending_ = true;   // cleared when the solve below has gone through
 
   // -4- initial guesses for every node   [:1649-1793]
   {
@@ -296,14 +300,27 @@ bool PoseGraphSLAM::solve_once(bool force) {
     std::vector<double> q, t;
     { std::lock_guard<std::mutex> lk(mutex_opt_vars); q = _opt_quat_; t = _opt_t_; }
     int rc = PGS_OK;
-    if (node_len > n_device_nodes_) rc = pgs_append_nodes(handle_, node_len - n_device_nodes_, &q[4 * (size_t)n_device_nodes_], &t[3 * (size_t)n_device_nodes_]);
+    // every counter moves as soon as its call has succeeded: what a failed trigger already put on the device is not sent again
+    if (node_len > n_device_nodes_) {
+      rc = pgs_append_nodes(handle_, node_len - n_device_nodes_, &q[4 * (size_t)n_device_nodes_], &t[3 * (size_t)n_device_nodes_]);
+      if (rc == PGS_OK) n_device_nodes_ = node_len;
+    }
     if (rc == PGS_OK) rc = pgs_update_nodes(handle_, 0, node_len, q.data(), t.data());
-    if (rc == PGS_OK && n_constant_ > n_constant_on_device_) { rc = pgs_set_constant_nodes(handle_, 0, n_constant_, 1); n_constant_on_device_ = n_constant_; }
-    if (rc == PGS_OK && !new_la.empty()) rc = pgs_add_loop_edges(handle_, (int)new_la.size(), new_la.data(), new_lb.data(), new_lq.data(), new_lt.data(), new_lw.data());
-    if (rc == PGS_OK && !new_odom.empty()) {
+    if (rc == PGS_OK && n_constant_ > n_constant_on_device_) { rc = pgs_set_constant_nodes(handle_, 0, n_constant_, 1); if (rc == PGS_OK) n_constant_on_device_ = n_constant_; }
+    const int n_loops = (int)loop_a_.size();
+    if (rc == PGS_OK && n_loops > n_device_loops_) {
+      const size_t f = (size_t)n_device_loops_;
+      rc = pgs_add_loop_edges(handle_, n_loops - n_device_loops_, &loop_a_[f], &loop_b_[f], &loop_q_[4 * f], &loop_t_[3 * f], &loop_w_[f]);
+      if (rc == PGS_OK) n_device_loops_ = n_loops;
+    }
+    if (rc == PGS_OK && (int)odom_terms_.size() > n_device_odom_) {
       std::vector<int> c1, c2; std::vector<double> oq, ot, ow;
-      for (const OdomTerm& o : new_odom) { c1.push_back(o.u); c2.push_back(o.umf); oq.insert(oq.end(), o.q, o.q + 4); ot.insert(ot.end(), o.t, o.t + 3); ow.push_back(o.weight); }
+      for (size_t k = (size_t)n_device_odom_; k < odom_terms_.size(); ++k) {
+        const OdomTerm& o = odom_terms_[k];
+        c1.push_back(o.u); c2.push_back(o.umf); oq.insert(oq.end(), o.q, o.q + 4); ot.insert(ot.end(), o.t, o.t + 3); ow.push_back(o.weight);
+      }
       rc = pgs_add_odom_edges(handle_, (int)c1.size(), c1.data(), c2.data(), oq.data(), ot.data(), ow.data());
+      if (rc == PGS_OK) n_device_odom_ = (int)odom_terms_.size();
     }
     if (rc == PGS_OK) {
       std::vector<int> rn; std::vector<double> rq, rt, rw;
@@ -311,7 +328,6 @@ bool PoseGraphSLAM::solve_once(bool force) {
       rc = pgs_set_regularizers(handle_, (int)rn.size(), rn.data(), rq.data(), rt.data(), rw.data());
     }
     if (rc != PGS_OK) return fail(std::string("device problem update: ") + pgs_last_error(handle_));
-    n_device_nodes_ = node_len; n_device_loops_ += (int)new_la.size();
 
     status = 2;
     pgs_summary sum{};
@@ -332,8 +348,9 @@ bool PoseGraphSLAM::solve_once(bool force) {
       for (int e = 0; e < loopedge_len; ++e) if (loop_slot_[e] >= 0) _opt_switch_[e] = sw[loop_slot_[e]];
     }
   } else {
-    n_device_loops_ += (int)new_la.size();
+    n_device_loops_ = (int)loop_a_.size();
   }
+  retry_pending_ = false;
   { std::lock_guard<std::mutex> lk(mutex_opt_vars); solved_until = node_len - 1; }   // unconditionally [:1908]
   status = 3;
   prev_loopedge_len = loopedge_len;

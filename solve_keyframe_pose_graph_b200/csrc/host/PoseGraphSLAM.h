@@ -131,7 +131,13 @@ class PoseGraphSLAM {
   mutable std::mutex mutex_pending_;          // addOdometryEdge may run on the ingest thread while the solver thread drains the list
   std::vector<OdomTerm> pending_explicit_odom_;
   std::vector<int> loop_slot_;       // manager loop-edge index -> device loop-edge index (-1: skipped, dead zone)
-  int n_device_nodes_ = 0, n_device_loops_ = 0;
+  int n_device_nodes_ = 0, n_device_loops_ = 0, n_device_odom_ = 0;   // how much of the lists below the device already holds
+  // Loop-closure blocks in device (slot) order.  The block lists only ever grow, and the device is brought up to them at the
+  // start of every solve, so a trigger whose device update or solve fails adds nothing twice when it is tried again.
+  std::vector<int> loop_a_, loop_b_; std::vector<double> loop_q_, loop_t_, loop_w_;
+  int loops_taken_until_ = 0;        // manager loop edges already turned into blocks
+  int odom_added_until_ = 0;         // keyframes whose odometry blocks exist (== solvedUntil() after a successful solve)
+  bool retry_pending_ = false;       // the last trigger built its blocks but the device failed: the next wake-up solves again
   int odom_scanned_until_ = 0;       // odometry edges exist for u <= this
   int n_constant_ = 0;               // variables [0, n_constant_) are constant blocks (load_state)
   int n_constant_on_device_ = 0;

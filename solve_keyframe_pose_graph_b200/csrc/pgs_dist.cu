@@ -269,7 +269,7 @@ int Solver::solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap) {
     Partition P;
     make_partition(N, world, Eo, o_c1.data(), o_c2.data(), El, l_a.data(), l_b.data(), K, r_node.data(), &P, opt.chains);
     const int R = (int)P.ranges.size();
-    if (world == 1 && (R < 2 || P.border.empty() || (int)P.border.size() > N / 4)) {
+    if (world == 1 && (R < 2 || P.border.empty() || (opt.chains == 0 && (int)P.border.size() > N / 4))) {
       // nothing to gain: one natural-order chain on this handle (no edge crosses the cut, or the separator is a
       // large part of the graph — loop closures that span most of the trajectory)
       inner.reset(); plain_chain = true; inner_dirty = false;

@@ -68,6 +68,8 @@ Solver::~Solver() {
   if (h_scal) cudaFreeHost(h_scal);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (ev_t0) cudaEventDestroy(ev_t0);
+  if (ev_t1) cudaEventDestroy(ev_t1);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -86,7 +88,7 @@ int Solver::init() {
   dev = opt.device;
   CU(cudaSetDevice(dev));
   CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+  CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1)); CU(cudaEventCreate(&ev_t0)); CU(cudaEventCreate(&ev_t1));
   CU(cudaMallocHost((void**)&h_scal, sizeof(double) * L_NSCAL));
   CU(d_scal.resize(L_NSCAL, true));
   CU(d_partial.resize(4 * MAX_GRID, true));
@@ -104,6 +106,12 @@ double Solver::toc() { cudaEventRecord(ev1, stream); cudaEventSynchronize(ev1); 
 // ------------------------------------------------------------------------------------------------ problem construction
 int Solver::set_nodes(int n, const double* q, const double* t, bool append) {
   if (n < 0 || (n > 0 && (!q || !t))) return fail(PGS_ERR_INVALID_ARGUMENT, "set_nodes: null input");
+  if (!append && n < N) {
+    // replacing the node set by a smaller one must not leave residual blocks pointing past its end
+    auto past = [n](const std::vector<int>& v) { for (int x : v) if (x >= n) return true; return false; };
+    if (past(o_c1) || past(o_c2) || past(l_a) || past(l_b) || past(r_node))
+      return fail(PGS_ERR_STATE, "set_nodes: existing residual blocks reference nodes beyond the new node count");
+  }
   if (int rc = sync_params_to_host()) return rc;
   if (!append) { h_q.clear(); h_t.clear(); h_node_const.clear(); }
   h_q.insert(h_q.end(), q, q + 4 * (size_t)n);
@@ -113,7 +121,8 @@ int Solver::set_nodes(int n, const double* q, const double* t, bool append) {
   return PGS_OK;
 }
 int Solver::update_nodes(int first, int n, const double* q, const double* t) {
-  if (first < 0 || n < 0 || first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "update_nodes: range out of bounds");
+  if (first < 0 || n < 0 || (int64_t)first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "update_nodes: range out of bounds");
+  if (n > 0 && (!q || !t)) return fail(PGS_ERR_INVALID_ARGUMENT, "update_nodes: null input");
   if (int rc = sync_params_to_host()) return rc;
   std::memcpy(&h_q[4 * (size_t)first], q, sizeof(double) * 4 * n);
   std::memcpy(&h_t[3 * (size_t)first], t, sizeof(double) * 3 * n);
@@ -121,14 +130,14 @@ int Solver::update_nodes(int first, int n, const double* q, const double* t) {
   return PGS_OK;
 }
 int Solver::get_poses(int first, int n, double* q, double* t) {
-  if (first < 0 || n < 0 || first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "get_poses: range out of bounds");
+  if (first < 0 || n < 0 || (int64_t)first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "get_poses: range out of bounds");
   if (int rc = sync_params_to_host()) return rc;
   if (q) std::memcpy(q, &h_q[4 * (size_t)first], sizeof(double) * 4 * n);
   if (t) std::memcpy(t, &h_t[3 * (size_t)first], sizeof(double) * 3 * n);
   return PGS_OK;
 }
 int Solver::set_constant(int first, int n, int constant) {
-  if (first < 0 || n < 0 || first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "set_constant_nodes: range out of bounds");
+  if (first < 0 || n < 0 || (int64_t)first + n > N) return fail(PGS_ERR_INVALID_ARGUMENT, "set_constant_nodes: range out of bounds");
   if (int rc = sync_params_to_host()) return rc;
   if ((int)h_node_const.size() < N) h_node_const.resize(N, 0);
   for (int i = first; i < first + n; ++i) h_node_const[i] = constant ? 1 : 0;
@@ -136,14 +145,16 @@ int Solver::set_constant(int first, int n, int constant) {
   return PGS_OK;
 }
 int Solver::set_switches(int first, int n, const double* s) {
-  if (first < 0 || n < 0 || first + n > (int)h_sw.size()) return fail(PGS_ERR_INVALID_ARGUMENT, "set_switches: range out of bounds");
+  if (first < 0 || n < 0 || (int64_t)first + n > (int64_t)h_sw.size()) return fail(PGS_ERR_INVALID_ARGUMENT, "set_switches: range out of bounds");
+  if (n > 0 && !s) return fail(PGS_ERR_INVALID_ARGUMENT, "set_switches: null input");
   if (int rc = sync_params_to_host()) return rc;
   std::memcpy(&h_sw[first], s, sizeof(double) * n);
   host_params_newer = true;
   return PGS_OK;
 }
 int Solver::get_switches(int first, int n, double* s) {
-  if (first < 0 || n < 0 || first + n > (int)h_sw.size()) return fail(PGS_ERR_INVALID_ARGUMENT, "get_switches: range out of bounds");
+  if (first < 0 || n < 0 || (int64_t)first + n > (int64_t)h_sw.size()) return fail(PGS_ERR_INVALID_ARGUMENT, "get_switches: range out of bounds");
+  if (n > 0 && !s) return fail(PGS_ERR_INVALID_ARGUMENT, "get_switches: null output");
   if (int rc = sync_params_to_host()) return rc;
   std::memcpy(s, &h_sw[first], sizeof(double) * n);
   return PGS_OK;
@@ -774,8 +785,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     if (comm) { const int a = comm->agree(prc, stream, &err); if (a) return prc ? prc : a; }
     else if (prc) return prc;
   }
-  cudaEvent_t t_begin, t_end; CU(cudaEventCreate(&t_begin)); CU(cudaEventCreate(&t_end));
-  CU(cudaEventRecord(t_begin, stream));
+  CU(cudaEventRecord(ev_t0, stream));
   const int El = (int)l_a.size(), Eo = (int)o_c1.size(), K = (int)r_node.size();
   const int rgrid = std::max(1, std::min(1024, cdiv(std::max(N, El), 256)));
   const int mg = std::max(1, std::min(1024, cdiv(std::max(Eo, El), 256)));
@@ -902,9 +912,8 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     }
   }
   device_params_newer = true;
-  CU(cudaEventRecord(t_end, stream)); CU(cudaEventSynchronize(t_end));
-  float total_ms = 0; CU(cudaEventElapsedTime(&total_ms, t_begin, t_end));
-  cudaEventDestroy(t_begin); cudaEventDestroy(t_end);
+  CU(cudaEventRecord(ev_t1, stream)); CU(cudaEventSynchronize(ev_t1));
+  float total_ms = 0; CU(cudaEventElapsedTime(&total_ms, ev_t0, ev_t1));
   if (sum) {
     sum->initial_cost = initial_cost; sum->final_cost = x_cost; sum->termination = termination;
     sum->num_successful_steps = n_succ; sum->num_unsuccessful_steps = n_unsucc; sum->num_iterations = (int)rows.size();

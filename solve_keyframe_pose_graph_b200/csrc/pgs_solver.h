@@ -145,7 +145,7 @@ class Solver {
 
   // device
   int dev = 0; cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   DBuf<double> d_pose, d_cpose, d_sw, d_csw, d_stage_q, d_stage_t, d_stage_s;
   DBuf<int2> d_oidx, d_lidx, d_pair;
   DBuf<double> d_oobs, d_lobs, d_ranchor;

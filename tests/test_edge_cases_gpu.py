@@ -94,3 +94,35 @@ def test_c_abi_rejects_bad_arguments_without_crashing():
     qq, tt = S.poses()
     assert np.array_equal(qq, q) and np.array_equal(tt, t)
     S.close()
+
+
+def test_replacing_the_node_set_under_existing_blocks_and_null_arguments_are_refused():
+    """pgs_set_nodes with a smaller n used to leave edge indices past the end (heap overrun in
+    finalize); update / switch calls dereferenced null pointers."""
+    import ctypes as C
+    g = random_graph(60, 2, 6, seed=31)
+    S = load_pgs(g)
+    with pytest.raises(pgs.PgsError, match="beyond the new node count"):
+        S.set_nodes(g["q"][:20], g["t"][:20])
+    S.set_nodes(g["q"], g["t"])                                      # same size: allowed, blocks stay valid
+    L = S.L
+    assert L.pgs_update_nodes(S.h, C.c_int32(0), C.c_int32(5), None, None) == -1
+    assert L.pgs_set_switches(S.h, C.c_int32(0), C.c_int32(3), None) == -1
+    assert L.pgs_get_switches(S.h, C.c_int32(0), C.c_int32(3), None) == -1
+    assert L.pgs_update_nodes(S.h, C.c_int32(2**31 - 10), C.c_int32(100), g["q"].ctypes.data_as(pgs.capi.c_dp), g["t"].ctypes.data_as(pgs.capi.c_dp)) == -1
+    s = S.solve()                                                    # the handle is still usable
+    assert s["final_cost"] < s["initial_cost"]
+    S.close()
+
+
+def test_factor_over_budget_falls_back_to_pcg_and_says_so():
+    """the skyline factor is dense inside the row envelope, so loop closures that reach far back
+    make it large.  Over the memory / flop budget the iterative solver takes over instead of PGS_ERR_OUT_OF_MEMORY."""
+    g = random_graph(400, 3, 60, seed=32)
+    a = load_pgs(g); sa = a.solve(); qa, ta = a.poses(); a.close()
+    assert sa["linear_solver_used"] == pgs.capi.SKYLINE_CHOLESKY and sa["factor_flops"] > 0
+    b = load_pgs(g, max_factor_flops=sa["factor_flops"] / 2, pcg_tolerance=1e-12); sb = b.solve(); qb, tb = b.poses(); b.close()
+    assert sb["linear_solver_used"] == pgs.capi.BLOCK_PCG and sb["linear_solver_iterations"] > 0 and sb["factor_nnz"] == 0
+    c = load_pgs(g, max_factor_bytes=1e4, pcg_tolerance=1e-12); sc = c.solve(); c.close()
+    assert sc["linear_solver_used"] == pgs.capi.BLOCK_PCG
+    assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-5 * sa["final_cost"] and np.abs(ta - tb).max() < 1e-5 and rot_angle_between(qa, qb).max() < 1e-4

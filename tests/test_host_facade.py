@@ -294,3 +294,23 @@ def test_c_abi_headers_compile_as_plain_c(tmp_path):
     src = tmp_path / "hdr.c"
     src.write_text("".join(f'#include "{os.path.basename(h)}"\n' for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))) + "int main(void) { return 0; }\n")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "hdr.o")])
+
+
+def test_loop_edge_onto_the_same_keyframe_builds_no_block_and_later_triggers_go_on():
+    """both stamps of a loop message can resolve to one keyframe (1 ms lookup).  The manager keeps the
+    edge, as the reference's does (src/NodeDataManager.cpp:107-189), but no residual block is built for it — Ceres
+    itself refuses a block that binds one parameter block twice — and the triggers after it work as usual; the block
+    lists never hold a term twice, however often the trigger runs."""
+    F = facade.Facade(dry_run=True, odom_fanout=2)
+    I = np.array([0, 0, 0, 1.0]); z = np.zeros(3)
+    st = np.arange(10, dtype=np.int64) * 10**8 + 10**9
+    F.add_nodes(st, np.tile(I, (10, 1)), np.cumsum(np.ones((10, 3)), axis=0))
+    F.add_loop_edges([5, 7], [5, 2], [I, I], [z, z], [1.0, 1.0])
+    assert F.solve_once()
+    n_odom = len(F.odom_terms()["u"])
+    assert n_odom == 2 * 10 - 3 and len(F.switches()) == 2
+    F.add_loop_edges([9], [1], [I], [z], [1.0])
+    assert F.solve_once() and F.status() == 3
+    assert len(F.odom_terms()["u"]) == n_odom            # nothing new to derive, nothing derived twice
+    assert not F.solve_once() and F.solve_once(force=True) and len(F.odom_terms()["u"]) == n_odom
+    F.close()

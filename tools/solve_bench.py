@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--nodes", type=int, default=0)
     ap.add_argument("--loops", type=int, default=0)
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--chains", type=int, default=0, help="elimination chains on the one GPU (0 = automatic)")
     args = ap.parse_args()
     import solve_keyframe_pose_graph_b200 as pgs
     from solve_keyframe_pose_graph_b200 import problems
@@ -35,7 +36,7 @@ def main():
     out = {"config": args.config, "N": int(p["N"]), "n_odom": len(p["oc1"]), "n_loop": len(p["la"]), "outliers": int(p["lout"].sum()), "build_s": t_build}
     for rep in range(args.repeat):
         S = problems.load_into_solver(p, linear_solver=pgs.capi.SKYLINE_CHOLESKY if args.solver == "skyline" else pgs.capi.BLOCK_PCG,
-                                      max_num_iterations=args.max_iters)
+                                      max_num_iterations=args.max_iters, chains=args.chains)
         t0 = time.perf_counter()
         s = S.solve()
         wall = time.perf_counter() - t0
@@ -45,6 +46,7 @@ def main():
         s["lm_iters_per_s"] = (len(its) - 1) / max(wall, 1e-9)
         s["costs"] = [r["cost"] for r in its]
         s["switches_off"] = int((S.switches() < 0.5).sum())
+        s["backward_errors"] = [float(x) for x in S.linear_backward_errors()]
         out[f"gpu{rep}"] = s
         qs, ts = S.poses(); sw = S.switches()
         S.close()
