@@ -74,8 +74,9 @@ typedef struct pgs_options {
   int32_t pcg_max_iterations;               /* per linear solve */
   double pcg_tolerance;                     /* relative residual ||b-Ax|| / ||b|| */
   int32_t chains;                           /* elimination chains of the skyline solver on ONE GPU: 0 = automatic (two chains
-                                               burning from both ends of the keyframe chain from 4096 nodes on), 1 = one
-                                               natural-order chain, 2.. = that many; with pgs_dist_init: chains per rank (0 = 1) */
+                                               burning from both ends of the keyframe chain when the graph has 4096+ nodes and
+                                               a thin front, i.e. when the per-panel critical path bounds the factorisation),
+                                               1 = one natural-order chain, 2.. = that many; with pgs_dist_init: chains per rank (0 = 1) */
   int32_t check_linear_solves;              /* != 0: measure the backward error ||b - A y|| / ||b|| of every linear solve
                                                (one block SpMV each; pgs_get_linear_backward_errors) */
   double max_factor_bytes;                  /* skyline factor larger than this (0 = 80 % of the free device memory) or ... */
@@ -98,7 +99,7 @@ typedef struct pgs_summary {
   int64_t factor_nnz;                       /* scalars stored by the skyline factor(s) (0 for PCG) */
   int32_t linear_solver_used;               /* pgs_linear_solver actually used (PGS_BLOCK_PCG when the skyline estimate exceeded the budget) */
   int32_t n_chains;                         /* elimination chains on this GPU (1 = plain natural order) */
-  double factor_flops;                      /* estimated flops of one factorisation (sum over rows of width^2) */
+  double factor_flops;                      /* estimated flops of one natural-order factorisation (sum over columns of rows-below^2) */
   double max_linear_backward_error;         /* max over the linear solves of ||b - A y|| / ||b||; -1 when not measured */
   double fixed_cost;                        /* Ceres Summary::fixed_cost: cost of the residual blocks whose parameter blocks are all constant */
   double ms_comm;                           /* device time spent in collectives incl. waiting for other ranks (multi-GPU) */

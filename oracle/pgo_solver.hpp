@@ -94,10 +94,12 @@ struct Problem {
   // scratch filled by evaluate()
   std::vector<double> r_o, J_o, r_l, J_l, r_r, J_r;  // 6,72 | 7,91 | 6,36 per block
 
-  // cost = 1/2 sum r^2.  want_jac: fill J_* too.
-  double evaluate(const double* Q, const double* T, const double* S, bool want_jac, const Options& opt) {
+  // cost = 1/2 sum r^2.  want_jac: fill J_* too.  keep_residuals = false: cost only, r_* stay as they are —
+  // Ceres evaluates the candidate point of an LM step with residuals == NULL (TrustRegionMinimizer), so the residuals of
+  // the current point x survive a rejected step and the next step is built from J(x)^T r(x).
+  double evaluate(const double* Q, const double* T, const double* S, bool want_jac, const Options& opt, bool keep_residuals = true) {
     const int Eo = n_odom(), El = n_loop(), K = n_reg();
-    r_o.resize(6 * (size_t)Eo); r_l.resize(7 * (size_t)El); r_r.resize(6 * (size_t)K);
+    if (keep_residuals) { r_o.resize(6 * (size_t)Eo); r_l.resize(7 * (size_t)El); r_r.resize(6 * (size_t)K); }
     if (want_jac) { J_o.resize(72 * (size_t)Eo); J_l.resize(91 * (size_t)El); J_r.resize(36 * (size_t)K); }
     double cost = 0.0;
     const bool ad = opt.use_autodiff != 0;
@@ -105,7 +107,8 @@ struct Problem {
     for (int e = e0; e < e1; ++e) {
       SixDOFError f{Quat<double>{oq[4 * e], oq[4 * e + 1], oq[4 * e + 2], oq[4 * e + 3]},
                     Vec3<double>{ot[3 * e], ot[3 * e + 1], ot[3 * e + 2]}, ow[e]};
-      double* r = &r_o[6 * (size_t)e];
+      double rtmp[6];
+      double* r = keep_residuals ? &r_o[6 * (size_t)e] : rtmp;
       double* J = want_jac ? &J_o[72 * (size_t)e] : nullptr;
       const int a = oc1[e], b = oc2[e];
       if (ad) eval_sixdof_autodiff(f, Q + 4 * a, T + 3 * a, Q + 4 * b, T + 3 * b, r, J);
@@ -118,7 +121,8 @@ struct Problem {
     for (int e = e0; e < e1; ++e) {
       SixDOFErrorWithSwitchingConstraints f{Quat<double>{lq[4 * e], lq[4 * e + 1], lq[4 * e + 2], lq[4 * e + 3]},
                                             Vec3<double>{lt[3 * e], lt[3 * e + 1], lt[3 * e + 2]}, lw[e]};
-      double* r = &r_l[7 * (size_t)e];
+      double rtmp[7];
+      double* r = keep_residuals ? &r_l[7 * (size_t)e] : rtmp;
       double* J = want_jac ? &J_l[91 * (size_t)e] : nullptr;
       const int a = lc1[e], b = lc2[e];
       if (ad) eval_switch_autodiff(f, Q + 4 * a, T + 3 * a, Q + 4 * b, T + 3 * b, S + lsi[e], r, J);
@@ -129,7 +133,8 @@ struct Problem {
     return cost; });
     for (int k = 0; k < K; ++k) {
       NodePoseRegularization f{pose_to_mat4(&rq[4 * k], &rt[3 * k]), rw[k]};
-      double* r = &r_r[6 * (size_t)k];
+      double rtmp[6];
+      double* r = keep_residuals ? &r_r[6 * (size_t)k] : rtmp;
       double* J = want_jac ? &J_r[36 * (size_t)k] : nullptr;
       const int a = rn[k];
       if (ad) eval_reg_autodiff(f, Q + 4 * a, T + 3 * a, r, J);
@@ -449,7 +454,7 @@ struct Solver {
       // ---- ComputeCandidatePointAndEvaluateCost
       plus(xq, xt, xs, dp, ds, cq, ct, cs);
       double te = wall_seconds();
-      double candidate_cost = P.evaluate(cq.data(), ct.data(), cs.data(), false, opt);
+      double candidate_cost = P.evaluate(cq.data(), ct.data(), cs.data(), false, opt, /*keep_residuals=*/false);
       sum.t_evaluate += wall_seconds() - te;
       if (!std::isfinite(candidate_cost)) candidate_cost = std::numeric_limits<double>::max();
 

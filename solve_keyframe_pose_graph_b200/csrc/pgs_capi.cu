@@ -29,7 +29,7 @@ int pgs_default_options(pgs_options* o) {
   o->max_num_consecutive_invalid_steps = 5; o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
   o->jacobi_scaling = 1; o->switch_init = 0.99;  // reference PoseGraphSLAM.cpp:353
   o->device = 0; o->linear_solver = PGS_SKYLINE_CHOLESKY; o->pcg_max_iterations = 20000; o->pcg_tolerance = 1e-10;
-  o->chains = 0; o->check_linear_solves = 0; o->max_factor_bytes = 0.0; o->max_factor_flops = 0.0;
+  o->chains = 0; o->check_linear_solves = 1; o->max_factor_bytes = 0.0; o->max_factor_flops = 0.0;
   return PGS_OK;
 }
 

@@ -253,9 +253,16 @@ int Solver::dist_stats(pgs_dist_stats* out) {
   return PGS_OK;
 }
 
+// Two chains meeting in the middle do the same work as one, on two dependency chains instead of one.  That pays when
+// the per-panel critical path (diagonal block + panel solve, ~40 us) is what bounds the factorisation, i.e. when the
+// trailing update of a panel is small: a thin front.  A thick front keeps the whole GPU busy from one chain already.
+static constexpr double kTwoChainsMaxFlopsPerPanel = 0.5e9;
 bool Solver::want_chains() const {
   if (is_inner || comm_owned || opt.linear_solver != PGS_SKYLINE_CHOLESKY) return false;
-  return opt.chains >= 2 || (opt.chains == 0 && N >= 4096);
+  if (opt.chains >= 2) return true;
+  if (opt.chains != 0 || N < 4096) return false;
+  const double panels = std::max(1.0, 6.0 * N / skyline_panel_width());
+  return est_flops / panels < kTwoChainsMaxFlopsPerPanel;
 }
 
 int Solver::solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap) {

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/pgs.h"
@@ -65,6 +66,7 @@ struct SkylineFactor {
   double* xacc = nullptr;          // [n] backward-solve accumulator
   int* fail = nullptr; int* h_fail = nullptr;
   int* pair_hi = nullptr; int* pair_lo = nullptr; int n_pairs = 0;
+  double* zeros = nullptr;         // PW zeros: what the update's bulk copies read for rows that do not exist
   int* node_src = nullptr; int* pair_src = nullptr;   // optional: factor node -> row of Ad / b (-1 = none), factor pair -> row of Ao
   long long tail = 0;              // extra doubles behind the envelope (travel with it in the border all-reduce)
 };
@@ -74,7 +76,7 @@ struct SkylineFactor {
 void skyline_destroy(SkylineFactor* f) {
   if (!f) return;
   cudaFree(f->val); cudaFree(f->ptr); cudaFree(f->start); cudaFree(f->rows_ptr); cudaFree(f->rows_idx); cudaFree(f->dinv);
-  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched); cudaFree(f->node_src); cudaFree(f->pair_src);
+  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched); cudaFree(f->node_src); cudaFree(f->pair_src); cudaFree(f->zeros);
   if (f->h_fail) cudaFreeHost(f->h_fail);
   for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); if (f->ev_c[i]) cudaEventDestroy(f->ev_c[i]); }
   if (f->ev_fork) cudaEventDestroy(f->ev_fork);
@@ -138,6 +140,8 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
   if ((e = cudaMalloc((void**)&f->dinv, sizeof(double) * (size_t)std::max(D, 1) * PW * PW)) != cudaSuccess) return bad(e, "dinv");
   if ((e = cudaMalloc((void**)&f->xacc, sizeof(double) * (size_t)std::max(D, 1) * PW)) != cudaSuccess) return bad(e, "xacc");
   if ((e = cudaMalloc((void**)&f->fail, sizeof(int))) != cudaSuccess) return bad(e, "fail");
+  if ((e = cudaMalloc((void**)&f->zeros, sizeof(double) * PW)) != cudaSuccess) return bad(e, "zeros");
+  if ((e = cudaMemsetAsync(f->zeros, 0, sizeof(double) * PW, stream)) != cudaSuccess) return bad(e, "zeros");
   if ((e = cudaMalloc((void**)&f->sched, 4 * sizeof(unsigned int))) != cudaSuccess) return bad(e, "sched");
   if ((e = cudaMemsetAsync(f->sched, 0, 4 * sizeof(unsigned int), stream)) != cudaSuccess) return bad(e, "sched");
   if ((e = cudaMallocHost((void**)&f->h_fail, sizeof(int))) != cudaSuccess) return bad(e, "h_fail");
@@ -675,6 +679,158 @@ __global__ void __launch_bounds__(256, 2) sky_update_kernel(int d, int n, int sk
   }
 }
 
+// ------------------------------------------------------------------------------------------------ update, persistent pipeline
+// The same tiles as sky_update_kernel, as a persistent software pipeline (one 256-thread CTA per SM, 166 KB of shared
+// memory): a CTA walks its tiles T = blockIdx.x, blockIdx.x + gridDim.x, ... and treats their K chunks as ONE stream
+// through a 3-stage ring.  As soon as every warp is done with chunk ch of tile t, chunk ch of tile t+1 is requested into
+// the same stage — one bulk asynchronous copy (cp.async.bulk, 256 B = one row x 32 columns) per row, completion counted
+// in bytes on the stage's mbarrier — so the operands of the next tile arrive while this one is being multiplied, and the
+// load phase that left every CTA of the one-tile kernel idle for a third of its life (tools/upd_lab.cu) disappears.
+// A_old is no longer preloaded into the accumulators: its predicated loads go into registers of their own at the top of
+// the tile, land during the multiply, and the epilogue stores A_old - X X^T.
+// Rows that do not exist (past the end of the row list; the rhs row as a column) are fed from a buffer of zeros.
+constexpr int WS_THREADS = 256;
+constexpr int WS_NS = PW / KC;                 // ring stages == K chunks of a tile
+static_assert(WS_NS == 3, "stage index == chunk index");
+struct WsTable { long long abase[UM]; long long bbase[UN]; int arow[UM]; int bcol[UN]; };
+constexpr int WS_STAGE = (UM + UN) * LDK;      // doubles per stage
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+               ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void upd_tile_of(int part, int T, int& ti, int& tj) {
+  if (part == 0) { ti = T >> 1; tj = T & 1; return; }
+  ti = (int)((1.0f + sqrtf(1.0f + 4.0f * (float)T)) * 0.5f);
+  while (ti * (ti - 1) > T) --ti;
+  while ((ti + 1) * ti <= T) ++ti;
+  tj = 2 + (T - ti * (ti - 1));
+}
+
+template <int PART>
+__global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int n, int skip_below, int Tr, int Tc, int n_tiles,
+                                                                      const long long* __restrict__ ptr, const int* __restrict__ start,
+                                                                      const int* __restrict__ rows_ptr, const int* __restrict__ rows_idx,
+                                                                      double* __restrict__ val, const double* __restrict__ zeros) {
+  constexpr int WARPS_M = 4, WARPS_N = 2;
+  constexpr int WTM = UM / WARPS_M, WTN = UN / WARPS_N, FM = WTM / 8, FN = WTN / 8;
+  constexpr unsigned STAGE_BYTES = (UM + UN) * KC * sizeof(double);
+  extern __shared__ __align__(128) unsigned char ws_smem[];
+  double* ring = reinterpret_cast<double*>(ws_smem);                                  // [WS_NS][UM + UN][LDK]
+  WsTable* tab = reinterpret_cast<WsTable*>(ring + WS_NS * WS_STAGE);                 // [2]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(tab + 2);          // [WS_NS]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c0 = d * PW;
+  const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = wid % WARPS_M, wn = wid / WARPS_M;
+  if (tid == 0) {
+    for (int s = 0; s < WS_NS; ++s) mbar_init(full + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // row (tid < UM) or column (UM <= tid < UM + UN) entry of tile T's table, in two steps so that the two levels of
+  // dependent global loads can be issued well before their results are needed
+  auto entry_row = [&](int T) -> int {
+    int ti, tj; upd_tile_of(PART, T, ti, tj);
+    if (ti >= Tr || tj >= Tc) return -1;                // the last row tile can run past the last column tile: an all-zero tile
+    if (tid < UM) { const int ir = ti * UM + tid; return ir < nr ? rows_idx[rb + ir] : -1; }
+    if (tid < UM + UN) { const int ic = tj * UN + (tid - UM); const int c = ic < nr ? rows_idx[rb + ic] : -1; return c >= n ? -1 : c; }   // the rhs row is never a column
+    return -1;
+  };
+  auto entry_store = [&](WsTable& tb, int r) {
+    const long long base = r >= 0 ? ptr[r] + (c0 - start[r]) : -1;
+    if (tid < UM) { tb.arow[tid] = r; tb.abase[tid] = base; }
+    else if (tid < UM + UN) { tb.bcol[tid - UM] = r; tb.bbase[tid - UM] = base; }
+  };
+  auto issue = [&](const WsTable& tb, int ch) {
+    if (tid == 0) mbar_expect_tx(full + ch, STAGE_BYTES);
+    if (tid < UM + UN) {
+      const long long bo = tid < UM ? tb.abase[tid] : tb.bbase[tid - UM];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last read through the generic proxy
+      bulk_g2s(ring + ch * WS_STAGE + tid * LDK, bo >= 0 ? (const void*)(val + bo + ch * KC) : (const void*)zeros, KC * sizeof(double), full + ch);
+    }
+  };
+  int T = blockIdx.x;
+  if (T >= n_tiles) return;
+  entry_store(tab[0], entry_row(T));
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < WS_NS; ++ch) issue(tab[0], ch);
+  for (int it = 0; T < n_tiles; T += gridDim.x, ++it) {
+    const unsigned par = (unsigned)(it & 1);
+    const int Tn = T + gridDim.x;
+    const bool more = Tn < n_tiles;
+    const int r_next = more ? entry_row(Tn) : -1;       // level 1 of the next tile's table, in flight during this tile
+    mbar_wait(full + 0, par);
+    const WsTable& tb = tab[it & 1];
+    int cidx[FN], ridx[FM];
+    long long rowoff[FM];
+#pragma unroll
+    for (int j = 0; j < FN; ++j) cidx[j] = tb.bcol[wn * WTN + 8 * j + 2 * t];
+#pragma unroll
+    for (int i = 0; i < FM; ++i) {
+      const int rl = wm * WTM + 8 * i + g;
+      const int r = tb.arow[rl];
+      ridx[i] = r >= skip_below ? r : -1;               // -1: no such row, or a row C(d+1) owns
+      rowoff[i] = r >= 0 ? tb.abase[rl] - c0 : 0;       // offset of (row, column 0)
+    }
+    // A_old: a lane owns two adjacent list positions (even, odd) of a row — always columns (c, c + 1), 16-byte aligned;
+    // on the diagonal (c == r) only the first of the two exists
+    double cold[FM][FN][2], acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        const int c = cidx[j], r = ridx[i];
+        const bool pair = c >= 0 && c + 1 <= r, diag = c >= 0 && c == r;
+        const double* p = val + ((pair || diag) ? rowoff[i] + c : 0);
+        cold[i][j][0] = 0.0; cold[i][j][1] = 0.0; acc[i][j][0] = 0.0; acc[i][j][1] = 0.0;
+        ldg128_if(cold[i][j][0], cold[i][j][1], p, pair);
+        ldg64_if(cold[i][j][0], p, diag);
+      }
+#pragma unroll
+    for (int ch = 0; ch < WS_NS; ++ch) {
+      if (ch > 0) mbar_wait(full + ch, par);
+      const double* a_s = ring + ch * WS_STAGE + (wm * WTM + g) * LDK + t;
+      const double* b_s = ring + ch * WS_STAGE + (UM + wn * WTN + g) * LDK + t;
+#pragma unroll
+      for (int k = 0; k < KC; k += 4) {
+        double a[FM], bf[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) a[i] = a_s[(8 * i) * LDK + k];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) bf[j] = b_s[(8 * j) * LDK + k];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+      }
+      if (ch == 0 && more) entry_store(tab[(it + 1) & 1], r_next);   // level 2 of the next tile's table
+      __syncthreads();                                  // every warp is done with stage ch (and, at ch == 0, the next table is complete)
+      if (more) issue(tab[(it + 1) & 1], ch);
+    }
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        const int c = cidx[j], r = ridx[i];
+        const bool pair = c >= 0 && c + 1 <= r, diag = c >= 0 && c == r;
+        double* p = val + ((pair || diag) ? rowoff[i] + c : 0);
+        stg128_if(p, cold[i][j][0] - acc[i][j][0], cold[i][j][1] - acc[i][j][1], pair);
+        stg64_if(p, cold[i][j][0] - acc[i][j][0], diag);
+      }
+  }
+}
+
 // backward sweep, one launch per panel d = D-1 .. 0 (plus one leading launch that only computes x of the last panel):
 //   push      acc[c] -= sum_{r in panel d} L[r][c] x_r  for every column c in [lo, c0) inside the rows' envelopes
 //             (256 threads = 32 columns x 8 row groups per CTA);
@@ -777,7 +933,10 @@ __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo,
 static const size_t SM_TRSM = sizeof(double) * (PW * LDT + TR * LDT);
 static const size_t SM_UPD = sizeof(double) * (2 * (UM + UN) * LDK);   // two stages: 108 KB, two CTAs per SM
 static const size_t SM_DIAG = sizeof(double) * (2 * PW * LDT + (PW / 8) * 64 + 8 * LDT);
+static const size_t SM_UPD_WS = sizeof(double) * (size_t)WS_NS * WS_STAGE + 2 * sizeof(WsTable) + WS_NS * sizeof(unsigned long long);
 
+static int g_rest_ctas = 132;     // grid of the persistent update kernel
+static int g_update_mode = 1;     // 0: one tile per CTA (sky_update_kernel), 1: warp-specialised persistent pipeline for rest(d), 2: for next(d) too
 static int set_attrs(std::string* err) {
   static bool attr_set = false;
   if (attr_set) return PGS_OK;
@@ -785,6 +944,12 @@ static int set_attrs(std::string* err) {
   SK(cudaFuncSetAttribute(sky_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TRSM));
   SK(cudaFuncSetAttribute(sky_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
   SK(cudaFuncSetAttribute(sky_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
+  SK(cudaFuncSetAttribute(sky_update_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD_WS));
+  SK(cudaFuncSetAttribute(sky_update_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD_WS));
+  { int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    // the persistent update CTAs fill a whole SM each; a few SMs stay free for the kernels of the panel chain
+    const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 16; if (g_rest_ctas < 1) g_rest_ctas = 1;
+    const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 1; }
   attr_set = true;
   return PGS_OK;
 }
@@ -837,9 +1002,14 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
     // The rhs row (index n) is always live, also when the last panel is short.
     const int skip_below = (d + 1 < f->D_elim) ? std::min((d + 2) * PW, n) : 0;
     if (d > 0) SK(cudaStreamWaitEvent(s2, f->ev_rest[(d - 1) % NEV], 0));
-    sky_update_kernel<0><<<2 * Tr, 256, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
+    if (g_update_mode >= 2) sky_update_ws_kernel<0><<<std::min(2 * Tr, g_rest_ctas), WS_THREADS, SM_UPD_WS, s2>>>(d, n, skip_below, Tr, Tc, 2 * Tr, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val, f->zeros);
+    else sky_update_kernel<0><<<2 * Tr, 256, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
-    if (Tr > 1) sky_update_kernel<1><<<Tr * (Tr - 1), 256, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
+    if (Tr > 1) {
+      const int nt = Tr * (Tr - 1);
+      if (g_update_mode >= 1) sky_update_ws_kernel<1><<<std::min(nt, g_rest_ctas), WS_THREADS, SM_UPD_WS, s0>>>(d, n, skip_below, Tr, Tc, nt, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val, f->zeros);
+      else sky_update_kernel<1><<<nt, 256, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
+    }
     SK(cudaEventRecord(f->ev_rest[d % NEV], s0));
   }
   // join: the main stream continues after all three are done

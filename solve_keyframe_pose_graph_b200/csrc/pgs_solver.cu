@@ -480,7 +480,8 @@ int Solver::get_backward_errors(double* out, int cap, int* n) {
 }
 
 // Envelope size and factorisation cost of the natural-order skyline, straight from the edge lists (host only):
-// row i spans [min neighbour, i], nnz = sum of the widths, flops ~ sum of the squared widths (scalars).
+// row i spans [min neighbour, i]; nnz = sum of the row widths; flops = sum over the columns of (rows that reach the
+// column)^2 — the rank-1 update every eliminated column applies to the rows below it.
 void Solver::estimate_skyline(double* bytes, double* flops) const {
   std::vector<int> nstart(std::max(N, 1));
   for (int i = 0; i < N; ++i) nstart[i] = i;
@@ -488,11 +489,16 @@ void Solver::estimate_skyline(double* bytes, double* flops) const {
   for (size_t e = 0; e < o_c1.size(); ++e) edge(o_c1[e], o_c2[e]);
   for (size_t e = 0; e < l_a.size(); ++e) edge(l_a[e], l_b[e]);
   const int PW = skyline_panel_width(), PN = PW / 6;
-  double nnz = 0.0, fl = 0.0;
+  const int D = (6 * N + PW - 1) / PW;
+  std::vector<int> diff(D + 1, 0);                 // rows (in nodes) that reach panel d from below
+  double nnz = 0.0;
   for (int i = 0; i < N; ++i) {
-    const double w = (double)(((6 * i) / PW + 1) * PW - (nstart[i] / PN) * PW);
-    nnz += 6.0 * w; fl += 6.0 * w * w;
+    const int d0 = nstart[i] / PN, d1 = i / PN;
+    nnz += 6.0 * (double)((d1 + 1 - d0) * PW);
+    if (d0 < d1) { ++diff[d0]; --diff[d1]; }
   }
+  double fl = 0.0; int reach = 0;
+  for (int d = 0; d < D; ++d) { reach += diff[d]; const double R = 6.0 * reach + PW / 2.0; fl += PW * R * R; }
   *bytes = nnz * sizeof(double); *flops = fl;
 }
 

@@ -70,7 +70,7 @@ def test_config1_and_full_size_config2_against_the_oracle(config):
     assert np.abs(t - to).max() < 1e-5 and rot_angle_between(q, qo).max() < 1e-4 and np.array_equal(sw > 0.5, swo > 0.5)
     assert be.max() < 1e-9
     if config == 2:
-        assert p["N"] == 10000 and len(p["oc1"]) == 29994 and len(p["la"]) == 2000 and s["n_chains"] == 2
+        assert p["N"] == 10000 and len(p["oc1"]) == 29994 and len(p["la"]) == 2000 and s["n_chains"] == 2   # thin front: two chains by default
 
 
 @pytest.mark.parametrize("config", [3, 4])

@@ -171,3 +171,18 @@ def test_minimiser_agrees_with_an_independent_scipy_least_squares_solve():
     assert np.abs(t - to).max() < 1e-5
     assert rot_angle_between(q, qo).max() < 1e-4
     assert np.abs(sol.x[7 * N:] - P.switches()).max() < 1e-5
+
+
+def test_rejected_steps_leave_the_residuals_of_the_current_point_in_place():
+    """Ceres evaluates the candidate of an LM step with residuals == NULL, so after a rejected step the next step is
+    again built from J(x)^T r(x).  (Until round 2 the oracle's cost-only evaluation overwrote r with the candidate's
+    residuals; after a rejection the following steps then blew up — candidate costs 1e8, 1e22, 1e50, ... in
+    config3_small — which the CUDA solve, comparing against the golden, brought to light.)  With the radius halved,
+    quartered, ... after every rejection, the rejected candidates have to come back towards the current cost."""
+    G = np.load(os.path.join(GOLD, "config3_small.npz"))
+    ok = G["iter_success"].astype(bool); cost = G["iter_cost"]
+    assert (~ok).sum() >= 5 and ok[-1]                                  # five rejections in a row, then progress again
+    x_cost = cost[2]
+    rejected = cost[3:8]
+    assert np.all(rejected < 10 * x_cost) and rejected[-1] < rejected[0]
+    assert cost[-1] < 0.1 * x_cost

@@ -96,6 +96,11 @@ def load_pgs(g, switches=None, **opt):
 
 
 def rot_angle_between(qa, qb):
-    """Geodesic angle (rad) between unit quaternion arrays (sign-insensitive)."""
-    d = np.abs(np.sum(qa * qb, axis=1)).clip(0, 1)
-    return 2 * np.arccos(d)
+    """Geodesic angle (rad) between unit quaternion arrays (sign-insensitive).  Through the vector part of conj(qa) * qb
+    (sin of the half angle), which keeps its precision for tiny angles where arccos of the dot product resolves ~3e-8."""
+    qa = np.atleast_2d(qa); qb = np.atleast_2d(qb)
+    va, wa = -qa[:, :3], qa[:, 3:4]
+    vb, wb = qb[:, :3], qb[:, 3:4]
+    v = wa * vb + wb * va + np.cross(va, vb)
+    w = (wa * wb)[:, 0] - np.sum(va * vb, axis=1)
+    return 2 * np.arctan2(np.linalg.norm(v, axis=1), np.abs(w))
