@@ -272,6 +272,9 @@ def run_sharded(args, rank, local_rank, world, dist, torch, barrier, lm_record):
             out["roofline_large"] = {"bound": "hbm", "kernel": "sweep_kernel<0>", "workload": out["workload"], "achieved": bytes5 / (msk * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": bytes5 / (msk * 1e-3) / 1e9 / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes5), "kernel_ms": msk,
                                      "l2": "no flush needed: one launch moves 20x the L2 capacity", "traffic": None}
+            ms_w5 = S.time_stream_write(bytes5, reps=5, flush_l2=False)
+            out["roofline_large"]["same_size_stream_write"] = {"gbs": bytes5 / (ms_w5 * 1e-3) / 1e9, "ms": ms_w5,
+                                                               "what": "pure st.global.cs write of the same byte count: what a store-bound kernel of this size can reach"}
             prof = os.path.join(ROOT, "profiles", "r02_sweep_traffic_c5.json")
             if os.path.exists(prof):
                 tr = json.load(open(prof))
@@ -392,6 +395,16 @@ def main():
             T = problems.load_into_solver(p2, device=local_rank)
             T.solve(); T.update_nodes(0, p2["q"], p2["t"]); T.set_switches(np.full(len(p2["la"]), 0.99))
             extra["lm_c2"] = lm_record(p2, T, T.solve())
+            T.close()
+            # config 3 with drift below the switch function's cliff: every inlier closure survives, every outlier is switched off
+            pt = problems.build_problem(3, odom_sigma_t=0.002, odom_sigma_r=0.0001, loop_gap_max=200)
+            T = problems.load_into_solver(pt, device=local_rank)
+            T.solve(); T.update_nodes(0, pt["q"], pt["t"]); T.set_switches(np.full(len(pt["la"]), 0.99))
+            rec = lm_record(pt, T, T.solve())
+            sw = T.switches(); outl = pt["lout"].astype(bool)
+            rec.update({"workload": rec["workload"] + " [tight: odom sigma 2 mm / 1e-4 rad, loop gap <= 200]",
+                        "inliers_on_frac": float((sw[~outl] > 0.5).mean()), "outliers_off_frac": float((sw[outl] < 0.5).mean())})
+            extra["lm_c3_tight"] = rec
             T.close()
         except Exception as ex:   # the headline number must not die with the extra section
             extra["lm"] = {"error": str(ex)[:300]}

@@ -207,7 +207,7 @@ int pgs_partition(int32_t n_nodes, int32_t world, int32_t n_odom, const int32_t*
  * mode: 0 = residuals + Jacobians (mode J), 1 = cost only. */
 int pgs_time_sweep(pgs_handle h, int32_t mode, int32_t reps, int32_t flush_l2, double* ms_per_sweep,
                    double* ms_sweep_kernel, int64_t* kernel_launches);
-/* Practical ceiling for a store-dominated kernel of this size: a pure streaming write of `bytes` bytes,
+/* Practical ceiling for a store-dominated kernel of this size: a pure streaming write of `bytes` bytes (up to 16 GiB),
  * timed exactly like pgs_time_sweep (per repetition, CUDA events, same L2 flush).  Diagnostic only. */
 int pgs_time_stream_write(pgs_handle h, int64_t bytes, int32_t reps, int32_t flush_l2, double* ms_per_write);
 /* End-to-end step: host poses/switches (pinned or pageable) -> device, one mode-J sweep, cost back

@@ -47,6 +47,7 @@ class Summary(C.Structure):
         ("t_evaluate", C.c_double),
         ("t_linear", C.c_double),
         ("t_total", C.c_double),
+        ("fixed_cost", C.c_double),
     ]
 
 
@@ -226,7 +227,7 @@ class Problem:
         rows = [{f: getattr(its[i], f) for f, _ in Iteration._fields_} for i in range(min(s.num_iterations, cap))]
         return dict(initial_cost=s.initial_cost, final_cost=s.final_cost, termination=TERMINATION[s.termination],
                     num_successful_steps=s.num_successful_steps, num_unsuccessful_steps=s.num_unsuccessful_steps,
-                    iterations=rows, t_evaluate=s.t_evaluate, t_linear=s.t_linear, t_total=s.t_total)
+                    iterations=rows, t_evaluate=s.t_evaluate, t_linear=s.t_linear, t_total=s.t_total, fixed_cost=s.fixed_cost)
 
 
 # ---- helper conversions (Eigen semantics) -----------------------------------------------

@@ -29,6 +29,7 @@ struct pgo_summary {
   double initial_cost, final_cost;
   int termination, num_successful_steps, num_unsuccessful_steps, num_iterations;
   double t_evaluate, t_linear, t_total;
+  double fixed_cost;
 };
 struct pgo_iteration {  // one row of Ceres' minimizer_progress_to_stdout table
   int iteration; double cost, cost_change, gradient_max_norm, gradient_norm, step_norm, relative_decrease, trust_region_radius;
@@ -138,7 +139,7 @@ int pgo_solve(void* h, const pgo_options* po, pgo_summary* out, pgo_iteration* i
   Summary s = S.solve();
   if (out) { out->initial_cost = s.initial_cost; out->final_cost = s.final_cost; out->termination = s.termination;
     out->num_successful_steps = s.num_successful_steps; out->num_unsuccessful_steps = s.num_unsuccessful_steps;
-    out->num_iterations = (int)s.iterations.size(); out->t_evaluate = s.t_evaluate; out->t_linear = s.t_linear; out->t_total = s.t_total; }
+    out->num_iterations = (int)s.iterations.size(); out->t_evaluate = s.t_evaluate; out->t_linear = s.t_linear; out->t_total = s.t_total; out->fixed_cost = s.fixed_cost; }
   for (int i = 0; iters && i < (int)s.iterations.size() && i < iters_cap; ++i) {
     const IterRecord& r = s.iterations[i];
     iters[i] = pgo_iteration{r.iteration, r.cost, r.cost_change, r.gradient_max_norm, r.gradient_norm, r.step_norm, r.relative_decrease,

@@ -53,6 +53,7 @@ struct IterRecord {
 
 struct Summary {
   double initial_cost = 0, final_cost = 0;
+  double fixed_cost = 0;   // ceres::Solver::Summary::fixed_cost: residual blocks whose parameter blocks are all constant
   int termination = NO_CONVERGENCE;
   int num_successful_steps = 0, num_unsuccessful_steps = 0;
   std::string message;
@@ -149,6 +150,16 @@ struct Problem {
       for (int k = 0; k < K; ++k) if (is_const(rn[k])) for (int i = 0; i < 36; ++i) J_r[36 * (size_t)k + i] = 0.0;
     }
     return 0.5 * cost;
+  }
+  // Cost of the residual blocks Ceres' preprocessor removes from the reduced program because every parameter block they
+  // bind is constant (Program::RemoveFixedBlocks): odometry blocks between two constant keyframes and regularisers on a
+  // constant keyframe — a loop block always keeps its free switch.  From the residuals of the last full evaluation.
+  double fixed_cost_of_current_residuals() const {
+    if (node_const.empty()) return 0.0;
+    double c = 0.0;
+    for (int e = 0; e < n_odom(); ++e) if (is_const(oc1[e]) && is_const(oc2[e])) for (int i = 0; i < 6; ++i) c += r_o[6 * (size_t)e + i] * r_o[6 * (size_t)e + i];
+    for (int k = 0; k < n_reg(); ++k) if (is_const(rn[k])) for (int i = 0; i < 6; ++i) c += r_r[6 * (size_t)k + i] * r_r[6 * (size_t)k + i];
+    return 0.5 * c;
   }
 };
 
@@ -385,11 +396,13 @@ struct Solver {
     double radius = opt.initial_trust_region_radius, decrease_factor = 2.0; bool reuse_diagonal = false;
     int num_consecutive_invalid_steps = 0;
     double x_norm = ambient_norm(xq, xt, xs);
-    double x_cost = 0, grad_max = 0, grad_norm = 0;
+    double x_cost = 0, grad_max = 0, grad_norm = 0, fixed_cost = 0;
 
     auto evaluate_gradient_and_jacobian = [&](int iteration) {
       double te = wall_seconds();
       x_cost = P.evaluate(xq.data(), xt.data(), xs.data(), true, opt);
+      if (iteration == 0) fixed_cost = P.fixed_cost_of_current_residuals();   // constant blocks do not move: evaluated once, as Ceres does
+      x_cost -= fixed_cost;                                                   // the minimiser sees the reduced program's cost
       compute_gradient();
       if (iteration == 0) {
         if (opt.jacobi_scaling) {
@@ -409,7 +422,7 @@ struct Solver {
 
     // ---- IterationZero
     evaluate_gradient_and_jacobian(0);
-    sum.initial_cost = x_cost;
+    sum.initial_cost = x_cost + fixed_cost; sum.fixed_cost = fixed_cost;
     IterRecord it{}; it.iteration = 0; it.cost = x_cost; it.gradient_max_norm = grad_max; it.gradient_norm = grad_norm;
     it.step_is_valid = 1; it.step_is_successful = 1; it.trust_region_radius = radius;
 
@@ -454,7 +467,7 @@ struct Solver {
       // ---- ComputeCandidatePointAndEvaluateCost
       plus(xq, xt, xs, dp, ds, cq, ct, cs);
       double te = wall_seconds();
-      double candidate_cost = P.evaluate(cq.data(), ct.data(), cs.data(), false, opt, /*keep_residuals=*/false);
+      double candidate_cost = P.evaluate(cq.data(), ct.data(), cs.data(), false, opt, /*keep_residuals=*/false) - fixed_cost;
       sum.t_evaluate += wall_seconds() - te;
       if (!std::isfinite(candidate_cost)) candidate_cost = std::numeric_limits<double>::max();
 
@@ -483,7 +496,7 @@ struct Solver {
       }
     }
     P.q = xq; P.t = xt; P.sw = xs;
-    sum.final_cost = x_cost;
+    sum.final_cost = x_cost + fixed_cost;
     sum.t_total = wall_seconds() - t0;
     return sum;
   }

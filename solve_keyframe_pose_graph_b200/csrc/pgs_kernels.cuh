@@ -711,6 +711,24 @@ __global__ void scaling_kernel(int N, int first_border, int n_loop, const double
   }
 }
 
+// ------------------------------------------------------------------ Summary::fixed_cost
+// 1/2 sum |r|^2 over the residual blocks whose parameter blocks are all constant (odometry blocks between two constant
+// keyframes, regularisers on a constant keyframe): Ceres' preprocessor takes them out of the reduced program and reports
+// their cost as Summary::fixed_cost.  One block, fixed summation order.
+__global__ void fixed_cost_kernel(int n_fo, const int* __restrict__ fo, const double* __restrict__ o_r, int n_fr, const int* __restrict__ fr,
+                                  const double* __restrict__ g_r, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_fo; i += blockDim.x) { const int e = fo[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double v = ro(o_r, e, k); s += v * v; } }
+  for (int i = threadIdx.x; i < n_fr; i += blockDim.x) { const int k0 = fr[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double v = g_r[6 * (size_t)k0 + k]; s += v * v; } }
+  const double t = block_sum(s, sm);
+  if (threadIdx.x == 0) *out = 0.5 * t;
+}
+
 // ------------------------------------------------------------------ re-layout for the C-ABI (parity / debugging path)
 // tiled SoA (sorted edge order) -> caller order, row-major r[E][R], J[E][R][C] with the two sides interleaved per row
 __global__ void export_odom_kernel(int n, const int* __restrict__ perm, const double* __restrict__ r, const double* __restrict__ J,

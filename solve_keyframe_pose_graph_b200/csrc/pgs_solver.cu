@@ -249,6 +249,15 @@ int Solver::finalize() {
   // a block is updated (and counted in the step / gradient norms) if some residual block uses it and it is not constant:
   // Ceres' reduced program drops unused and constant parameter blocks alike
   for (int i = 0; i < N; ++i) h_node_used[i] = (inc_ptr[i + 1] > inc_ptr[i] || (i < (int)forced_used.size() && forced_used[i])) && !h_node_const[i];
+  {
+    std::vector<int> fo, fr;
+    for (int e = 0; e < Eo; ++e) if (h_node_const[oidx[e].x] && h_node_const[oidx[e].y]) fo.push_back(e);
+    for (int k = 0; k < K; ++k) if (h_node_const[r_node[k]]) fr.push_back(k);
+    n_fixed_o = (int)fo.size(); n_fixed_r = (int)fr.size();
+    if (fo.empty()) fo.push_back(0);
+    if (fr.empty()) fr.push_back(0);
+    CU(d_fixed_o.upload(fo, stream)); CU(d_fixed_r.upload(fr, stream));
+  }
   // 3. distinct node pairs (hi, lo) and their edges (edge<<2 | kind<<1 | c1_is_hi)
   std::vector<std::pair<uint64_t, int>> keyed; keyed.reserve((size_t)Eo + El);
   auto key_of = [](int c1, int c2) { const uint64_t hi = (uint64_t)std::max(c1, c2), lo = (uint64_t)std::min(c1, c2); return (hi << 32) | lo; };
@@ -729,9 +738,9 @@ int Solver::time_sweep(int mode, int reps, int flush_l2, double* ms, double* ms_
 
 int Solver::time_stream_write(int64_t bytes, int reps, int flush_l2, double* ms) {
   CU(cudaSetDevice(dev));
-  if (bytes <= 0 || (size_t)bytes > FLUSH_DOUBLES * sizeof(double)) return fail(PGS_ERR_INVALID_ARGUMENT, "time_stream_write: bytes must be in (0, 384 MiB]");
+  if (bytes <= 0 || bytes > ((int64_t)16 << 30)) return fail(PGS_ERR_INVALID_ARGUMENT, "time_stream_write: bytes must be in (0, 16 GiB]");
   if (reps < 1) reps = 1;
-  CU(d_flush.resize(FLUSH_DOUBLES));
+  CU(d_flush.resize(std::max(FLUSH_DOUBLES, (size_t)(bytes + 7) / 8)));
   double total = 0.0;
   for (int i = 0; i < reps; ++i) {
     if (flush_l2) if (int rc = flush_l2_now()) return rc;
@@ -801,7 +810,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
   double radius = opt.initial_trust_region_radius, decrease_factor = 2.0;
   bool reuse_diagonal = false;
   int invalid = 0, n_succ = 0, n_unsucc = 0, lin_total = 0;
-  double x_cost = 0, grad_max = 0, grad_norm = 0;
+  double x_cost = 0, grad_max = 0, grad_norm = 0, fixed_cost = 0;
   int termination = PGS_NO_CONVERGENCE;
   int rc = PGS_OK;
 
@@ -826,14 +835,20 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
       if (int r = comm->allreduce_sum(d_scal.p + L_DIFF2, 1, stream, &err)) return r;
       if (int r = comm->allreduce_max(d_scal.p + L_MAX, 1, stream, &err)) return r;
     }
+    if (iteration == 0) {
+      // Summary::fixed_cost: the blocks that bind constant keyframes only do not move; evaluated once, as Ceres does
+      fixed_cost_kernel<<<1, 256, 0, stream>>>(n_fixed_o, d_fixed_o.p, d_or.p, n_fixed_r, d_fixed_r.p, d_gr.p, d_scal.p + L_FIXED);
+      if (comm) if (int r = comm->allreduce_sum(d_scal.p + L_FIXED, 1, stream, &err)) return r;
+    }
     ms_asm += toc();
     if (int r = read_scalars(L_NSCAL)) return r;
-    x_cost = h_scal[L_COST]; grad_norm = std::sqrt(h_scal[L_DIFF2]); grad_max = h_scal[L_MAX];
+    if (iteration == 0) fixed_cost = h_scal[L_FIXED];
+    x_cost = h_scal[L_COST] - fixed_cost; grad_norm = std::sqrt(h_scal[L_DIFF2]); grad_max = h_scal[L_MAX];   // the minimiser sees the reduced program's cost
     return PGS_OK;
   };
 
   if ((rc = eval_grad_jac(0))) return rc;
-  const double initial_cost = x_cost;
+  const double initial_cost = x_cost + fixed_cost;
   pgs_iteration it{}; it.iteration = 0; it.cost = x_cost; it.gradient_max_norm = grad_max; it.gradient_norm = grad_norm;
   it.step_is_valid = 1; it.step_is_successful = 1;
 
@@ -882,7 +897,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
       // model change, candidate cost, step norms and the pivot flags, summed over the ranks
       if (comm) if ((rc = comm->allreduce_sum(d_scal.p + L_MCC, L_FAIL - L_MCC + 1, stream, &err))) return rc;
       if ((rc = read_scalars(L_NSCAL))) return rc;
-      mcc = h_scal[L_MCC]; cand_cost = h_scal[L_CCOST]; diff2 = h_scal[L_DIFF2]; x2 = h_scal[L_X2];
+      mcc = h_scal[L_MCC]; cand_cost = h_scal[L_CCOST] - fixed_cost; diff2 = h_scal[L_DIFF2]; x2 = h_scal[L_X2];
       step_ok = std::isfinite(mcc) && std::isfinite(diff2) && mcc > 0.0;
       if (sharded && h_scal[L_FAIL] != 0.0) step_ok = false;   // some chain (of some rank) hit a non-positive pivot
     }
@@ -921,7 +936,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
   CU(cudaEventRecord(ev_t1, stream)); CU(cudaEventSynchronize(ev_t1));
   float total_ms = 0; CU(cudaEventElapsedTime(&total_ms, ev_t0, ev_t1));
   if (sum) {
-    sum->initial_cost = initial_cost; sum->final_cost = x_cost; sum->termination = termination;
+    sum->initial_cost = initial_cost; sum->final_cost = x_cost + fixed_cost; sum->termination = termination;
     sum->num_successful_steps = n_succ; sum->num_unsuccessful_steps = n_unsucc; sum->num_iterations = (int)rows.size();
     sum->linear_solver_iterations = lin_total; sum->ms_sweep = ms_sweep; sum->ms_assemble = ms_asm; sum->ms_linear_solve = ms_lin; sum->ms_total = total_ms;
     sum->factor_nnz = use_pcg() ? 0 : factor_nnz;
@@ -930,7 +945,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     sum->factor_flops = use_pcg() ? 0.0 : est_flops;
     sum->max_linear_backward_error = -1.0;
     for (double e : backward_error) sum->max_linear_backward_error = std::max(sum->max_linear_backward_error, e);
-    sum->fixed_cost = 0.0;
+    sum->fixed_cost = fixed_cost;
     sum->ms_comm = ms_comm;
   }
   for (int i = 0; iters && i < (int)rows.size() && i < cap; ++i) iters[i] = rows[i];

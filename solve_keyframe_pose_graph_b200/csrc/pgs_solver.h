@@ -43,7 +43,7 @@ static constexpr int MAX_GRID = 2048;
 // slots of the small device/pinned scalar array.  L_MCC..L_FAIL are contiguous: the multi-GPU loop sums them
 // over the ranks with one small all-reduce
 enum { PGS_PLAIN_CHAIN = 1 };   // internal: solve_dist found nothing to split, the caller solves on its own handle
-enum { L_COST = 8, L_MCC = 9, L_DIFF2 = 10, L_X2 = 11, L_CCOST = 12, L_FAIL = 13, L_MAX = 14, L_RES = 16, L_NSCAL = 32 };
+enum { L_COST = 8, L_MCC = 9, L_DIFF2 = 10, L_X2 = 11, L_CCOST = 12, L_FAIL = 13, L_MAX = 14, L_FIXED = 15, L_RES = 16, L_NSCAL = 32 };
 
 class Solver {
  public:
@@ -175,6 +175,7 @@ class Solver {
   std::vector<ChainState> cstate;
   cudaEvent_t ev_fork = nullptr;
   DBuf<int> d_border_gpos; DBuf<char> d_node_counted;
+  DBuf<int> d_fixed_o, d_fixed_r; int n_fixed_o = 0, n_fixed_r = 0;   // residual blocks whose parameter blocks are all constant (Summary::fixed_cost)
   DBuf<const int*> d_flag_ptrs; bool flag_ptrs_ready = false;
   std::vector<double> backward_error;    // per linear solve of the last LM run: ||b - A y|| / ||b||
   void release_chains();

@@ -94,3 +94,25 @@ def test_full_size_solve_two_chains_vs_one_chain_and_pcg_step(config):
     assert iters > 0
     assert np.abs(dp - dp2).max() <= 1e-6 * np.abs(dp).max() and (np.abs(ds - ds2).max() <= 1e-6 * max(np.abs(ds).max(), 1e-300) if len(ds) else True)
     assert abs(mcc - mcc2) <= 1e-9 * abs(mcc)
+
+
+C3_TIGHT = dict(odom_sigma_t=0.002, odom_sigma_r=0.0001, loop_gap_max=200)
+
+
+def test_config3_tight_closures_survive_and_match_the_oracle():
+    """Config 3's recipe with odometry drift that stays under the switch function's cliff (inlier |e|^2 < 1/8 at the
+    initial guess): every inlier closure stays switched on, every gross outlier goes off — so "same switch
+    states" compares two solvers that both USE the closures (plain config 3 integrates drift over up to 2000 keyframes
+    and discards half of its inliers).  2000 nodes, 600 closures (10 % outliers), against the oracle."""
+    p = problems.build_problem(3, n_nodes=2000, n_loop=600, **C3_TIGHT)
+    so, qo, to, swo = _oracle(p)
+    out = p["lout"].astype(bool)
+    assert out.sum() > 30 and (swo[~out] > 0.5).mean() > 0.95 and (swo[out] < 0.5).all()
+    for chains in (1, 2):
+        s, q, t, sw, be = _gpu(p, chains=chains)
+        assert [r["step_is_successful"] for r in s["iterations"]] == [r["step_is_successful"] for r in so["iterations"]]
+        assert np.allclose([r["cost"] for r in s["iterations"]], [r["cost"] for r in so["iterations"]], rtol=1e-6)
+        assert abs(s["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]
+        assert np.abs(t - to).max() < 1e-5 and rot_angle_between(q, qo).max() < 1e-4
+        assert np.array_equal(sw > 0.5, swo > 0.5) and np.abs(sw - swo).max() < 1e-6
+        assert be.max() < 1e-9

@@ -147,6 +147,13 @@ def test_constant_parameter_blocks_match_oracle(solver):
     for a, b in zip(ss["iterations"], so["iterations"]):
         assert a["step_is_successful"] == b["step_is_successful"]
         assert abs(a["cost"] - b["cost"]) <= 1e-6 * max(1e-12, abs(b["cost"]))
+    # Summary::fixed_cost: the odometry blocks among keyframes 0..69 (and the regulariser on keyframe 0) bind constant blocks
+    # only; Ceres takes them out of the reduced program — the iteration table above is without them, the summary adds them back
+    both = (g["oc1"] < 70) & (g["oc2"] < 70)
+    fc = 0.5 * (np.sum(eo["r_o"][both] ** 2) + np.sum(eo["r_r"] ** 2))
+    assert fc > 0 and abs(so["fixed_cost"] - fc) <= 1e-12 * fc and abs(ss["fixed_cost"] - fc) <= 1e-12 * fc
+    assert abs(ss["initial_cost"] - eo["cost"]) <= 1e-12 * eo["cost"] and abs(ss["iterations"][0]["cost"] + fc - eo["cost"]) <= 1e-12 * eo["cost"]
+    assert abs(ss["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
     qo, to = O.poses(); qs, ts = S.poses()
     fixed = np.r_[0:70, 100:103]
     assert np.array_equal(ts[fixed], g["t"][fixed]) and np.array_equal(qs[fixed], g["q"][fixed])      # bit for bit

@@ -186,3 +186,18 @@ def test_rejected_steps_leave_the_residuals_of_the_current_point_in_place():
     rejected = cost[3:8]
     assert np.all(rejected < 10 * x_cost) and rejected[-1] < rejected[0]
     assert cost[-1] < 0.1 * x_cost
+
+
+def test_fixed_cost_follows_ceres_reduced_program():
+    """Residual blocks whose parameter blocks are all constant leave the reduced program: Summary::fixed_cost holds their
+    cost, the iteration table is without it, initial/final cost include it (ceres/solver.h, Program::RemoveFixedBlocks)."""
+    g = random_graph(80, 2, 10, seed=33)
+    P = load_oracle(g); P.set_constant_nodes(0, 30)
+    e = P.evaluate(autodiff=True)
+    both = (g["oc1"] < 30) & (g["oc2"] < 30)
+    fc = 0.5 * (np.sum(e["r_o"][both] ** 2) + np.sum(e["r_r"] ** 2))          # the regulariser sits on keyframe 0
+    s = P.solve()
+    assert fc > 0 and abs(s["fixed_cost"] - fc) <= 1e-13 * fc
+    assert abs(s["initial_cost"] - e["cost"]) <= 1e-13 * e["cost"] and abs(s["iterations"][0]["cost"] - (e["cost"] - fc)) <= 1e-12 * e["cost"]
+    assert abs(s["final_cost"] - (s["iterations"][-1]["cost"] + fc)) <= 1e-12 * s["final_cost"] or not s["iterations"][-1]["step_is_successful"]
+    Q = load_oracle(g); assert Q.solve()["fixed_cost"] == 0.0
