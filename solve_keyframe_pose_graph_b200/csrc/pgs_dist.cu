@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "host/partition.h"
 #include "pgs_skyline.h"
@@ -169,10 +170,23 @@ int Solver::solve_chains() {
   // 1. the chains, concurrently.  Pivot failures are not checked here: the flags travel with the scalar all-reduce
   //    of the LM step so that every rank takes the same branch.
   CU(cudaEventRecord(ev_fork, stream));
-  for (ChainState& cs : cstate) {
-    CU(cudaStreamWaitEvent(cs.st, ev_fork, 0));
-    if (int rc = skyline_factor(cs.f, d_Ad.p, d_Ao.p, d_b.p, &err)) return rc;
-    CU(cudaEventRecord(cs.done, cs.st));
+  {
+    // A chain is ~4 launches and ~8 event operations per panel: one host thread per chain, or the second chain's first
+    // kernel would be enqueued only after all of the first chain's and the chains would hardly overlap on the device.
+    std::vector<int> rcs(cstate.size(), PGS_OK); std::vector<std::string> errs(cstate.size());
+    auto enqueue = [&](size_t c) {
+      ChainState& cs = cstate[c];
+      cudaSetDevice(dev);
+      cudaError_t e = cudaStreamWaitEvent(cs.st, ev_fork, 0);
+      if (e != cudaSuccess) { rcs[c] = PGS_ERR_CUDA; errs[c] = cudaGetErrorString(e); return; }
+      rcs[c] = skyline_factor(cs.f, d_Ad.p, d_Ao.p, d_b.p, &errs[c]);
+      if (rcs[c] == PGS_OK && cudaEventRecord(cs.done, cs.st) != cudaSuccess) { rcs[c] = PGS_ERR_CUDA; errs[c] = "cudaEventRecord"; }
+    };
+    std::vector<std::thread> th;
+    for (size_t c = 1; c < cstate.size(); ++c) th.emplace_back(enqueue, c);
+    enqueue(0);
+    for (std::thread& t : th) t.join();
+    for (size_t c = 0; c < cstate.size(); ++c) if (rcs[c] != PGS_OK) { err = errs[c]; return rcs[c]; }
   }
   if (sky_border) if (int rc = skyline_begin_border(sky_border, &err)) return rc;
   for (ChainState& cs : cstate) CU(cudaStreamWaitEvent(stream, cs.done, 0));

@@ -33,6 +33,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "../../include/pgs.h"
@@ -47,6 +49,7 @@ constexpr int UM = 128, UN = 64;  // update tiles: rows x cols
 constexpr int KC = 32;            // update K chunk
 constexpr int LDK = KC + 4;       // 36 doubles = 72 words = 8 mod 32: conflict-free DMMA fragment loads, 16-B aligned rows
 constexpr int NEV = 8;            // event ring
+constexpr int XP_RING = 4;        // packed panel copies in flight: trsm(d) cannot run before rest(d-2) is done
 
 struct SkylineFactor {
   int N = 0, n = 0, D = 0;         // nodes, scalars, panels
@@ -66,7 +69,11 @@ struct SkylineFactor {
   double* xacc = nullptr;          // [n] backward-solve accumulator
   int* fail = nullptr; int* h_fail = nullptr;
   int* pair_hi = nullptr; int* pair_lo = nullptr; int n_pairs = 0;
-  double* zeros = nullptr;         // PW zeros: what the update's bulk copies read for rows that do not exist
+  // Packed copy of the current panel's X = A[R, panel] Linv^T for the trailing update (ring over panels): layout
+  // [K chunk][list position][LDK] with the shared-memory padding already in place, so that a tile's operand chunk — 128 or 64
+  // consecutive list positions — is ONE contiguous block a single bulk copy can fetch; rinfo = per list position the row index
+  // (-1 past the end of the list) and the offset of (row, column 0) in val.
+  double* xp = nullptr; long long* rinfo = nullptr; long long xp_stride = 0, rinfo_stride = 0; int rpad = 0;
   int* node_src = nullptr; int* pair_src = nullptr;   // optional: factor node -> row of Ad / b (-1 = none), factor pair -> row of Ao
   long long tail = 0;              // extra doubles behind the envelope (travel with it in the border all-reduce)
 };
@@ -76,7 +83,7 @@ struct SkylineFactor {
 void skyline_destroy(SkylineFactor* f) {
   if (!f) return;
   cudaFree(f->val); cudaFree(f->ptr); cudaFree(f->start); cudaFree(f->rows_ptr); cudaFree(f->rows_idx); cudaFree(f->dinv);
-  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched); cudaFree(f->node_src); cudaFree(f->pair_src); cudaFree(f->zeros);
+  cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched); cudaFree(f->node_src); cudaFree(f->pair_src); cudaFree(f->xp); cudaFree(f->rinfo);
   if (f->h_fail) cudaFreeHost(f->h_fail);
   for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); if (f->ev_c[i]) cudaEventDestroy(f->ev_c[i]); }
   if (f->ev_fork) cudaEventDestroy(f->ev_fork);
@@ -140,8 +147,10 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
   if ((e = cudaMalloc((void**)&f->dinv, sizeof(double) * (size_t)std::max(D, 1) * PW * PW)) != cudaSuccess) return bad(e, "dinv");
   if ((e = cudaMalloc((void**)&f->xacc, sizeof(double) * (size_t)std::max(D, 1) * PW)) != cudaSuccess) return bad(e, "xacc");
   if ((e = cudaMalloc((void**)&f->fail, sizeof(int))) != cudaSuccess) return bad(e, "fail");
-  if ((e = cudaMalloc((void**)&f->zeros, sizeof(double) * PW)) != cudaSuccess) return bad(e, "zeros");
-  if ((e = cudaMemsetAsync(f->zeros, 0, sizeof(double) * PW, stream)) != cudaSuccess) return bad(e, "zeros");
+  f->rpad = ((f->max_rows + UM - 1) / UM) * UM;
+  f->xp_stride = (long long)(PW / KC) * f->rpad * LDK; f->rinfo_stride = 2LL * f->rpad;
+  if ((e = cudaMalloc((void**)&f->xp, sizeof(double) * (size_t)std::max<long long>(XP_RING * f->xp_stride, 1))) != cudaSuccess) return bad(e, "xp");
+  if ((e = cudaMalloc((void**)&f->rinfo, sizeof(long long) * (size_t)std::max<long long>(XP_RING * f->rinfo_stride, 1))) != cudaSuccess) return bad(e, "rinfo");
   if ((e = cudaMalloc((void**)&f->sched, 4 * sizeof(unsigned int))) != cudaSuccess) return bad(e, "sched");
   if ((e = cudaMemsetAsync(f->sched, 0, 4 * sizeof(unsigned int), stream)) != cudaSuccess) return bad(e, "sched");
   if ((e = cudaMallocHost((void**)&f->h_fail, sizeof(int))) != cudaSuccess) return bad(e, "h_fail");
@@ -465,7 +474,8 @@ __global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, int prev, c
 // triangular, so output columns j0..j0+7 only need k <= j0+7.
 __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const long long* __restrict__ ptr, const int* __restrict__ start,
                                                           const int* __restrict__ rows_ptr, const int* __restrict__ rows_idx,
-                                                          const double* __restrict__ dinv, double* __restrict__ val) {
+                                                          const double* __restrict__ dinv, double* __restrict__ val,
+                                                          double* __restrict__ xp, long long* __restrict__ rinfo, int rpad) {
   extern __shared__ __align__(16) double sm[];
   double* Li = sm;                    // [PW][LDT]  Linv
   double* A = sm + PW * LDT;          // [TR][LDT]
@@ -474,11 +484,20 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
   const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
   const int row0 = blockIdx.x * TR;
   if (tid < TR) {
-    long long b = -1;
-    if (row0 + tid < nr) { const int r = rows_idx[rb + row0 + tid]; b = ptr[r] + (c0 - start[r]); }
+    long long b = -1; int r = -1;
+    if (row0 + tid < nr) { r = rows_idx[rb + row0 + tid]; b = ptr[r] + (c0 - start[r]); }
     rbase[tid] = b;
+    // row table of the packed copy: (row index or -1, offset of (row, column 0)); CTAs past the end of the list only pad
+    rinfo[2 * (size_t)(row0 + tid)] = r; rinfo[2 * (size_t)(row0 + tid) + 1] = b >= 0 ? b - c0 : 0;
   }
   __syncthreads();
+  if (row0 >= nr) {   // padding rows of the packed copy (the list is padded to whole 128-row tiles): zeros
+    for (int e = tid; e < TR * (PW / 2); e += blockDim.x) {
+      const int i = e / (PW / 2), c = 2 * (e % (PW / 2));
+      *reinterpret_cast<double2*>(xp + ((size_t)(c / KC) * rpad + row0 + i) * LDK + c % KC) = make_double2(0.0, 0.0);
+    }
+    return;
+  }
   const double* dsrc = dinv + (size_t)d * PW * PW;
   for (int e = tid; e < TR * (PW / 2); e += blockDim.x) {
     const int i = e / (PW / 2), j2 = e % (PW / 2);
@@ -515,10 +534,15 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const long long b = rbase[16 * wm + 8 * i + g];
-    if (b < 0) continue;
+    const int rl = 16 * wm + 8 * i + g;
+    const long long b = rbase[rl];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) *reinterpret_cast<double2*>(val + b + 24 * wn + 8 * j + 2 * t) = make_double2(acc[i][j][0], acc[i][j][1]);
+    for (int j = 0; j < 3; ++j) {
+      const int c = 24 * wn + 8 * j + 2 * t;
+      const double2 v = b >= 0 ? make_double2(acc[i][j][0], acc[i][j][1]) : make_double2(0.0, 0.0);   // rows past the end of the list: A was zero-filled
+      if (b >= 0) *reinterpret_cast<double2*>(val + b + c) = v;
+      *reinterpret_cast<double2*>(xp + ((size_t)(c / KC) * rpad + row0 + rl) * LDK + c % KC) = v;
+    }
   }
 }
 
@@ -630,11 +654,14 @@ __global__ void __launch_bounds__(256, 2) sky_update_kernel(int d, int n, int sk
 #pragma unroll
       for (int j = 0; j < FN; ++j) {
         const int c = cidx[j], r = ridx[i];
-        const bool pair = c >= 0 && c + 1 <= r, diag = c >= 0 && c == r;
-        const double* p = val + ((pair || diag) ? rowoff[i] + c : 0);
+        // c <= r covers the pair (c, c + 1) below the diagonal and the diagonal element c == r; there the second slot is
+        // (r, r + 1), which exists in the row's storage (c is even, a node's six scalars never straddle a panel) and is
+        // never stored back.  ONE load per fragment: a second, differently predicated load into the same registers
+        // would have to wait for the first (scoreboard), serialising sixteen round trips to L2 per tile.
+        const bool any = c >= 0 && c <= r;
+        const double* p = val + (any ? rowoff[i] + c : 0);
         acc[i][j][0] = 0.0; acc[i][j][1] = 0.0;
-        ldg128_if(acc[i][j][0], acc[i][j][1], p, pair);
-        ldg64_if(acc[i][j][0], p, diag);
+        ldg128_if(acc[i][j][0], acc[i][j][1], p, any);
       }
     UPD_STAMP(2);
 #pragma unroll
@@ -681,19 +708,20 @@ __global__ void __launch_bounds__(256, 2) sky_update_kernel(int d, int n, int sk
 
 // ------------------------------------------------------------------------------------------------ update, persistent pipeline
 // The same tiles as sky_update_kernel, as a persistent software pipeline (one 512-thread CTA per SM, 166 KB of shared
-// memory; sixteen warps, because with the fragment loads in the loop eight warps reach only half of the DMMA rate —
-// measured: 12.5 us per 128x64x96 tile against 6.3 us at the pipe's peak): a CTA walks its tiles T = blockIdx.x, blockIdx.x + gridDim.x, ... and treats their K chunks as ONE stream
-// through a 3-stage ring.  As soon as every warp is done with chunk ch of tile t, chunk ch of tile t+1 is requested into
-// the same stage — one bulk asynchronous copy (cp.async.bulk, 256 B = one row x 32 columns) per row, completion counted
-// in bytes on the stage's mbarrier — so the operands of the next tile arrive while this one is being multiplied, and the
-// load phase that left every CTA of the one-tile kernel idle for a third of its life (tools/upd_lab.cu) disappears.
-// A_old is no longer preloaded into the accumulators: its predicated loads go into registers of their own at the top of
-// the tile, land during the multiply, and the epilogue stores A_old - X X^T.
-// Rows that do not exist (past the end of the row list; the rhs row as a column) are fed from a buffer of zeros.
+// memory): a CTA walks its tiles T = blockIdx.x, blockIdx.x + gridDim.x, ... and treats their K chunks as ONE stream
+// through a 3-stage ring.  The operands come from the packed copy of X that trsm leaves behind ([K chunk][list position]
+// [LDK], shared-memory padding included): a tile's chunk is two contiguous blocks, 128 and 64 list positions, fetched
+// by TWO bulk asynchronous copies (cp.async.bulk, 36 KB and 18 KB, completion counted in bytes on the stage's
+// mbarrier).  As soon as every warp is done with chunk ch of tile t, chunk ch of tile t+1 is requested into the same
+// stage, so the operands of the next tile arrive while this one is being multiplied.  (One bulk copy per ROW and chunk
+// straight from the envelope — 576 copies of 256 B per tile — kept the tile at twice its multiply time: measured
+// 12.3 us against the 6.3 us the same loop takes from resident shared memory, tools/mma_lab.cu.)
+// A_old is not preloaded into the accumulators: its loads go into registers of their own, one fragment per k-step of the
+// middle chunk, land during the multiply, and the epilogue stores A_old - X X^T.  Sixteen warps, each a 32 x 16 piece
+// of the 128 x 64 tile, synchronised only through the ring (no block-wide barrier inside the loop).
 constexpr int WS_THREADS = 512;
 constexpr int WS_NS = PW / KC;                 // ring stages == K chunks of a tile
 static_assert(WS_NS == 3, "stage index == chunk index");
-struct WsTable { long long abase[UM]; long long bbase[UN]; int arow[UM]; int bcol[UN]; };
 constexpr int WS_STAGE = (UM + UN) * LDK;      // doubles per stage
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -717,90 +745,94 @@ __device__ __forceinline__ void upd_tile_of(int part, int T, int& ti, int& tj) {
   tj = 2 + (T - ti * (ti - 1));
 }
 
+#ifdef SKY_WS_CLOCKS   // tools/ws_lab.cu: cycle stamps of thread 0 of the first CTAs of panel SKY_WS_CLOCKS (rest kernel)
+__device__ long long g_ws_clk[64][48];
+#define WS_STAMP(i) do { if (PART == 1 && d == SKY_WS_CLOCKS && threadIdx.x == 0 && blockIdx.x < 64 && (i) < 48) g_ws_clk[blockIdx.x][i] = clock64(); } while (0)
+#else
+#define WS_STAMP(i) do { } while (0)
+#endif
 template <int PART>
-__global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int n, int skip_below, int Tr, int Tc, int n_tiles,
-                                                                      const long long* __restrict__ ptr, const int* __restrict__ start,
-                                                                      const int* __restrict__ rows_ptr, const int* __restrict__ rows_idx,
-                                                                      double* __restrict__ val, const double* __restrict__ zeros) {
-  constexpr int WARPS_M = 4, WARPS_N = 4;
+__global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int n, int skip_below, int Tr, int Tc, int n_tiles, int rpad,
+                                                                      const double* __restrict__ xp, const long long* __restrict__ rinfo,
+                                                                      double* __restrict__ val) {
+  constexpr int WARPS_M = 4, WARPS_N = 4, NWARPS = WARPS_M * WARPS_N;
   constexpr int WTM = UM / WARPS_M, WTN = UN / WARPS_N, FM = WTM / 8, FN = WTN / 8;
-  constexpr unsigned STAGE_BYTES = (UM + UN) * KC * sizeof(double);
+  static_assert(FM * FN == KC / 4, "one A_old fragment load per k-step of a chunk");
+  constexpr unsigned A_BYTES = UM * LDK * sizeof(double), B_BYTES = UN * LDK * sizeof(double), TAB_BYTES = 2 * (UM + UN) * sizeof(long long);
   extern __shared__ __align__(128) unsigned char ws_smem[];
   double* ring = reinterpret_cast<double*>(ws_smem);                                  // [WS_NS][UM + UN][LDK]
-  WsTable* tab = reinterpret_cast<WsTable*>(ring + WS_NS * WS_STAGE);                 // [2]
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(tab + 2);          // [WS_NS]
+  long long* tab = reinterpret_cast<long long*>(ring + WS_NS * WS_STAGE);             // [UM + UN][2] row table of the current tile
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(tab + 2 * (UM + UN));   // [WS_NS]
+  int* done = reinterpret_cast<int*>(full + WS_NS);                                   // [WS_NS] warps finished with the stage
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int c0 = d * PW;
-  const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
   const int g = lane >> 2, t = lane & 3;
   const int wm = wid % WARPS_M, wn = wid / WARPS_M;
+  WS_STAMP(0);
   if (tid == 0) {
-    for (int s = 0; s < WS_NS; ++s) mbar_init(full + s, 1);
+    for (int s = 0; s < WS_NS; ++s) { mbar_init(full + s, 1); done[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // row (tid < UM) or column (UM <= tid < UM + UN) entry of tile T's table, in two steps so that the two levels of
-  // dependent global loads can be issued well before their results are needed
-  auto entry_row = [&](int T) -> int {
-    int ti, tj; upd_tile_of(PART, T, ti, tj);
-    if (ti >= Tr || tj >= Tc) return -1;                // the last row tile can run past the last column tile: an all-zero tile
-    if (tid < UM) { const int ir = ti * UM + tid; return ir < nr ? rows_idx[rb + ir] : -1; }
-    if (tid < UM + UN) { const int ic = tj * UN + (tid - UM); const int c = ic < nr ? rows_idx[rb + ic] : -1; return c >= n ? -1 : c; }   // the rhs row is never a column
-    return -1;
-  };
-  auto entry_store = [&](WsTable& tb, int r) {
-    const long long base = r >= 0 ? ptr[r] + (c0 - start[r]) : -1;
-    if (tid < UM) { tb.arow[tid] = r; tb.abase[tid] = base; }
-    else if (tid < UM + UN) { tb.bcol[tid - UM] = r; tb.bbase[tid - UM] = base; }
-  };
-  auto issue = [&](const WsTable& tb, int ch) {
-    if (tid == 0) mbar_expect_tx(full + ch, STAGE_BYTES);
-    if (tid < UM + UN) {
-      const long long bo = tid < UM ? tb.abase[tid] : tb.bbase[tid - UM];
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last read through the generic proxy
-      bulk_g2s(ring + ch * WS_STAGE + tid * LDK, bo >= 0 ? (const void*)(val + bo + ch * KC) : (const void*)zeros, KC * sizeof(double), full + ch);
+  __syncthreads();
+  // chunk ch of tile (ti, tj) -> stage ch: two contiguous blocks of the packed copy; with chunk 0 also the tile's row table
+  // (row index, offset) for its 128 + 64 list positions.  Called by ONE lane.  No proxy fence: the warps' reads of the
+  // stage have returned their data (the multiplies that consumed it have been issued) before the counter that elects
+  // this lane is incremented.
+  auto issue = [&](int ti, int tj, int ch) {
+    if (tj >= Tc) tj = Tc - 1;                         // the last row tile can run past the last column tile: nothing of it is stored
+    mbar_expect_tx(full + ch, A_BYTES + B_BYTES + (ch == 0 ? TAB_BYTES : 0u));
+    bulk_g2s(ring + ch * WS_STAGE, xp + ((size_t)ch * rpad + (size_t)ti * UM) * LDK, A_BYTES, full + ch);
+    bulk_g2s(ring + ch * WS_STAGE + UM * LDK, xp + ((size_t)ch * rpad + (size_t)tj * UN) * LDK, B_BYTES, full + ch);
+    if (ch == 0) {
+      bulk_g2s(tab, rinfo + 2 * (size_t)ti * UM, 2 * UM * sizeof(long long), full + ch);
+      bulk_g2s(tab + 2 * UM, rinfo + 2 * (size_t)tj * UN, 2 * UN * sizeof(long long), full + ch);
     }
   };
   int T = blockIdx.x;
   if (T >= n_tiles) return;
-  entry_store(tab[0], entry_row(T));
-  __syncthreads();
+  int ti, tj; upd_tile_of(PART, T, ti, tj);
+  if (tid == 0) {
 #pragma unroll
-  for (int ch = 0; ch < WS_NS; ++ch) issue(tab[0], ch);
+    for (int ch = 0; ch < WS_NS; ++ch) issue(ti, tj, ch);
+  }
+  // No block-wide barrier below: a warp that is done with a stage says so on a counter and moves on; the warp that
+  // arrives last requests the stage's next contents.  Warps drift apart, so that the global loads of A_old and the
+  // stores of one warp run under the multiplies of the others instead of stopping all sixteen at once (measured in
+  // lock-step: ~4k cycles of loads + ~3k of stores around 12k cycles of DMMA per tile, tools/ws_lab.cu).
   for (int it = 0; T < n_tiles; T += gridDim.x, ++it) {
     const unsigned par = (unsigned)(it & 1);
     const int Tn = T + gridDim.x;
     const bool more = Tn < n_tiles;
-    const int r_next = more ? entry_row(Tn) : -1;       // level 1 of the next tile's table, in flight during this tile
-    mbar_wait(full + 0, par);
-    const WsTable& tb = tab[it & 1];
+    const bool live = tj < Tc;
+    int tin = 0, tjn = 0;
+    if (more) upd_tile_of(PART, Tn, tin, tjn);
     int cidx[FN], ridx[FM];
     long long rowoff[FM];
-#pragma unroll
-    for (int j = 0; j < FN; ++j) cidx[j] = tb.bcol[wn * WTN + 8 * j + 2 * t];
-#pragma unroll
-    for (int i = 0; i < FM; ++i) {
-      const int rl = wm * WTM + 8 * i + g;
-      const int r = tb.arow[rl];
-      ridx[i] = r >= skip_below ? r : -1;               // -1: no such row, or a row C(d+1) owns
-      rowoff[i] = r >= 0 ? tb.abase[rl] - c0 : 0;       // offset of (row, column 0)
-    }
-    // A_old: a lane owns two adjacent list positions (even, odd) of a row — always columns (c, c + 1), 16-byte aligned;
-    // on the diagonal (c == r) only the first of the two exists
     double cold[FM][FN][2], acc[FM][FN][2];
 #pragma unroll
     for (int i = 0; i < FM; ++i)
 #pragma unroll
-      for (int j = 0; j < FN; ++j) {
-        const int c = cidx[j], r = ridx[i];
-        const bool pair = c >= 0 && c + 1 <= r, diag = c >= 0 && c == r;
-        const double* p = val + ((pair || diag) ? rowoff[i] + c : 0);
-        cold[i][j][0] = 0.0; cold[i][j][1] = 0.0; acc[i][j][0] = 0.0; acc[i][j][1] = 0.0;
-        ldg128_if(cold[i][j][0], cold[i][j][1], p, pair);
-        ldg64_if(cold[i][j][0], p, diag);
-      }
+      for (int j = 0; j < FN; ++j) { cold[i][j][0] = 0.0; cold[i][j][1] = 0.0; acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    WS_STAMP(1 + 12 * it);
 #pragma unroll
     for (int ch = 0; ch < WS_NS; ++ch) {
-      if (ch > 0) mbar_wait(full + ch, par);
+      mbar_wait(full + ch, par);
+      if (ch == 0) {
+        // rows / columns of this thread's fragments from the tile's row table (it came with chunk 0; the next tile's
+        // table can only replace it after every warp has passed this point and finished the chunk)
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+          const long long c = live ? tab[2 * (UM + wn * WTN + 8 * j + 2 * t)] : -1;
+          cidx[j] = c >= n ? -1 : (int)c;               // the rhs row is never a column
+        }
+#pragma unroll
+        for (int i = 0; i < FM; ++i) {
+          const int rl = wm * WTM + 8 * i + g;
+          const int r = (int)tab[2 * rl];
+          ridx[i] = r >= skip_below ? r : -1;           // -1: no such row, or a row C(d+1) owns
+          rowoff[i] = tab[2 * rl + 1];
+        }
+      }
+      WS_STAMP(2 + 12 * it + 3 * ch);
       const double* a_s = ring + ch * WS_STAGE + (wm * WTM + g) * LDK + t;
       const double* b_s = ring + ch * WS_STAGE + (UM + wn * WTN + g) * LDK + t;
 #pragma unroll
@@ -810,14 +842,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int
         for (int i = 0; i < FM; ++i) a[i] = a_s[(8 * i) * LDK + k];
 #pragma unroll
         for (int j = 0; j < FN; ++j) bf[j] = b_s[(8 * j) * LDK + k];
+        if (ch == 1) {
+          // A_old, one fragment per k-step of the middle chunk (the row table has arrived by now, the values are not
+          // needed before the epilogue).  A lane owns two adjacent list positions (even, odd) of a row — always columns
+          // (c, c + 1), 16-byte aligned; c <= r covers the pair below the diagonal and the diagonal element c == r, where
+          // the second slot (r, r + 1) exists in the row's storage and is never stored back.
+          const int fi = (k / 4) / FN, fj = (k / 4) % FN;
+          const int c = cidx[fj], r = ridx[fi];
+          const bool any = c >= 0 && c <= r;
+          ldg128_if(cold[fi][fj][0], cold[fi][fj][1], val + (any ? rowoff[fi] + c : 0), any);
+        }
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
           for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
       }
-      if (ch == 0 && more) entry_store(tab[(it + 1) & 1], r_next);   // level 2 of the next tile's table
-      __syncthreads();                                  // every warp is done with stage ch (and, at ch == 0, the next table is complete)
-      if (more) issue(tab[(it + 1) & 1], ch);
+      WS_STAMP(3 + 12 * it + 3 * ch);
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = atomicAdd(done + ch, 1) == NWARPS - 1;
+        if (last) { done[ch] = 0; if (more) issue(tin, tjn, ch); }
+      }
+      WS_STAMP(4 + 12 * it + 3 * ch);
     }
 #pragma unroll
     for (int i = 0; i < FM; ++i)
@@ -829,6 +877,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int
         stg128_if(p, cold[i][j][0] - acc[i][j][0], cold[i][j][1] - acc[i][j][1], pair);
         stg64_if(p, cold[i][j][0] - acc[i][j][0], diag);
       }
+    WS_STAMP(11 + 12 * it);
+    ti = tin; tj = tjn;
   }
 }
 
@@ -934,13 +984,16 @@ __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo,
 static const size_t SM_TRSM = sizeof(double) * (PW * LDT + TR * LDT);
 static const size_t SM_UPD = sizeof(double) * (2 * (UM + UN) * LDK);   // two stages: 108 KB, two CTAs per SM
 static const size_t SM_DIAG = sizeof(double) * (2 * PW * LDT + (PW / 8) * 64 + 8 * LDT);
-static const size_t SM_UPD_WS = sizeof(double) * (size_t)WS_NS * WS_STAGE + 2 * sizeof(WsTable) + WS_NS * sizeof(unsigned long long);
+static const size_t SM_UPD_WS = sizeof(double) * (size_t)WS_NS * WS_STAGE + 2 * (UM + UN) * sizeof(long long) + WS_NS * sizeof(unsigned long long) + WS_NS * sizeof(int) + 4;
 
 static int g_rest_ctas = 132;     // grid of the persistent update kernel
 static int g_update_mode = 1;     // 0: one tile per CTA (sky_update_kernel), 1: warp-specialised persistent pipeline for rest(d), 2: for next(d) too
 static int set_attrs(std::string* err) {
-  static bool attr_set = false;
-  if (attr_set) return PGS_OK;
+  // per device (the attributes live in the context) and under a lock (chains are enqueued from several host threads)
+  static std::mutex mu; static std::set<int> ready;
+  std::lock_guard<std::mutex> lk(mu);
+  int cur = 0; cudaGetDevice(&cur);
+  if (ready.count(cur)) return PGS_OK;
   SK(cudaFuncSetAttribute(sky_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
   SK(cudaFuncSetAttribute(sky_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TRSM));
   SK(cudaFuncSetAttribute(sky_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
@@ -950,8 +1003,8 @@ static int set_attrs(std::string* err) {
   { int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     // the persistent update CTAs fill a whole SM each; a few SMs stay free for the kernels of the panel chain
     const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 8; if (g_rest_ctas < 1) g_rest_ctas = 1;
-    const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 1; }
-  attr_set = true;
+    const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 2; }
+  ready.insert(cur);
   return PGS_OK;
 }
 
@@ -997,18 +1050,19 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
     sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
     SK(cudaEventRecord(f->ev_c[d % NEV], s1));
     SK(cudaStreamWaitEvent(s2, f->ev_c[d % NEV], 0));
-    sky_trsm_kernel<<<(nr + TR - 1) / TR, 256, SM_TRSM, s2>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val);
+    double* xp = f->xp + (size_t)(d % XP_RING) * f->xp_stride; long long* rinfo = f->rinfo + (size_t)(d % XP_RING) * f->rinfo_stride;
+    sky_trsm_kernel<<<Tr * (UM / TR), 256, SM_TRSM, s2>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val, xp, rinfo, f->rpad);
     SK(cudaEventRecord(f->ev_trsm[d % NEV], s2));
     // C(d+1) applies panel d's update to its own diagonal block; past the eliminated part nobody does, so next(d) keeps it.
     // The rhs row (index n) is always live, also when the last panel is short.
     const int skip_below = (d + 1 < f->D_elim) ? std::min((d + 2) * PW, n) : 0;
     if (d > 0) SK(cudaStreamWaitEvent(s2, f->ev_rest[(d - 1) % NEV], 0));
-    if (g_update_mode >= 2) sky_update_ws_kernel<0><<<std::min(2 * Tr, g_rest_ctas), WS_THREADS, SM_UPD_WS, s2>>>(d, n, skip_below, Tr, Tc, 2 * Tr, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val, f->zeros);
+    if (g_update_mode >= 2) sky_update_ws_kernel<0><<<std::min(2 * Tr, g_rest_ctas), WS_THREADS, SM_UPD_WS, s2>>>(d, n, skip_below, Tr, Tc, 2 * Tr, f->rpad, xp, rinfo, f->val);
     else sky_update_kernel<0><<<2 * Tr, 256, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
     if (Tr > 1) {
       const int nt = Tr * (Tr - 1);
-      if (g_update_mode >= 1) sky_update_ws_kernel<1><<<std::min(nt, g_rest_ctas), WS_THREADS, SM_UPD_WS, s0>>>(d, n, skip_below, Tr, Tc, nt, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val, f->zeros);
+      if (g_update_mode >= 1) sky_update_ws_kernel<1><<<std::min(nt, g_rest_ctas), WS_THREADS, SM_UPD_WS, s0>>>(d, n, skip_below, Tr, Tc, nt, f->rpad, xp, rinfo, f->val);
       else sky_update_kernel<1><<<nt, 256, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     }
     SK(cudaEventRecord(f->ev_rest[d % NEV], s0));
