@@ -74,9 +74,9 @@ typedef struct pgs_options {
   int32_t pcg_max_iterations;               /* per linear solve */
   double pcg_tolerance;                     /* relative residual ||b-Ax|| / ||b|| */
   int32_t chains;                           /* elimination chains of the skyline solver on ONE GPU: 0 = automatic (two chains
-                                               burning from both ends of the keyframe chain when the graph has 4096+ nodes and
-                                               a thin front, i.e. when the per-panel critical path bounds the factorisation),
-                                               1 = one natural-order chain, 2.. = that many; with pgs_dist_init: chains per rank (0 = 1) */
+                                               burning from both ends of the keyframe chain from 4096 nodes on, unless the
+                                               separator in the middle would be a quarter of the graph), 1 = one natural-order
+                                               chain, 2.. = that many; with pgs_dist_init: chains per rank (0 = 1) */
   int32_t check_linear_solves;              /* != 0: measure the backward error ||b - A y|| / ||b|| of every linear solve
                                                (one block SpMV each; pgs_get_linear_backward_errors) */
   double max_factor_bytes;                  /* skyline factor larger than this (0 = 80 % of the free device memory) or ... */

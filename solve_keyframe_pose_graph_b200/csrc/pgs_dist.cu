@@ -144,6 +144,7 @@ int Solver::prepare_chains() {
     CU(cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
     cs.f = skyline_create(cs.nf, (int)phi.size(), phi.data(), plo.data(), cs.st, &err, cs.nb, false, node_src.data(), pairs_of[c].data());
     if (!cs.f) return PGS_ERR_OUT_OF_MEMORY;
+    skyline_set_share(cs.f, (int)chains.size());
     factor_nnz += skyline_nnz(cs.f);
     CU(cs.y.resize((size_t)std::max(6 * cs.nf, 1), true));
     CU(cs.bmap.upload(bmap, cs.st));
@@ -267,16 +268,13 @@ int Solver::dist_stats(pgs_dist_stats* out) {
   return PGS_OK;
 }
 
-// Two chains meeting in the middle do the same work as one, on two dependency chains instead of one.  That pays when
-// the per-panel critical path (diagonal block + panel solve, ~40 us) is what bounds the factorisation, i.e. when the
-// trailing update of a panel is small: a thin front.  A thick front keeps the whole GPU busy from one chain already.
-static constexpr double kTwoChainsMaxFlopsPerPanel = 0.5e9;
+// Two chains meeting in the middle do the same work as one, on two dependency chains instead of one: while one chain
+// sits in its diagonal block (one CTA, ~33 us per panel) the other one's panel solve and trailing update have the GPU.
+// Measured on BASELINE config 3 (front ~2700 rows): 327 -> 267 ms per factorisation; config 2 (thin front): 31 -> 51 LM it/s.
 bool Solver::want_chains() const {
   if (is_inner || comm_owned || opt.linear_solver != PGS_SKYLINE_CHOLESKY) return false;
   if (opt.chains >= 2) return true;
-  if (opt.chains != 0 || N < 4096) return false;
-  const double panels = std::max(1.0, 6.0 * N / skyline_panel_width());
-  return est_flops / panels < kTwoChainsMaxFlopsPerPanel;
+  return opt.chains == 0 && N >= 4096;
 }
 
 int Solver::solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap) {

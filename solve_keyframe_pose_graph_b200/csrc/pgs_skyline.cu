@@ -54,6 +54,7 @@ constexpr int XP_RING = 4;        // packed panel copies in flight: trsm(d) cann
 struct SkylineFactor {
   int N = 0, n = 0, D = 0;         // nodes, scalars, panels
   int D_elim = 0;                  // panels to eliminate (== D for a full factorisation)
+  int share = 1;                   // factorisations that run on this GPU at the same time (chains): the persistent update takes 1/share of its SMs
   cudaStream_t stream = nullptr, s1 = nullptr, s2 = nullptr;   // main (rest), chain (C), panel (trsm + next)
   cudaEvent_t ev_trsm[NEV], ev_rest[NEV], ev_c[NEV], ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   unsigned int* sched = nullptr;   // [2] CTAs-done counter of the backward sweep (self-resetting)
@@ -94,6 +95,7 @@ void skyline_destroy(SkylineFactor* f) {
   delete f;
 }
 int64_t skyline_nnz(const SkylineFactor* f) { return f ? f->nnz : 0; }
+void skyline_set_share(SkylineFactor* f, int share) { if (f) f->share = share < 1 ? 1 : share; }
 int skyline_panel_width() { return PW; }
 
 SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
@@ -1002,7 +1004,7 @@ static int set_attrs(std::string* err) {
   SK(cudaFuncSetAttribute(sky_update_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD_WS));
   { int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     // the persistent update CTAs fill a whole SM each; a few SMs stay free for the kernels of the panel chain
-    const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 8; if (g_rest_ctas < 1) g_rest_ctas = 1;
+    const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 16; if (g_rest_ctas < 1) g_rest_ctas = 1;
     const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 2; }
   ready.insert(cur);
   return PGS_OK;
@@ -1042,6 +1044,9 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
   // main  stream s0:  [wait trsm(d)]              rest(d) -> ev_rest[d]
   // next(d-1) precedes trsm(d) on s2, rest(d-1) precedes rest(d) on s0.  (trsm on the chain stream, back to back
   // with C, saves the two event hops but was measured no faster on c3 and slower on heavier fronts.)
+  // The persistent update CTAs fill a whole SM each; g_rest_ctas SMs are theirs, split between the factorisations that
+  // share the GPU, the others stay free for the kernels of the panel chains (diag, trsm, next) at all times.
+  const int rest_ctas = std::max(1, g_rest_ctas / f->share);
   for (int d = 0; d < f->D_elim; ++d) {
     const int nr = f->h_rows_ptr[d + 1] - f->h_rows_ptr[d];
     const int Tr = (nr + UM - 1) / UM, Tc = (nr + UN - 1) / UN;
@@ -1062,7 +1067,7 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
     SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
     if (Tr > 1) {
       const int nt = Tr * (Tr - 1);
-      if (g_update_mode >= 1) sky_update_ws_kernel<1><<<std::min(nt, g_rest_ctas), WS_THREADS, SM_UPD_WS, s0>>>(d, n, skip_below, Tr, Tc, nt, f->rpad, xp, rinfo, f->val);
+      if (g_update_mode >= 1) sky_update_ws_kernel<1><<<std::min(nt, rest_ctas), WS_THREADS, SM_UPD_WS, s0>>>(d, n, skip_below, Tr, Tc, nt, f->rpad, xp, rinfo, f->val);
       else sky_update_kernel<1><<<nt, 256, SM_UPD, s0>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
     }
     SK(cudaEventRecord(f->ev_rest[d % NEV], s0));

@@ -19,6 +19,7 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
                               long long tail = 0);
 void skyline_destroy(SkylineFactor* f);
 int64_t skyline_nnz(const SkylineFactor* f);
+void skyline_set_share(SkylineFactor* f, int share);   // how many factorisations run on the GPU at the same time (elimination chains)
 int skyline_panel_width();
 // Numeric phase (device): scatter Ad[N][36] / Ao[P][36] into the envelope, factor A = L L^T, solve A y = b.
 // Returns PGS_OK, PGS_ERR_LINEAR_SOLVER (non-positive pivot) or a CUDA error code.

@@ -60,8 +60,8 @@ def test_chains_on_one_gpu_match_plain_and_oracle(n, nl, seed):
     assert np.abs(t - to).max() < 1e-5 and rot_angle_between(q, qo).max() < 1e-4 and np.array_equal(sw > 0.5, O.switches() > 0.5)
 
 
-def test_default_plan_uses_two_chains_for_large_graphs_with_a_thin_front():
-    p = problems.build_problem(2, n_nodes=6000, n_loop=600)          # sparse loop closures: the panel chain is the bound
+def test_default_plan_uses_two_chains_from_4096_nodes_on():
+    p = problems.build_problem(2, n_nodes=6000, n_loop=600)
     g = _as_graph(p)
     auto = _solve(g)
     assert auto[0]["n_chains"] == 2 and auto[4]["n_chains"] == 2
