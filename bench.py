@@ -245,7 +245,8 @@ def run_sharded(args, rank, local_rank, world, dist, torch, barrier, lm_record):
         st = S.dist_stats() if (world > 1 or s["n_chains"] > 1) else {}
         mine = dict(rank=rank, ms_total=s["ms_total"], ms_linear_solve=s["ms_linear_solve"], ms_sweep=s["ms_sweep"], ms_assemble=s["ms_assemble"], ms_comm=s["ms_comm"],
                     factor_nnz=int(st.get("factor_nnz", s["factor_nnz"])), n_interior_nodes=int(st.get("n_interior_nodes", p["N"])),
-                    n_local_border_nodes=int(st.get("n_local_border_nodes", 0)), n_collectives=int(st.get("n_collectives", 0)), bytes_reduced=int(st.get("bytes_reduced", 0)))
+                    n_local_border_nodes=int(st.get("n_local_border_nodes", 0)), n_collectives=int(st.get("n_collectives", 0)), bytes_reduced=int(st.get("bytes_reduced", 0)),
+                    ms_eliminate=float(st.get("ms_eliminate", 0.0)), ms_wait_in_border_allreduce=float(st.get("ms_exchange", 0.0)), ms_border_system=float(st.get("ms_border", 0.0)))
         per_rank = [mine]
         tmax = torch.tensor([s["ms_total"]], dtype=torch.float64, device="cuda")
         if world > 1:

@@ -176,6 +176,9 @@ typedef struct pgs_dist_stats {
   int32_t n_chains, n_local_border_nodes;           /* chains this rank eliminates; border nodes its factors hold */
   int64_t factor_nnz;                               /* this rank's chain factors + its copy of the border factor */
   double ms_comm;                                   /* this rank's time in collectives over the last solve (waiting included) */
+  double ms_eliminate;                              /* ... in eliminating its own chains (what the partition balances) */
+  double ms_exchange;                               /* ... in the border all-reduce, i.e. mostly waiting for the slowest rank (part of ms_comm) */
+  double ms_border;                                 /* ... in factoring and solving the border system */
 } pgs_dist_stats;
 int pgs_dist_unique_id(void* id128);                /* rank 0: ncclGetUniqueId; distribute the 128 bytes yourself */
 int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128);

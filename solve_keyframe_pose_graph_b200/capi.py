@@ -74,7 +74,8 @@ class DistStats(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_interior_nodes", C.c_int32), ("n_border_nodes", C.c_int32),
                 ("n_odom_owned", C.c_int32), ("n_loop_owned", C.c_int32), ("n_reg_owned", C.c_int32),
                 ("border_buffer_bytes", C.c_int64), ("n_collectives", C.c_int64), ("bytes_reduced", C.c_int64),
-                ("n_chains", C.c_int32), ("n_local_border_nodes", C.c_int32), ("factor_nnz", C.c_int64), ("ms_comm", C.c_double)]
+                ("n_chains", C.c_int32), ("n_local_border_nodes", C.c_int32), ("factor_nnz", C.c_int64), ("ms_comm", C.c_double),
+                ("ms_eliminate", C.c_double), ("ms_exchange", C.c_double), ("ms_border", C.c_double)]
 
 
 SKYLINE_CHOLESKY, BLOCK_PCG = 0, 1

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace pgs {
 
@@ -20,7 +21,9 @@ void make_partition(int N, int world, int n_odom, const int* oc1, const int* oc2
   // ones in between go up and carry the separator at their low end (weight kCarryCost per node)
   std::vector<double> units(R);
   double total = 0.0;
-  for (int c = 0; c < R; ++c) { units[c] = (c == 0 || c == R - 1) ? kCarryCost : 1.0; total += units[c]; }
+  double carry = kCarryCost;
+  if (const char* e = std::getenv("PGS_CARRY_COST")) { const double v = std::atof(e); if (v >= 1.0 && v <= 16.0) carry = v; }
+  for (int c = 0; c < R; ++c) { units[c] = (c == 0 || c == R - 1) ? carry : 1.0; total += units[c]; }
   P->ranges.assign(R, PlanRange());
   double acc = 0.0;
   for (int c = 0; c < R; ++c) {

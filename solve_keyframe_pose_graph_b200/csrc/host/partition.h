@@ -33,9 +33,11 @@ struct Partition {
   std::vector<int> border_env;            // per border position: first border position of its row envelope in the border system
 };
 
-// Weight of a range that carries a separator relative to one that does not (front of ~2 separators instead of 1
-// => ~3x the flops per eliminated column, measured on BASELINE config 5).
-constexpr double kCarryCost = 3.0;
+// Time per eliminated node of a range that carries a separator relative to one that does not.  The carried separator
+// roughly triples the flops of a panel's trailing update, but a free range is bound by its panel chain (diagonal block
+// + panel solve), not by the update: measured on BASELINE config 5 the ratio of the times is ~2.  (PGS_CARRY_COST in
+// the environment overrides it, for tuning.)
+constexpr double kCarryCost = 2.0;
 
 // chains_per_rank: 0 = default (world == 1: two chains burning from both ends when the graph is large enough,
 // else one; world > 1: one chain per rank).  Odometry edge e couples (oc1[e], oc2[e]); loop edge e couples

@@ -191,12 +191,16 @@ int Solver::solve_chains() {
   }
   if (sky_border) if (int rc = skyline_begin_border(sky_border, &err)) return rc;
   for (ChainState& cs : cstate) CU(cudaStreamWaitEvent(stream, cs.done, 0));
+  if (!ev_ph[0]) for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&ev_ph[i]));
+  CU(cudaEventRecord(ev_ph[0], stream));   // this rank's chains are eliminated
   if (sky_border) {
     // 2. border system = sum of the chains' Schur complements (+ the other ranks')
     for (ChainState& cs : cstate) if (cs.nb) if (int rc = skyline_border_accumulate(cs.f, sky_border, cs.bmap.p, stream, &err)) return rc;
     double* diagH = skyline_tail(sky_border);
     if (b6) border_pack_diag_kernel<<<cdiv(b6, 256), 256, 0, stream>>>(b6, fb, d_border_gpos.p, d_Hd.p, diagH);
+    CU(cudaEventRecord(ev_ph[1], stream));
     if (comm) if (int rc = comm->allreduce_sum(skyline_values(sky_border), (size_t)skyline_values_count(sky_border), stream, &err)) return rc;
+    CU(cudaEventRecord(ev_ph[2], stream));   // ... and every other rank's: the wait for the slowest rank is in [1, 2]
     // 3. damping of the border unknowns, border factorisation and solve
     border_damp_kernel<<<cdiv(ng6, 256), 256, 0, stream>>>(ng6, diagH, border_scale_ready ? 0 : 1, opt.jacobi_scaling, cur_reuse_diag ? 1 : 0, opt.min_lm_diagonal,
                                                           opt.max_lm_diagonal, 1.0 / cur_radius, d_sb.p, d_diagb.p, d_dampb.p);
@@ -209,6 +213,8 @@ int Solver::solve_chains() {
     CU(cudaGetLastError());
   }
   // 4. back-substitution of the chains, concurrently again
+  CU(cudaEventRecord(ev_ph[3], stream));
+  ph_pending = sky_border != nullptr;
   CU(cudaEventRecord(ev_fork, stream));
   for (size_t c = 0; c < cstate.size(); ++c) {
     ChainState& cs = cstate[c];
@@ -221,6 +227,17 @@ int Solver::solve_chains() {
   }
   for (ChainState& cs : cstate) CU(cudaStreamWaitEvent(stream, cs.done, 0));
   return PGS_OK;
+}
+
+// Phase times of the last solve_chains (call after the stream has been synchronised past it): local elimination is
+// billed to ms_linear_solve's caller, the border exchange (all-reduce incl. the wait for the slowest rank) to ms_comm.
+void Solver::collect_chain_times(float ms_from_start_to_eliminated) {
+  if (!ph_pending) return;
+  ph_pending = false;
+  float a = 0, b = 0;
+  if (cudaEventElapsedTime(&a, ev_ph[1], ev_ph[2]) == cudaSuccess) ms_exchange += a;
+  if (cudaEventElapsedTime(&b, ev_ph[2], ev_ph[3]) == cudaSuccess) ms_border += b;
+  ms_eliminate += ms_from_start_to_eliminated;
 }
 
 int Solver::dist_fail_flag() {
@@ -263,7 +280,8 @@ int Solver::dist_stats(pgs_dist_stats* out) {
   if (!comm_owned && !inner) return fail(PGS_ERR_STATE, "dist_stats: no sharded solve has run on this handle");
   *out = dstats;
   out->rank = comm_owned ? comm_owned->rank : 0; out->world = comm_owned ? comm_owned->world : 1;
-  if (inner) { out->border_buffer_bytes = inner->dstats.border_buffer_bytes; out->factor_nnz = inner->dstats.factor_nnz; out->ms_comm = inner->ms_comm; }
+  if (inner) { out->border_buffer_bytes = inner->dstats.border_buffer_bytes; out->factor_nnz = inner->dstats.factor_nnz; out->ms_comm = inner->ms_comm + inner->ms_exchange;
+               out->ms_eliminate = inner->ms_eliminate; out->ms_border = inner->ms_border; out->ms_exchange = inner->ms_exchange; }
   out->n_collectives = comm_owned ? comm_owned->n_collectives : 0; out->bytes_reduced = comm_owned ? comm_owned->bytes_reduced : 0;
   return PGS_OK;
 }

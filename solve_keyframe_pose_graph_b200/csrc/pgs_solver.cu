@@ -64,6 +64,7 @@ Solver::~Solver() {
   inner.reset();
   release_chains();
   if (ev_fork) cudaEventDestroy(ev_fork);
+  for (cudaEvent_t e : ev_ph) if (e) cudaEventDestroy(e);
   if (sky) skyline_destroy(sky);
   if (h_scal) cudaFreeHost(h_scal);
   if (ev0) cudaEventDestroy(ev0);
@@ -792,7 +793,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
   if (int rc = sync_params_to_device()) return rc;
   const bool sharded = !chains.empty();
   border_scale_ready = false;
-  ms_sweep = ms_asm = ms_lin = ms_comm = 0.0;
+  ms_sweep = ms_asm = ms_lin = ms_comm = ms_eliminate = ms_exchange = ms_border = 0.0;
   backward_error.clear();
   {
     // the factors are allocated up front: a rank that cannot hold its share says so before anyone waits for it
@@ -872,6 +873,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     cur_radius = radius; cur_reuse_diag = reuse_diagonal;
     const int lrc = solve_linear(&lin_it);
     ms_lin += toc();
+    if (ph_pending) { float e = 0; cudaEventElapsedTime(&e, ev0, ev_ph[0]); collect_chain_times(e); }
     if (lrc != PGS_OK && lrc != PGS_ERR_LINEAR_SOLVER) return lrc;
     if (lrc == PGS_OK && opt.check_linear_solves) { double rel = 0.0; if ((rc = linear_residual(&rel))) return rc; backward_error.push_back(rel); }
     it.linear_solver_iterations = lin_it; lin_total += lin_it;
@@ -946,7 +948,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     sum->max_linear_backward_error = -1.0;
     for (double e : backward_error) sum->max_linear_backward_error = std::max(sum->max_linear_backward_error, e);
     sum->fixed_cost = fixed_cost;
-    sum->ms_comm = ms_comm;
+    sum->ms_comm = ms_comm + ms_exchange;
   }
   for (int i = 0; iters && i < (int)rows.size() && i < cap; ++i) iters[i] = rows[i];
   return PGS_OK;

@@ -179,7 +179,9 @@ class Solver {
   DBuf<const int*> d_flag_ptrs; bool flag_ptrs_ready = false;
   std::vector<double> backward_error;    // per linear solve of the last LM run: ||b - A y|| / ||b||
   void release_chains();
-  double ms_comm = 0;
+  double ms_comm = 0, ms_eliminate = 0, ms_exchange = 0, ms_border = 0;   // sharded: collectives of the LM loop | this rank's chains | border all-reduce incl. waiting | border factor + solve
+  cudaEvent_t ev_ph[4] = {nullptr, nullptr, nullptr, nullptr}; bool ph_pending = false;
+  void collect_chain_times(float ms_from_start_to_eliminated);
   double cur_radius = 0.0; bool cur_reuse_diag = false, border_scale_ready = false;
 
   // phase timers (ms, accumulated per solve)
