@@ -40,6 +40,10 @@ struct SweepArgs {
   double* __restrict__ cost_tile;                          // [tiles] sum of squared residuals per tile of 32 edges
   unsigned int* __restrict__ sched;                        // [2] {next tile, blocks done}; zero between launches
   double* __restrict__ cost_out;                           // 0.5 * sum of cost_tile, written by the last block to finish
+  // A launch may cover only part of the tiles (the end-to-end step sweeps the edges whose keyframes have arrived while the
+  // rest of the poses is still on the bus): tiles [o_t0, o_t1) of the odometry edges, [l_t0, l_t1) of the loop edges and
+  // [r_t0, r_t1) of the regularisers; reduce != 0 on the launch that completes the sweep (sums ALL per-tile partials).
+  int o_t0, o_t1, l_t0, l_t1, r_t0, r_t1, reduce;
 };
 
 // ------------------------------------------------------------------ small math
@@ -142,11 +146,13 @@ __global__ void __launch_bounds__(256, PGS_SWEEP_MINB) sweep_kernel(SweepArgs A)
 
   // (Drawing the ticket for the NEXT tile before processing the current one — to hide the atomic's round trip — was
   // measured on the same box: 51.2 us against 48.0 us per sweep.  The plain loop stays.)
+  const int no = A.o_t1 - A.o_t0, nl = A.l_t1 - A.l_t0, nt = no + nl + (A.r_t1 - A.r_t0);
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = (int)atomicAdd(A.sched, 1u);
     tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= T) break;
+    if (tile >= nt) break;
+    tile = tile < no ? A.o_t0 + tile : (tile < no + nl ? To + A.l_t0 + (tile - no) : To + Tl + A.r_t0 + (tile - no - nl));   // ticket -> tile of this launch's ranges
     double cost = 0.0;
     if (tile < To) {
       // ---- odometry edges: r = w e, J = w Je
@@ -290,6 +296,7 @@ __global__ void __launch_bounds__(256, PGS_SWEEP_MINB) sweep_kernel(SweepArgs A)
   }
   __syncthreads();
   if (!is_last) return;
+  if (!A.reduce) { if (threadIdx.x == 0) { A.sched[0] = 0u; A.sched[1] = 0u; } return; }   // a partial launch only re-arms the scheduler
   __threadfence();
   double s = 0.0;
   for (int i0 = threadIdx.x; i0 < T; i0 += 8 * blockDim.x) {   // eight loads in flight, added in index order

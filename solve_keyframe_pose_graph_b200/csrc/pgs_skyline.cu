@@ -863,7 +863,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int
       __syncwarp();
       int last = 0;
       if (lane == 0) {
-        __threadfence_block();
+        // (no fence: the warps publish nothing through shared memory, and their reads of the stage have completed —
+        // a fence here would also wait for this lane's A_old loads, which are meant to stay in flight)
         last = atomicAdd(done + ch, 1) == NWARPS - 1;
         if (last) { done[ch] = 0; if (more) issue(tin, tjn, ch); }
       }

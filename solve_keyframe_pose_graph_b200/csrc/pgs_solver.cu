@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -19,12 +20,15 @@ namespace pgs {
 
 // ---- small pack/unpack kernels between the C-ABI's SoA (q[4N], t[3N], s[El] caller order) and the device layout
 // the 8th slot of a pose record carries the constant-block flag (1.0 = constant), which the sweep turns into zero Jacobian columns
+// (grid-stride: q and t may be pinned HOST memory read over the bus by a small grid, see evaluate_from_host)
 __global__ void pack_pose_kernel(int first, int n, const double* __restrict__ q, const double* __restrict__ t, const char* __restrict__ fixed, double* __restrict__ pose) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double* p = pose + 8 * (size_t)(first + i);
-  p[0] = q[4 * (size_t)i]; p[1] = q[4 * (size_t)i + 1]; p[2] = q[4 * (size_t)i + 2]; p[3] = q[4 * (size_t)i + 3];
-  p[4] = t[3 * (size_t)i]; p[5] = t[3 * (size_t)i + 1]; p[6] = t[3 * (size_t)i + 2]; p[7] = fixed[first + i] ? 1.0 : 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double2 q01 = *reinterpret_cast<const double2*>(q + 4 * (size_t)i), q23 = *reinterpret_cast<const double2*>(q + 4 * (size_t)i + 2);
+    const double t0 = t[3 * (size_t)i], t1 = t[3 * (size_t)i + 1], t2 = t[3 * (size_t)i + 2];
+    double* p = pose + 8 * (size_t)(first + i);
+    *reinterpret_cast<double2*>(p) = q01; *reinterpret_cast<double2*>(p + 2) = q23;
+    *reinterpret_cast<double2*>(p + 4) = make_double2(t0, t1); *reinterpret_cast<double2*>(p + 6) = make_double2(t2, fixed[first + i] ? 1.0 : 0.0);
+  }
 }
 __global__ void unpack_pose_kernel(int first, int n, const double* __restrict__ pose, double* __restrict__ q, double* __restrict__ t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,6 +75,9 @@ Solver::~Solver() {
   if (ev1) cudaEventDestroy(ev1);
   if (ev_t0) cudaEventDestroy(ev_t0);
   if (ev_t1) cudaEventDestroy(ev_t1);
+  for (cudaEvent_t e : ev_chunk) if (e) cudaEventDestroy(e);
+  if (ev_copy_go) cudaEventDestroy(ev_copy_go);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -235,6 +242,15 @@ int Solver::finalize() {
     for (int c = 0; c < 3; ++c) ranchor[8 * (size_t)k + 4 + c] = r_t[3 * (size_t)k + c];
     ranchor[8 * (size_t)k + 7] = r_w[k];
   }
+  // per tile of 32 edges: the largest keyframe index any tile up to and including it touches (end-to-end step: a prefix
+  // of the tiles can be swept as soon as the keyframes below a bound have arrived)
+  o_pm.assign(To, 0); l_pm.assign(Tl, 0); r_pm.assign(cdiv(K, TILE), 0);
+  for (int e = 0; e < Eo; ++e) o_pm[e / TILE] = std::max(o_pm[e / TILE], std::max(oidx[e].x, oidx[e].y));
+  for (int e = 0; e < El; ++e) l_pm[e / TILE] = std::max(l_pm[e / TILE], std::max(lidx[e].x, lidx[e].y));
+  for (int k = 0; k < K; ++k) r_pm[k / TILE] = std::max(r_pm[k / TILE], r_node[k]);
+  for (size_t i = 1; i < o_pm.size(); ++i) o_pm[i] = std::max(o_pm[i], o_pm[i - 1]);
+  for (size_t i = 1; i < l_pm.size(); ++i) l_pm[i] = std::max(l_pm[i], l_pm[i - 1]);
+  for (size_t i = 1; i < r_pm.size(); ++i) r_pm[i] = std::max(r_pm[i], r_pm[i - 1]);
   // 2. node incidence lists (edge<<3 | kind<<1 | side)
   std::vector<int> inc_ptr(N + 1, 0);
   for (int e = 0; e < Eo; ++e) { ++inc_ptr[oidx[e].x + 1]; ++inc_ptr[oidx[e].y + 1]; }
@@ -373,7 +389,7 @@ int Solver::read_scalars(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-int Solver::launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev, cudaEvent_t after_kernel) {
+int Solver::launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev, cudaEvent_t after_kernel, const int* ranges, int reduce) {
   SweepArgs A;
   A.pose = pose; A.sw = sw;
   A.o_idx = d_oidx.p; A.o_obs = d_oobs.p; A.n_odom = (int)o_c1.size();
@@ -381,7 +397,10 @@ int Solver::launch_sweep(int mode, const double* pose, const double* sw, double*
   A.r_node = d_rnode.p; A.r_anchor = d_ranchor.p; A.n_reg = (int)r_node.size();
   A.o_r = d_or.p; A.o_J = d_oJ.p; A.l_r = d_lr.p; A.l_J = d_lJ.p; A.g_r = d_gr.p; A.g_J = d_gJ.p;
   A.cost_tile = d_cost_tile.p; A.sched = d_counter.p + 2;   // slots 0-1 belong to the PCG kernels
-  const int tiles = cdiv(A.n_odom, TILE) + cdiv(A.n_loop, TILE) + cdiv(A.n_reg, TILE);
+  A.o_t0 = 0; A.o_t1 = cdiv(A.n_odom, TILE); A.l_t0 = 0; A.l_t1 = cdiv(A.n_loop, TILE); A.r_t0 = 0; A.r_t1 = cdiv(A.n_reg, TILE); A.reduce = reduce;
+  if (ranges) { A.o_t0 = ranges[0]; A.o_t1 = ranges[1]; A.l_t0 = ranges[2]; A.l_t1 = ranges[3]; A.r_t0 = ranges[4]; A.r_t1 = ranges[5]; }
+  const int tiles = (A.o_t1 - A.o_t0) + (A.l_t1 - A.l_t0) + (A.r_t1 - A.r_t0);
+  if (tiles == 0 && !reduce) return PGS_OK;
   const int grid = std::max(1, std::min(sweep_grid, cdiv(tiles, 8)));
   A.cost_out = cost_out_dev;
   if (mode == 0) sweep_kernel<0><<<grid, 256, 0, stream>>>(A); else sweep_kernel<1><<<grid, 256, 0, stream>>>(A);
@@ -757,22 +776,78 @@ int Solver::time_stream_write(int64_t bytes, int reps, int flush_l2, double* ms)
   return PGS_OK;
 }
 
+// End-to-end step: poses and switches arrive from host memory, the mode-J sweep runs, the cost goes back.  The upload is
+// the long pole (6 MB over PCIe against a 50 us sweep), so it is cut into chunks of keyframes on a copy stream, and
+// after every chunk the compute stream packs those poses and sweeps the tiles whose keyframes are all there (edges are
+// sorted by keyframe, so that is a growing prefix of every tile list); only the last chunk's share of the sweep and
+// the 8-byte read-back are left when the bus falls silent.
 int Solver::evaluate_from_host(const double* q, const double* t, const double* s, double* cost) {
   CU(cudaSetDevice(dev));
   if (int rc = finalize()) return rc;
   if (host_params_newer) if (int rc = sync_params_to_device()) return rc;
   const int El = (int)l_a.size();
-  if (q) CU(cudaMemcpyAsync(d_stage_q.p, q, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, stream));
-  if (t) CU(cudaMemcpyAsync(d_stage_t.p, t, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
-  if ((q || t) && N) {
-    if (!q || !t) return fail(PGS_ERR_INVALID_ARGUMENT, "evaluate_from_host: q and t must be given together");
-    pack_pose_kernel<<<cdiv(N, 256), 256, 0, stream>>>(0, N, d_stage_q.p, d_stage_t.p, d_node_const.p, d_pose.p);
+  if ((q || t) && N && (!q || !t)) return fail(PGS_ERR_INVALID_ARGUMENT, "evaluate_from_host: q and t must be given together");
+  if (!copy_stream) {
+    CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_copy_go, cudaEventDisableTiming));
   }
-  if (s && El) {
-    CU(cudaMemcpyAsync(d_stage_s.p, s, sizeof(double) * (size_t)El, cudaMemcpyHostToDevice, stream));
-    gather_kernel<<<cdiv(El, 256), 256, 0, stream>>>(El, d_perm_l.p, d_stage_s.p, d_sw.p);
+  const int To = (int)o_pm.size(), Tl = (int)l_pm.size(), Tr = (int)r_pm.size();
+  static const int e2e_mode = [] { const char* e = getenv("PGS_E2E_MODE"); return e ? atoi(e) : 1; }();   // 0 chunked copies, 1 chunked reads of pinned memory, 2 one shot
+  if (!(q && t) || N < 4096 || e2e_mode == 2) {
+    // nothing to overlap: one shot
+    if (q && N) {
+      CU(cudaMemcpyAsync(d_stage_q.p, q, sizeof(double) * 4 * (size_t)N, cudaMemcpyHostToDevice, stream));
+      CU(cudaMemcpyAsync(d_stage_t.p, t, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, stream));
+      pack_pose_kernel<<<cdiv(N, 256), 256, 0, stream>>>(0, N, d_stage_q.p, d_stage_t.p, d_node_const.p, d_pose.p);
+    }
+    if (s && El) {
+      CU(cudaMemcpyAsync(d_stage_s.p, s, sizeof(double) * (size_t)El, cudaMemcpyHostToDevice, stream));
+      gather_kernel<<<cdiv(El, 256), 256, 0, stream>>>(El, d_perm_l.p, d_stage_s.p, d_sw.p);
+    }
+    if (int rc = launch_sweep(0, d_pose.p, d_sw.p, d_scal.p + L_COST)) return rc;
+  } else {
+    constexpr int NCHUNK = (int)(sizeof(ev_chunk) / sizeof(ev_chunk[0]));
+    // Pinned (registered) host memory is visible to the device: the pack kernel then reads q and t straight over the bus,
+    // chunk by chunk, with no staging copy and none of the per-copy set-up cost that nine small cudaMemcpyAsync calls have.
+    // Pageable memory goes through cudaMemcpyAsync as before.
+    bool direct = false;
+    if (e2e_mode == 1) {
+      cudaPointerAttributes aq{}, at{};
+      direct = cudaPointerGetAttributes(&aq, q) == cudaSuccess && cudaPointerGetAttributes(&at, t) == cudaSuccess && aq.type == cudaMemoryTypeHost && at.type == cudaMemoryTypeHost &&
+               aq.devicePointer && at.devicePointer;
+      cudaGetLastError();
+      if (direct) { q = (const double*)aq.devicePointer; t = (const double*)at.devicePointer; }
+    }
+    CU(cudaEventRecord(ev_copy_go, stream));                 // the staging buffers are free once earlier work on the compute stream is done
+    CU(cudaStreamWaitEvent(copy_stream, ev_copy_go, 0));
+    if (s && El) {
+      CU(cudaMemcpyAsync(d_stage_s.p, s, sizeof(double) * (size_t)El, cudaMemcpyHostToDevice, copy_stream));
+    }
+    int done_o = 0, done_l = 0, done_r = 0;
+    for (int k = 0; k < NCHUNK; ++k) {
+      const int n0 = (int)((long long)N * k / NCHUNK), n1 = (int)((long long)N * (k + 1) / NCHUNK);
+      if (direct) {
+        // few CTAs: the bus is the bound, and the SMs are wanted by the sweep of the previous chunk
+        pack_pose_kernel<<<std::min(cdiv(n1 - n0, 256), 64), 256, 0, copy_stream>>>(n0, n1 - n0, q + 4 * (size_t)n0, t + 3 * (size_t)n0, d_node_const.p, d_pose.p);
+      } else {
+        CU(cudaMemcpyAsync(d_stage_q.p + 4 * (size_t)n0, q + 4 * (size_t)n0, sizeof(double) * 4 * (size_t)(n1 - n0), cudaMemcpyHostToDevice, copy_stream));
+        CU(cudaMemcpyAsync(d_stage_t.p + 3 * (size_t)n0, t + 3 * (size_t)n0, sizeof(double) * 3 * (size_t)(n1 - n0), cudaMemcpyHostToDevice, copy_stream));
+      }
+      CU(cudaEventRecord(ev_chunk[k], copy_stream));
+      CU(cudaStreamWaitEvent(stream, ev_chunk[k], 0));
+      if (k == 0 && s && El) gather_kernel<<<cdiv(El, 256), 256, 0, stream>>>(El, d_perm_l.p, d_stage_s.p, d_sw.p);
+      if (!direct) pack_pose_kernel<<<cdiv(n1 - n0, 256), 256, 0, stream>>>(n0, n1 - n0, d_stage_q.p + 4 * (size_t)n0, d_stage_t.p + 3 * (size_t)n0, d_node_const.p, d_pose.p);
+      // tiles whose keyframes are all below n1
+      const bool last = k == NCHUNK - 1;
+      const int up_o = last ? To : (int)(std::upper_bound(o_pm.begin(), o_pm.end(), n1 - 1) - o_pm.begin());
+      const int up_l = last ? Tl : (int)(std::upper_bound(l_pm.begin(), l_pm.end(), n1 - 1) - l_pm.begin());
+      const int up_r = last ? Tr : (int)(std::upper_bound(r_pm.begin(), r_pm.end(), n1 - 1) - r_pm.begin());
+      const int ranges[6] = {done_o, up_o, done_l, up_l, done_r, up_r};
+      if (int rc = launch_sweep(0, d_pose.p, d_sw.p, d_scal.p + L_COST, nullptr, ranges, last ? 1 : 0)) return rc;
+      done_o = up_o; done_l = up_l; done_r = up_r;
+    }
   }
-  if (int rc = launch_sweep(0, d_pose.p, d_sw.p, d_scal.p + L_COST)) return rc;
   CU(cudaMemcpyAsync(h_scal + L_COST, d_scal.p + L_COST, sizeof(double), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
   if (cost) *cost = h_scal[L_COST];

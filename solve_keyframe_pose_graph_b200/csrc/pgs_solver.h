@@ -102,7 +102,8 @@ class Solver {
   int finalize();                        // sort edges, build incidence/pair/adjacency structures, upload
   int sync_params_to_device();           // host q,t,sw -> device pose / sw (if dirty)
   int sync_params_to_host();             // device -> host mirrors (if device is newer)
-  int launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev, cudaEvent_t after_kernel = nullptr);
+  int launch_sweep(int mode, const double* pose, const double* sw, double* cost_out_dev, cudaEvent_t after_kernel = nullptr,
+                   const int* tile_ranges = nullptr, int reduce = 1);   // tile_ranges: {o0, o1, l0, l1, r0, r1} for a partial sweep
   int run_assemble();
   int compute_scaling(bool compute_scale);
   int build_system(double radius);
@@ -142,6 +143,8 @@ class Solver {
   int n_pairs = 0;
   std::vector<int> h_pair_hi, h_pair_lo;
   std::vector<char> h_node_used, h_node_const;
+  std::vector<int> o_pm, l_pm, r_pm;     // per tile: largest keyframe index touched by the tiles up to it (prefix maximum)
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev_copy_go = nullptr;
 
   // device
   int dev = 0; cudaStream_t stream = nullptr;

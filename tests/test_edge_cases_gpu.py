@@ -126,3 +126,62 @@ def test_factor_over_budget_falls_back_to_pcg_and_says_so():
     c = load_pgs(g, max_factor_bytes=1e4, pcg_tolerance=1e-12); sc = c.solve(); c.close()
     assert sc["linear_solver_used"] == pgs.capi.BLOCK_PCG
     assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-5 * sa["final_cost"] and np.abs(ta - tb).max() < 1e-5 and rot_angle_between(qa, qb).max() < 1e-4
+
+
+def test_one_loop_closure_across_the_whole_trajectory_at_100k_keyframes():
+    """the reference accepts a loop closure between ANY two keyframes
+    (src/NodeDataManager.cpp:107-189).  100 000 keyframes with a single closure from the last one back to the first:
+    one row of the factor spans the whole matrix, everything else stays a thin band — no out-of-memory, same result
+    as the oracle (whose skyline has the same envelope)."""
+    from solve_keyframe_pose_graph_b200 import problems
+    p = problems.build_problem(2, n_nodes=100000, n_loop=1)              # (the front end only triggers on a loop closure: one short one from the generator)
+    N = p["N"]
+    rel_t = p["gt_t"][N - 1] - p["gt_t"][0]
+    from scipy.spatial.transform import Rotation as Rot
+    R0 = Rot.from_quat(p["gt_q"][0]); R1 = Rot.from_quat(p["gt_q"][N - 1])
+    q_ba = (R0.inv() * R1).as_quat(); t_ba = R0.inv().apply(rel_t)          # b_T_a with a = N-1, b = 0
+    q_ba = q_ba if q_ba[3] >= 0 else -q_ba
+    g = dict(N=N, q=p["q"], t=p["t"], oc1=p["oc1"], oc2=p["oc2"], oq=p["oq"], ot=p["ot"], ow=p["ow"],
+             la=np.append(p["la"], N - 1).astype(np.int32), lb=np.append(p["lb"], 0).astype(np.int32), lq=np.vstack([p["lq"], q_ba]), lt=np.vstack([p["lt"], t_ba]),
+             lw=np.append(p["lw"], 1.0), rn=p["rn"], rq=p["rq"], rt=p["rt"], rw=p["rw"])
+    for chains in (1, 2):
+        S = load_pgs(g, chains=chains); ss = S.solve(); qs, ts = S.poses(); be = S.linear_backward_errors()
+        # (the residual is taken relative to |b| alone; on a 100 km chain |A||y| is orders of magnitude above |b|)
+        assert ss["linear_solver_used"] == pgs.capi.SKYLINE_CHOLESKY and ss["factor_nnz"] < 2e9 and be.max() < 1e-7
+        if chains == 1:
+            O = load_oracle(g); so = O.solve(); qo, to = O.poses()
+            assert [r["step_is_successful"] for r in ss["iterations"]] == [r["step_is_successful"] for r in so["iterations"]]
+        assert abs(ss["final_cost"] - so["final_cost"]) <= 1e-5 * so["final_cost"]
+        assert np.abs(ts - to).max() < 1e-5 and rot_angle_between(qs, qo).max() < 1e-4
+        S.close()
+
+
+def test_many_far_reaching_loop_closures_stay_within_budget():
+    """30 000 keyframes (the reference's own capacity, src/PoseGraphSLAM.cpp:19-24) with 2 000 loop closures of mean gap N/3:
+    the natural-order envelope is wide.  The estimate decides: inside the budget the skyline factor is used, past it the
+    solve goes to block PCG instead of failing; both reach the same minimum (the oracle's LM is out of reach here, so the
+    checks are the cross-solver agreement, monotone descent and the backward errors)."""
+    rng = np.random.default_rng(77)
+    from solve_keyframe_pose_graph_b200 import problems
+    p = problems.build_problem(2, n_nodes=30000, n_loop=1)
+    N = p["N"]
+    from scipy.spatial.transform import Rotation as Rot
+    b = rng.integers(0, N - 2, size=2000); gap = np.minimum(rng.exponential(N / 3, size=2000).astype(int) + 1, N - 1 - b); a = b + gap
+    Rb = Rot.from_quat(p["gt_q"][b]); Ra = Rot.from_quat(p["gt_q"][a])
+    lq = (Rb.inv() * Ra).as_quat(); lq = lq * np.where(lq[:, 3:4] >= 0, 1.0, -1.0)
+    lt = Rb.inv().apply(p["gt_t"][a] - p["gt_t"][b]) + 0.01 * rng.normal(size=(2000, 3))
+    g = dict(N=N, q=p["q"], t=p["t"], oc1=p["oc1"], oc2=p["oc2"], oq=p["oq"], ot=p["ot"], ow=p["ow"],
+             la=a.astype(np.int32), lb=b.astype(np.int32), lq=lq, lt=lt, lw=np.ones(2000), rn=p["rn"], rq=p["rq"], rt=p["rt"], rw=p["rw"])
+    S = load_pgs(g); ss = S.solve(); qs, ts = S.poses(); be = S.linear_backward_errors(); S.close()
+    assert ss["linear_solver_used"] == pgs.capi.SKYLINE_CHOLESKY and be.max() < 1e-8
+    cost = ss["initial_cost"]
+    for r in ss["iterations"][1:]:
+        if r["step_is_successful"]:
+            assert r["cost"] < cost; cost = r["cost"]
+    assert ss["final_cost"] < 1e-3 * ss["initial_cost"]
+    # the same problem under a budget the envelope does not fit: falls back to the iterative solver, same first LM steps
+    T = load_pgs(g, max_factor_flops=ss["factor_flops"] / 4, pcg_tolerance=1e-12, pcg_max_iterations=100000, max_num_iterations=3)
+    st = T.solve(); T.close()
+    U = load_pgs(g, max_num_iterations=3); su = U.solve(); U.close()
+    assert st["linear_solver_used"] == pgs.capi.BLOCK_PCG and su["linear_solver_used"] == pgs.capi.SKYLINE_CHOLESKY
+    assert np.allclose([r["cost"] for r in st["iterations"]], [r["cost"] for r in su["iterations"]], rtol=1e-5)

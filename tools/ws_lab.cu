@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
     if (!k[0]) continue;
     printf("  cta %2d:", c);
     for (int it = 0; it < 3; ++it) {
-      if (!k[1 + 12 * it]) break;
+      if (!k[11 + 12 * it]) break;
       const long long base = it == 0 ? k[0] : k[11 + 12 * (it - 1)];
       printf("  | tile %d pre %5lld", it, k[1 + 12 * it] - base);
       for (int ch = 0; ch < 3; ++ch)
