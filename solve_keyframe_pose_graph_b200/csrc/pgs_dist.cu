@@ -216,14 +216,24 @@ int Solver::solve_chains() {
   CU(cudaEventRecord(ev_ph[3], stream));
   ph_pending = sky_border != nullptr;
   CU(cudaEventRecord(ev_fork, stream));
-  for (size_t c = 0; c < cstate.size(); ++c) {
-    ChainState& cs = cstate[c];
-    const int len6 = 6 * chains[c].len;
-    CU(cudaStreamWaitEvent(cs.st, ev_fork, 0));
-    if (cs.nb) border_take_kernel<<<cdiv(6 * cs.nb, 256), 256, 0, cs.st>>>(6 * cs.nb, cs.bmap.p, d_zb.p, cs.y.p + len6);
-    if (int rc = skyline_backward(cs.f, cs.y.p, &err)) return rc;
-    if (len6) CU(cudaMemcpyAsync(d_y.p + 6 * (size_t)chains[c].off, cs.y.p, sizeof(double) * len6, cudaMemcpyDeviceToDevice, cs.st));
-    CU(cudaEventRecord(cs.done, cs.st));
+  {
+    std::vector<int> rcs(cstate.size(), PGS_OK); std::vector<std::string> errs(cstate.size());
+    auto enqueue = [&](size_t c) {
+      ChainState& cs = cstate[c];
+      const int len6 = 6 * chains[c].len;
+      cudaSetDevice(dev);
+      if (cudaStreamWaitEvent(cs.st, ev_fork, 0) != cudaSuccess) { rcs[c] = PGS_ERR_CUDA; errs[c] = "cudaStreamWaitEvent"; return; }
+      if (cs.nb) border_take_kernel<<<cdiv(6 * cs.nb, 256), 256, 0, cs.st>>>(6 * cs.nb, cs.bmap.p, d_zb.p, cs.y.p + len6);
+      rcs[c] = skyline_backward(cs.f, cs.y.p, &errs[c]);
+      if (rcs[c] != PGS_OK) return;
+      if (len6 && cudaMemcpyAsync(d_y.p + 6 * (size_t)chains[c].off, cs.y.p, sizeof(double) * len6, cudaMemcpyDeviceToDevice, cs.st) != cudaSuccess) { rcs[c] = PGS_ERR_CUDA; errs[c] = "cudaMemcpyAsync"; return; }
+      if (cudaEventRecord(cs.done, cs.st) != cudaSuccess) { rcs[c] = PGS_ERR_CUDA; errs[c] = "cudaEventRecord"; }
+    };
+    std::vector<std::thread> th;
+    for (size_t c = 1; c < cstate.size(); ++c) th.emplace_back(enqueue, c);
+    enqueue(0);
+    for (std::thread& t : th) t.join();
+    for (size_t c = 0; c < cstate.size(); ++c) if (rcs[c] != PGS_OK) { err = errs[c]; return rcs[c]; }
   }
   for (ChainState& cs : cstate) CU(cudaStreamWaitEvent(stream, cs.done, 0));
   return PGS_OK;
