@@ -326,38 +326,38 @@ __global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, int prev, c
       for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int c = 0; c < 8; ++c) Dg[a][c] = (c <= a) ? L[(jb + a) * LDQ + jb + c] : 0.0;
+      // Right-looking (outer-product) form, everything in registers: as soon as column c is scaled, its rank-1 update
+      // goes into the columns to its right — independent FMAs — so the next pivot is one FMA behind the previous one
+      // instead of a dot product of growing length (the dependent chain per column is rsqrt + mul + fma).  The thread's
+      // own row of the block column rides along: row[b] -= row[c] * Dg[b][c], the same operations a forward
+      // substitution would do, without its serial dot products.
       double arow[8];
       if (row_thread) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) arow[c] = L[(jb + tid) * LDQ + jb + c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) arow[c] = 0.0;
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         double dd = Dg[c][c];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < c) dd -= Dg[c][k] * Dg[c][k];
         if (!(dd > 0.0)) { if (tid == 0) bad = 1; dd = 1.0; }
         const double inv = rsqrt(dd);      // 1 ulp; the sqrt + divide pair would put ~600 cycles per column on the critical path
         Dg[c][c] = dd * inv; dinv8[c] = inv;
+        arow[c] *= inv;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) if (a > c) {
-          double sacc = Dg[a][c];
+        for (int a = 0; a < 8; ++a) if (a > c) Dg[a][c] *= inv;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) if (k < c) sacc -= Dg[a][k] * Dg[c][k];
-          Dg[a][c] = sacc * inv;
+        for (int b = 0; b < 8; ++b) if (b > c) {
+          arow[b] -= arow[c] * Dg[b][c];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) if (a >= b) Dg[a][b] -= Dg[a][c] * Dg[b][c];
         }
       }
-      if (row_thread && tid >= 8) {        // rows below the diagonal block: x = arow * Dg^-T
-        double row[8];
+      if (row_thread && tid >= 8) {        // rows below the diagonal block: x = arow * Dg^-T, computed above
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          double sacc = arow[c];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) if (k < c) sacc -= row[k] * Dg[c][k];
-          row[c] = sacc * dinv8[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(&L[(jb + tid) * LDQ + jb + c]) = make_double2(row[c], row[c + 1]);
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(&L[(jb + tid) * LDQ + jb + c]) = make_double2(arow[c], arow[c + 1]);
       }
       if (inv_thread) {                    // W = Dg^-1 (lower triangular) -> Dinv[I] and the diagonal block of X
         double Xi[8][8];
