@@ -240,8 +240,10 @@ __device__ __forceinline__ void diag_block_of(int b, int& bi, int& bk) {
 #ifdef SKY_DIAG_CLOCKS   // tools/diag_lab.cu: cycle stamps of thread 0 after every barrier phase
 __device__ long long g_diag_clk[64];
 #define DIAG_STAMP(i) do { if (threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#define DIAG_STAMP_U(i) do { if (threadIdx.x == 128) g_diag_clk[i] = clock64(); } while (0)
 #else
 #define DIAG_STAMP(i) do { } while (0)
+#define DIAG_STAMP_U(i) do { } while (0)
 #endif
 __global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, int prev, const long long* __restrict__ ptr, const int* __restrict__ start,
                                                        double* __restrict__ val, double* __restrict__ dinv, int* __restrict__ fail) {
@@ -460,6 +462,230 @@ __global__ void __launch_bounds__(256) sky_diag_kernel(int d, int n, int prev, c
   double* dout = dinv + (size_t)d * PW * PW;
 #pragma unroll 4
   for (int i = wid; i < PW; i += 8) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * (lane + 32 * h);                        // j even: (j, j+1) both in the lower triangle unless j == i
+      if (j >= PW) break;
+      double2 x = make_double2(0.0, 0.0);
+      if (i < w && j <= i) { x = *reinterpret_cast<const double2*>(&X[i * LDQ + j]); if (j == i) x.y = 0.0; }
+      *reinterpret_cast<double2*>(dout + i * PW + j) = x;
+    }
+  }
+  if (tid == 0 && bad) *fail = 1;
+  DIAG_STAMP(3 + 2 * NB);
+}
+
+// diag, pipelined (the default): the same factorisation with the two barrier phases of a step overlapped.  512 threads:
+//   panel warps 0-3   step I: wait until block column I has its last update; every row thread re-factors the 8x8
+//                     diagonal block in registers and scales its own row; the block's own eight rows compute the rows
+//                     of W = (8x8 factor)^-1 instead -> Dinv[I] and the diagonal block of X.  Then on to step I+1 as soon
+//                     as the update warps have done the ONE block column it needs.
+//   update warps 4-15 step I: wait for block column I; first the "urgent" blocks — block column I+1 of the trailing
+//                     matrix, what the panel warps are waiting for — then, under the panel warps' next factorisation,
+//                     X row-block I-1 = -W_{I-1} S, S = L[I, 0:8I] X[0:8I, 0:8I] for row-block I, and the rest of the
+//                     rank-8 trailing update.  A global 8x8 block always belongs to the same warp, so the updates of
+//                     one block stay in program order from step to step.
+// Named barriers: 1 = "block column I is scaled" (panel arrives, update warps wait), 2 = "block column I+1 is updated"
+// (update warps arrive, panel waits), 3 = among the update warps (S complete / X row-block complete).
+constexpr int DG2_THREADS = 512, DG2_UW = 12;
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__global__ void __launch_bounds__(DG2_THREADS) sky_diag2_kernel(int d, int n, int prev, const long long* __restrict__ ptr, const int* __restrict__ start,
+                                                                 double* __restrict__ val, double* __restrict__ dinv, int* __restrict__ fail) {
+  constexpr int NB = PW / 8, LDQ = LDT, NW = DG2_THREADS / 32;
+  DIAG_STAMP(0);
+  extern __shared__ __align__(16) double sm_diag[];
+  double* L = sm_diag;                 // [PW][LDQ]
+  double* X = sm_diag + PW * LDQ;      // [PW][LDQ]  only the lower block triangle is ever written or read
+  double* Dinv = X + PW * LDQ;         // [NB][64] inverses of the 8x8 diagonal factors (full 8x8, upper part zero)
+  double* Sb = Dinv + NB * 64;         // [8][LDQ]  S of the current row-block
+  __shared__ long long rbase[PW];
+  __shared__ int bad;
+  __shared__ int rprev[PW];            // 1 = the row's envelope reaches panel d-1
+  const int c0 = d * PW, w = min(PW, n - c0), tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  if (tid == 0) bad = 0;
+  if (tid < PW) {
+    const int r = c0 + tid;
+    const int st = tid < w ? start[r] : 0;
+    rbase[tid] = tid < w ? ptr[r] + (c0 - st) : 0;
+    rprev[tid] = (prev && tid < w && st <= c0 - PW) ? 1 : 0;
+  }
+  __syncthreads();
+#pragma unroll 2
+  for (int i = wid; i < PW; i += NW) {
+    const double* src = val + rbase[i];
+    const bool row_ok = i < w;
+    {
+      const bool ok = row_ok && 2 * lane <= i;               // lower triangle by pairs, the rest zero-filled
+      cp_async16(&L[i * LDQ + 2 * lane], ok ? (const void*)(src + 2 * lane) : (const void*)val, ok);
+    }
+    if (lane < PW / 2 - 32) {
+      const int j2 = lane + 32;
+      const bool ok = row_ok && 2 * j2 <= i;
+      cp_async16(&L[i * LDQ + 2 * j2], ok ? (const void*)(src + 2 * j2) : (const void*)val, ok);
+    }
+    if (prev) {
+      const bool ok = rprev[i] != 0;
+      cp_async16(&X[i * LDQ + 2 * lane], ok ? (const void*)(src - PW + 2 * lane) : (const void*)val, ok);
+      if (lane < PW / 2 - 32) cp_async16(&X[i * LDQ + 2 * (lane + 32)], ok ? (const void*)(src - PW + 2 * (lane + 32)) : (const void*)val, ok);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (prev) {
+    // A_dd -= X X^T on the lower block triangle: 78 blocks of 8x8, two per warp in flight, K = 96
+    constexpr int NBLK = NB * (NB + 1) / 2;
+    for (int b = 2 * wid; b < NBLK; b += 2 * NW) {
+      const bool two = b + 1 < NBLK;
+      const int bsec = two ? b + 1 : b;
+      int bi0, bk0, bi1, bk1; diag_block_of(b, bi0, bk0); diag_block_of(bsec, bi1, bk1);
+      double2* cp0 = reinterpret_cast<double2*>(&L[(8 * bi0 + g) * LDQ + 8 * bk0 + 2 * t]);
+      double2* cp1 = reinterpret_cast<double2*>(&L[(8 * bi1 + g) * LDQ + 8 * bk1 + 2 * t]);
+      double2 u = *cp0, v = *cp1;
+      const double* a0 = &X[(8 * bi0 + g) * LDQ + t]; const double* b0 = &X[(8 * bk0 + g) * LDQ + t];
+      const double* a1 = &X[(8 * bi1 + g) * LDQ + t]; const double* b1 = &X[(8 * bk1 + g) * LDQ + t];
+#pragma unroll 6
+      for (int k = 0; k < PW; k += 4) {
+        dmma884(u.x, u.y, -a0[k], b0[k]);
+        dmma884(v.x, v.y, -a1[k], b1[k]);
+      }
+      *cp0 = u;
+      if (two) *cp1 = v;
+    }
+    __syncthreads();
+  }
+  if (tid >= w && tid < PW) L[tid * LDQ + tid] = 1.0;         // identity padding of a short last panel
+  __syncthreads();
+  DIAG_STAMP(1);
+  if (wid < 4) {
+    // ------------------------------------------------------------------ panel warps
+    double Dg[8][8];
+    for (int I = 0; I < NB; ++I) {
+      const int jb = 8 * I, nrow = PW - jb;
+      if (I > 0) bar_sync_n(2, DG2_THREADS);               // block column I carries every update of the steps before
+      if (tid < nrow) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) Dg[a][c] = (c <= a) ? L[(jb + a) * LDQ + jb + c] : 0.0;
+        double arow[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) arow[c] = L[(jb + tid) * LDQ + jb + c];
+        double dinv8[8];
+        // right-looking, in registers: scale column c, push its rank-1 update to the right; the thread's own row rides along
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          double dd = Dg[c][c];
+          if (!(dd > 0.0)) { if (tid == 0) bad = 1; dd = 1.0; }
+          const double inv = rsqrt(dd);
+          Dg[c][c] = dd * inv; dinv8[c] = inv;
+          arow[c] *= inv;
+#pragma unroll
+          for (int a = 0; a < 8; ++a) if (a > c) Dg[a][c] *= inv;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) if (b > c) {
+            arow[b] -= arow[c] * Dg[b][c];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) if (a >= b) Dg[a][b] -= Dg[a][c] * Dg[b][c];
+          }
+        }
+        if (tid >= 8) {                      // rows below the diagonal block: x = arow * Dg^-T
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(&L[(jb + tid) * LDQ + jb + c]) = make_double2(arow[c], arow[c + 1]);
+        } else {
+          // row `tid` of W = Dg^-1: w Dg = e_tid, solved from the right (entries left of the diagonal only)
+          double wr[8];
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {
+            double sacc = (j == tid) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k > j) sacc -= wr[k] * Dg[k][j];
+            wr[j] = (j <= tid) ? sacc * dinv8[j] : 0.0;
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            *reinterpret_cast<double2*>(&Dinv[I * 64 + tid * 8 + c]) = make_double2(wr[c], wr[c + 1]);
+            *reinterpret_cast<double2*>(&X[(jb + tid) * LDQ + jb + c]) = make_double2(wr[c], wr[c + 1]);
+          }
+        }
+      }
+      __threadfence_block();
+      bar_arrive_n(1, DG2_THREADS);                          // block column I is scaled, W_I is there
+      DIAG_STAMP(2 + 2 * I);
+    }
+  } else {
+    // ------------------------------------------------------------------ update warps
+    const int uw = wid - 4;
+    auto owner_row = [&](int Cb) { int r = (uw - 5 * Cb) % DG2_UW; return r < 0 ? r + DG2_UW : r; };   // the one block row of block column Cb this warp owns
+    auto update_block = [&](int Rb, int Cb, int jb) {
+      double2* cp = reinterpret_cast<double2*>(&L[(8 * Rb + g) * LDQ + 8 * Cb + 2 * t]);
+      double2 c = *cp;
+      const double* ap = &L[(8 * Rb + g) * LDQ + jb + t]; const double* bp = &L[(8 * Cb + g) * LDQ + jb + t];
+      dmma884(c.x, c.y, -ap[0], bp[0]); dmma884(c.x, c.y, -ap[4], bp[4]);
+      *cp = c;                                               // diagonal blocks also get their (unused) upper half
+    };
+    for (int I = 0; I < NB; ++I) {
+      const int jb = 8 * I;
+      bar_sync_n(1, DG2_THREADS);                            // block column I is scaled
+      if (I + 1 < NB) {
+        const int Rb = owner_row(I + 1);                     // urgent: block column I+1, one block per warp at most
+        if (Rb >= I + 1 && Rb < NB) update_block(Rb, I + 1, jb);
+        __threadfence_block();
+        bar_arrive_n(2, DG2_THREADS);
+      }
+      // X row-block I-1 = -W_{I-1} * S  (S of row-block I-1 was completed by all update warps in the step before)
+      if (I >= 1) {
+        bar_sync_n(3, DG2_UW * 32);
+        const int P = I - 1;
+        if (uw < P) {
+          const int J = uw;
+          const double* Wp = Dinv + P * 64;
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int sk = 0; sk < 2; ++sk) dmma884(d0, d1, Wp[g * 8 + 4 * sk + t], Sb[(4 * sk + t) * LDQ + 8 * J + g]);
+          *reinterpret_cast<double2*>(&X[(8 * P + g) * LDQ + 8 * J + 2 * t]) = make_double2(-d0, -d1);
+        }
+        bar_sync_n(3, DG2_UW * 32);                          // X row-block I-1 complete; S may be overwritten
+      }
+      // S[:, 8J..8J+7] = sum_{k = 8J}^{jb-1} L[jb+., k] X[k, 8J+.] for row-block I; two interleaved accumulators
+      if (uw < I) {
+        const int J = uw;
+        double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+        const double* ap = &L[(jb + g) * LDQ + t];
+        const double* bp = &X[t * LDQ + 8 * J + g];
+        for (int k = 8 * J; k + 8 <= jb; k += 8) {
+          dmma884(e0, e1, ap[k], bp[k * LDQ]);
+          dmma884(f0, f1, ap[k + 4], bp[(k + 4) * LDQ]);
+        }
+        *reinterpret_cast<double2*>(&Sb[g * LDQ + 8 * J + 2 * t]) = make_double2(e0 + f0, e1 + f1);
+      }
+      // the rest of the trailing update: block columns I+2 .. (one block per column at most; four columns at a time with
+      // predicated dummies was measured slower: 30.1 vs 25.7 us, tools/diag_lab.cu)
+      for (int Cb = I + 2; Cb < NB; ++Cb) {
+        const int Rb = owner_row(Cb);
+        if (Rb >= Cb && Rb < NB) update_block(Rb, Cb, jb);
+      }
+      DIAG_STAMP_U(3 + 2 * I);
+    }
+    // last row-block: X[NB-1, 0:8(NB-1)] = -W_{NB-1} * S
+    bar_sync_n(3, DG2_UW * 32);
+    if (uw < NB - 1) {
+      const int J = uw;
+      const double* Wp = Dinv + (NB - 1) * 64;
+      double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+      for (int sk = 0; sk < 2; ++sk) dmma884(d0, d1, Wp[g * 8 + 4 * sk + t], Sb[(4 * sk + t) * LDQ + 8 * J + g]);
+      *reinterpret_cast<double2*>(&X[(8 * (NB - 1) + g) * LDQ + 8 * J + 2 * t]) = make_double2(-d0, -d1);
+    }
+  }
+  __syncthreads();
+  DIAG_STAMP(2 + 2 * NB);
+  // Only Linv goes back to memory (L_dd itself has no reader).
+  double* dout = dinv + (size_t)d * PW * PW;
+#pragma unroll 2
+  for (int i = wid; i < PW; i += NW) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = 2 * (lane + 32 * h);                        // j even: (j, j+1) both in the lower triangle unless j == i
@@ -992,6 +1218,7 @@ static const size_t SM_DIAG = sizeof(double) * (2 * PW * LDT + (PW / 8) * 64 + 8
 static const size_t SM_UPD_WS = sizeof(double) * (size_t)WS_NS * WS_STAGE + 2 * (UM + UN) * sizeof(long long) + WS_NS * sizeof(unsigned long long) + WS_NS * sizeof(int) + 4;
 
 static int g_rest_ctas = 132;     // grid of the persistent update kernel
+static int g_diag_mode = 1;       // 0: two barrier phases per step (sky_diag_kernel), 1: panel / update warps pipelined (sky_diag2_kernel)
 static int g_update_mode = 1;     // 0: one tile per CTA (sky_update_kernel), 1: warp-specialised persistent pipeline for rest(d), 2: for next(d) too
 static int set_attrs(std::string* err) {
   // per device (the attributes live in the context) and under a lock (chains are enqueued from several host threads)
@@ -1000,6 +1227,7 @@ static int set_attrs(std::string* err) {
   int cur = 0; cudaGetDevice(&cur);
   if (ready.count(cur)) return PGS_OK;
   SK(cudaFuncSetAttribute(sky_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
+  SK(cudaFuncSetAttribute(sky_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
   SK(cudaFuncSetAttribute(sky_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TRSM));
   SK(cudaFuncSetAttribute(sky_update_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
   SK(cudaFuncSetAttribute(sky_update_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_UPD));
@@ -1008,7 +1236,8 @@ static int set_attrs(std::string* err) {
   { int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     // the persistent update CTAs fill a whole SM each; a few SMs stay free for the kernels of the panel chain
     const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 16; if (g_rest_ctas < 1) g_rest_ctas = 1;
-    const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 2; }
+    const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 2;
+    const char* dm = getenv("PGS_DIAG_MODE"); g_diag_mode = dm ? atoi(dm) : 1; }
   ready.insert(cur);
   return PGS_OK;
 }
@@ -1055,7 +1284,8 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
     const int Tr = (nr + UM - 1) / UM, Tc = (nr + UN - 1) / UN;
     if (d > 0) SK(cudaStreamWaitEvent(s1, f->ev_trsm[(d - 1) % NEV], 0));
     if (d > 1) SK(cudaStreamWaitEvent(s1, f->ev_rest[(d - 2) % NEV], 0));   // rest(d-2) holds part of panel d-2's update of A_dd
-    sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
+    if (g_diag_mode == 1) sky_diag2_kernel<<<1, DG2_THREADS, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
+    else sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
     SK(cudaEventRecord(f->ev_c[d % NEV], s1));
     SK(cudaStreamWaitEvent(s2, f->ev_c[d % NEV], 0));
     double* xp = f->xp + (size_t)(d % XP_RING) * f->xp_stride; long long* rinfo = f->rinfo + (size_t)(d % XP_RING) * f->rinfo_stride;

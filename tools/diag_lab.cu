@@ -6,7 +6,8 @@
 using namespace pgs;
 #define CKL(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); exit(1); } } while (0)
 
-int main() {
+int main(int argc, char** argv) {
+  const int mode = argc > 1 ? atoi(argv[1]) : 1;   // 0: sky_diag_kernel, 1: sky_diag2_kernel
   const int n = PW;
   // one panel: rows 0..95 each store columns [0, 96); SPD matrix A = M M^T + 96 I
   std::vector<double> M(n * n), A(n * n, 0.0);
@@ -21,18 +22,20 @@ int main() {
   CKL(cudaMemcpy(dptr, ptr.data(), sizeof(long long) * (n + 2), cudaMemcpyHostToDevice)); CKL(cudaMemcpy(dstart, start.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
   CKL(cudaMemset(fail, 0, 4));
   CKL(cudaFuncSetAttribute(sky_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
+  CKL(cudaFuncSetAttribute(sky_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_DIAG));
   cudaEvent_t e0, e1; CKL(cudaEventCreate(&e0)); CKL(cudaEventCreate(&e1));
   float best = 1e9;
   for (int rep = 0; rep < 5; ++rep) {
     CKL(cudaMemcpy(val, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
     CKL(cudaEventRecord(e0));
-    sky_diag_kernel<<<1, 256, SM_DIAG>>>(0, n, 0, dptr, dstart, val, dinv, fail);
+    if (mode == 1) sky_diag2_kernel<<<1, DG2_THREADS, SM_DIAG>>>(0, n, 0, dptr, dstart, val, dinv, fail);
+    else sky_diag_kernel<<<1, 256, SM_DIAG>>>(0, n, 0, dptr, dstart, val, dinv, fail);
     CKL(cudaEventRecord(e1)); CKL(cudaEventSynchronize(e1));
     float ms; CKL(cudaEventElapsedTime(&ms, e0, e1)); best = std::min(best, ms);
   }
   CKL(cudaGetLastError());
   long long clk[64]; CKL(cudaMemcpyFromSymbol(clk, g_diag_clk, sizeof(clk)));
-  printf("diag kernel: %.2f us (events, best of 5)\n", best * 1e3);
+  printf("diag kernel (mode %d: %s): %.2f us (events, best of 5)\n", mode, mode ? "panel / update warps pipelined; 'phase A' = panel warps' step, 'phase B' = update warps' step, both since the previous stamp of thread 0 of their group" : "two barrier phases per step", best * 1e3);
   printf("load: %lld cycles\n", clk[1] - clk[0]);
   for (int I = 0; I < PW / 8; ++I) printf("step %2d: phase A %6lld  phase B %6lld cycles\n", I, clk[2 + 2 * I] - clk[1 + 2 * I], clk[3 + 2 * I] - clk[2 + 2 * I]);
   printf("finish: %lld  store: %lld cycles; total %lld cycles\n", clk[2 + 2 * (PW / 8)] - clk[1 + 2 * (PW / 8)], clk[3 + 2 * (PW / 8)] - clk[2 + 2 * (PW / 8)], clk[3 + 2 * (PW / 8)] - clk[0]);
