@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(DG2_THREADS) sky_diag2_kernel(int d, int n, in
   } else {
     // ------------------------------------------------------------------ update warps
     const int uw = wid - 4;
-    auto owner_row = [&](int Cb) { int r = (uw - 5 * Cb) % DG2_UW; return r < 0 ? r + DG2_UW : r; };   // the one block row of block column Cb this warp owns
+    auto owner_row = [&](int Cb) { const int r = uw - Cb; return r < 0 ? r + DG2_UW : r; };   // block (Rb, Cb) belongs to warp (Rb + Cb) mod 12: one block row per block column and warp, no division
     auto update_block = [&](int Rb, int Cb, int jb) {
       double2* cp = reinterpret_cast<double2*>(&L[(8 * Rb + g) * LDQ + 8 * Cb + 2 * t]);
       double2 c = *cp;
