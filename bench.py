@@ -378,7 +378,7 @@ def main():
                 "initial_cost": s["initial_cost"], "final_cost": s["final_cost"], "lm_iters_per_s": n_it / (s["ms_total"] * 1e-3), "ms_total": s["ms_total"],
                 "ms_per_iter": s["ms_total"] / n_it, "ms_sweep": s["ms_sweep"], "ms_assemble": s["ms_assemble"], "ms_linear_solve": s["ms_linear_solve"],
                 "ms_comm": s["ms_comm"], "factor_nnz": s["factor_nnz"], "factor_flops_est": s["factor_flops"], "n_chains": s["n_chains"],
-                "linear_backward_error": {"max": float(be.max()) if len(be) else None, "per_solve": [float(x) for x in be], "what": "||b - A y|| / ||b|| of every linear solve (reduced, scaled, damped pose system)"},
+                "linear_backward_error": {"max": float(be.max()) if len(be) else None, "per_solve": [float(x) for x in be], "what": "componentwise backward error max_i |b - A y|_i / (|A||y| + |b|)_i of every linear solve (reduced, scaled, damped pose system)"},
                 "costs": [r["cost"] for r in s["iterations"]], "accepted": [int(r["step_is_successful"]) for r in s["iterations"]],
                 "switches_off": int((T.switches() < 0.5).sum()), "outliers": int(p["lout"].sum())}
 

@@ -77,8 +77,8 @@ typedef struct pgs_options {
                                                burning from both ends of the keyframe chain from 4096 nodes on, unless the
                                                separator in the middle would be a quarter of the graph), 1 = one natural-order
                                                chain, 2.. = that many; with pgs_dist_init: chains per rank (0 = 1) */
-  int32_t check_linear_solves;              /* != 0: measure the backward error ||b - A y|| / ||b|| of every linear solve
-                                               (one block SpMV each; pgs_get_linear_backward_errors) */
+  int32_t check_linear_solves;              /* != 0: measure the componentwise backward error max_i |b - A y|_i / (|A||y| + |b|)_i of
+                                               every linear solve (one block SpMV each; pgs_get_linear_backward_errors) */
   double max_factor_bytes;                  /* skyline factor larger than this (0 = 80 % of the free device memory) or ... */
   double max_factor_flops;                  /* ... costlier than this per factorisation (0 = no limit): fall back to PGS_BLOCK_PCG */
 } pgs_options;
@@ -100,7 +100,7 @@ typedef struct pgs_summary {
   int32_t linear_solver_used;               /* pgs_linear_solver actually used (PGS_BLOCK_PCG when the skyline estimate exceeded the budget) */
   int32_t n_chains;                         /* elimination chains on this GPU (1 = plain natural order) */
   double factor_flops;                      /* estimated flops of one natural-order factorisation (sum over columns of rows-below^2) */
-  double max_linear_backward_error;         /* max over the linear solves of ||b - A y|| / ||b||; -1 when not measured */
+  double max_linear_backward_error;         /* max over the linear solves of max_i |b - A y|_i / (|A||y| + |b|)_i; -1 when not measured */
   double fixed_cost;                        /* Ceres Summary::fixed_cost: cost of the residual blocks whose parameter blocks are all constant */
   double ms_comm;                           /* device time spent in collectives incl. waiting for other ranks (multi-GPU) */
 } pgs_summary;
@@ -187,7 +187,7 @@ int pgs_dist_init(pgs_handle h, int32_t rank, int32_t world, const void* id128);
  * for hosts that drive several GPUs from one process, and for running any number of ranks on a single GPU. */
 int pgs_dist_init_local(pgs_handle h, int32_t rank, int32_t world, const char* group);
 int pgs_dist_get_stats(pgs_handle h, pgs_dist_stats* out);   /* also valid after a single-GPU solve that used several chains */
-/* Backward errors ||b - A y|| / ||b|| of the linear solves of the last pgs_solve (pgs_options.check_linear_solves),
+/* Componentwise backward errors (Oettli-Prager) of the linear solves of the last pgs_solve (pgs_options.check_linear_solves),
  * in the order they were done; at most cap values are written, *n gets the number available. */
 int pgs_get_linear_backward_errors(pgs_handle h, double* out, int32_t cap, int32_t* n);
 /* The partition rule on its own (host only, no device needed): node_owner[N] = owning rank or -1 for a border

@@ -545,81 +545,79 @@ int Solver::choose_linear_solver() {
   return PGS_OK;
 }
 
-// r = b - A y of the reduced block system (Ad, Ao); one thread per scalar row
+// r = b - A y of the reduced block system (Ad, Ao) and den = |A| |y| + |b|, row by row; one thread per scalar row
 __global__ void lin_residual_kernel(int N, const double* __restrict__ Ad, const double* __restrict__ Ao, const int2* __restrict__ pair,
                                     const int* __restrict__ adj_ptr, const int* __restrict__ adj_item, const double* __restrict__ b,
-                                    const double* __restrict__ y, double* __restrict__ r) {
+                                    const double* __restrict__ y, double* __restrict__ r, double* __restrict__ den) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 6 * N) return;
   const int i = t / 6, a = t % 6;
-  double s = b[t];
+  double s = b[t], m = fabs(b[t]);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) s -= Ad[36 * (size_t)i + 6 * a + c] * y[6 * (size_t)i + c];
+  for (int c = 0; c < 6; ++c) { const double p = Ad[36 * (size_t)i + 6 * a + c] * y[6 * (size_t)i + c]; s -= p; m += fabs(p); }
   for (int q = adj_ptr[i]; q < adj_ptr[i + 1]; ++q) {
-    const int code = adj_item[q], p = code >> 1;
-    const int2 hl = pair[p];
+    const int code = adj_item[q], pp = code >> 1;
+    const int2 hl = pair[pp];
     if (code & 1) {   // this node is the pair's hi: block (row hi, col lo)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) s -= Ao[36 * (size_t)p + 6 * a + c] * y[6 * (size_t)hl.y + c];
+      for (int c = 0; c < 6; ++c) { const double p = Ao[36 * (size_t)pp + 6 * a + c] * y[6 * (size_t)hl.y + c]; s -= p; m += fabs(p); }
     } else {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) s -= Ao[36 * (size_t)p + 6 * c + a] * y[6 * (size_t)hl.x + c];
+      for (int c = 0; c < 6; ++c) { const double p = Ao[36 * (size_t)pp + 6 * c + a] * y[6 * (size_t)hl.x + c]; s -= p; m += fabs(p); }
     }
   }
-  r[t] = s;
+  r[t] = s; den[t] = m;
 }
-// partial[blk] = sum r^2, partial[grid + blk] = sum b^2 over [0, n)
-__global__ void sumsq2_kernel(int n, const double* __restrict__ r, const double* __restrict__ b, double* __restrict__ partial) {
+// partial[blk] = max_i |r_i| / den_i over [0, n) (rows with den == 0 — unused blocks — are skipped)
+__global__ void maxratio_kernel(int n, const double* __restrict__ r, const double* __restrict__ den, double* __restrict__ partial) {
   __shared__ double sm[32];
-  double s0 = 0.0, s1 = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { s0 += r[i] * r[i]; s1 += b[i] * b[i]; }
-  const double t0 = block_sum(s0, sm), t1 = block_sum(s1, sm);
-  if (threadIdx.x == 0) { partial[blockIdx.x] = t0; partial[gridDim.x + blockIdx.x] = t1; }
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) if (den[i] > 0.0) m = fmax(m, fabs(r[i]) / den[i]);
+  const double t = block_max(m, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
-// buf[gpos] <- r of the local border rows, buf[ng6 + gpos] <- b of the local border rows
-__global__ void border_pack_res_kernel(int nb6, int first6, const int* __restrict__ gpos, const double* __restrict__ r, const double* __restrict__ b, int ng6,
+// buf[gpos] <- r of the local border rows, buf[ng6 + gpos] <- den of the local border rows
+__global__ void border_pack_res_kernel(int nb6, int first6, const int* __restrict__ gpos, const double* __restrict__ r, const double* __restrict__ den, int ng6,
                                        double* __restrict__ buf) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nb6) { const int g = 6 * gpos[i / 6] + i % 6; buf[g] = r[first6 + i]; buf[ng6 + g] = b[first6 + i]; }
+  if (i < nb6) { const int g = 6 * gpos[i / 6] + i % 6; buf[g] = r[first6 + i]; buf[ng6 + g] = den[first6 + i]; }
 }
-// the summed border rows lack the damping term: r_b -= damp * z_b
+// the summed border rows lack the damping term: r_b -= damp * z_b, den_b += damp * |z_b|
 __global__ void border_fix_res_kernel(int ng6, const double* __restrict__ damp, const double* __restrict__ zb, double* __restrict__ buf) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ng6) buf[i] -= damp[i] * zb[i];
+  if (i < ng6) { buf[i] -= damp[i] * zb[i]; buf[ng6 + i] += damp[i] * fabs(zb[i]); }
 }
 
-// Backward error of the linear solve just done: ||b - A y|| / ||b|| on the reduced pose system (scaled, damped,
-// switches eliminated).  Sharded: interior rows are local; border rows are summed over the ranks first.
+// Backward error of the linear solve just done, componentwise (Oettli-Prager): max_i |b - A y|_i / (|A| |y| + |b|)_i on
+// the reduced pose system (scaled, damped, switches eliminated) — the size of the smallest relative perturbation of A
+// and b for which y is the exact solution.  Independent of the conditioning and of how small the gradient b has become.
+// Sharded: interior rows are local; border rows (numerator and denominator) are summed over the ranks first.
 int Solver::linear_residual(double* rel) {
   const int n6 = 6 * N;
   *rel = 0.0;
   if (n6 == 0) return PGS_OK;
-  CU(d_pr.resize((size_t)n6));
-  lin_residual_kernel<<<cdiv(n6, 128), 128, 0, stream>>>(N, d_Ad.p, d_Ao.p, d_pair.p, d_adj_ptr.p, d_adj_item.p, d_b.p, d_y.p, d_pr.p);
+  CU(d_pr.resize((size_t)n6)); CU(d_prn.resize((size_t)n6));
+  lin_residual_kernel<<<cdiv(n6, 128), 128, 0, stream>>>(N, d_Ad.p, d_Ao.p, d_pair.p, d_adj_ptr.p, d_adj_item.p, d_b.p, d_y.p, d_pr.p, d_prn.p);
   const int fb = (!chains.empty() && first_border >= 0) ? first_border : N, int6 = 6 * fb, b6 = n6 - int6, ng6 = 6 * n_gborder;
-  const int grid = std::max(1, std::min(MAX_GRID / 2, cdiv(std::max(int6, 1), 256)));
-  double* P = d_partial.p + 2 * MAX_GRID;   // [2][grid]
-  sumsq2_kernel<<<grid, 256, 0, stream>>>(int6, d_pr.p, d_b.p, P);
-  reduce_sum_kernel<<<1, 256, 0, stream>>>(P, grid, 1.0, d_scal.p + L_RES);
-  reduce_sum_kernel<<<1, 256, 0, stream>>>(P + grid, grid, 1.0, d_scal.p + L_RES + 1);
-  if (comm) if (int rc = comm->allreduce_sum(d_scal.p + L_RES, 2, stream, &err)) return rc;
-  double rb = 0.0, bb = 0.0;
-  if (!chains.empty() && ng6 > 0) {
+  const int grid = std::max(1, std::min(MAX_GRID, cdiv(std::max(int6, 1), 256)));
+  double* P = d_partial.p + 2 * MAX_GRID;
+  maxratio_kernel<<<grid, 256, 0, stream>>>(int6, d_pr.p, d_prn.p, P);
+  reduce_max_kernel<<<1, 256, 0, stream>>>(P, grid, d_scal.p + L_RES);
+  if (comm) if (int rc = comm->allreduce_max(d_scal.p + L_RES, 1, stream, &err)) return rc;
+  const bool border = !chains.empty() && ng6 > 0;
+  if (border) {
     CU(d_xbuf.resize(2 * (size_t)ng6));
     CU(cudaMemsetAsync(d_xbuf.p, 0, sizeof(double) * 2 * (size_t)ng6, stream));
-    if (b6) border_pack_res_kernel<<<cdiv(b6, 256), 256, 0, stream>>>(b6, int6, d_border_gpos.p, d_pr.p, d_b.p, ng6, d_xbuf.p);
+    if (b6) border_pack_res_kernel<<<cdiv(b6, 256), 256, 0, stream>>>(b6, int6, d_border_gpos.p, d_pr.p, d_prn.p, ng6, d_xbuf.p);
     if (comm) if (int rc = comm->allreduce_sum(d_xbuf.p, 2 * (size_t)ng6, stream, &err)) return rc;
     border_fix_res_kernel<<<cdiv(ng6, 256), 256, 0, stream>>>(ng6, d_dampb.p, d_zb.p, d_xbuf.p);
-    const int g2 = std::max(1, std::min(MAX_GRID / 2, cdiv(ng6, 256)));
-    sumsq2_kernel<<<g2, 256, 0, stream>>>(ng6, d_xbuf.p, d_xbuf.p + ng6, P);
-    reduce_sum_kernel<<<1, 256, 0, stream>>>(P, g2, 1.0, d_scal.p + L_RES + 2);
-    reduce_sum_kernel<<<1, 256, 0, stream>>>(P + g2, g2, 1.0, d_scal.p + L_RES + 3);
+    const int g2 = std::max(1, std::min(MAX_GRID, cdiv(ng6, 256)));
+    maxratio_kernel<<<g2, 256, 0, stream>>>(ng6, d_xbuf.p, d_xbuf.p + ng6, P);
+    reduce_max_kernel<<<1, 256, 0, stream>>>(P, g2, d_scal.p + L_RES + 1);
   }
   CU(cudaGetLastError());
   if (int rc = read_scalars(L_NSCAL)) return rc;
-  if (!chains.empty() && ng6 > 0) { rb = h_scal[L_RES + 2]; bb = h_scal[L_RES + 3]; }
-  const double r2 = h_scal[L_RES] + rb, b2 = h_scal[L_RES + 1] + bb;
-  *rel = b2 > 0.0 ? std::sqrt(r2 / b2) : 0.0;
+  *rel = std::max(h_scal[L_RES], border ? h_scal[L_RES + 1] : 0.0);
   return PGS_OK;
 }
 
@@ -793,7 +791,8 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
     CU(cudaEventCreateWithFlags(&ev_copy_go, cudaEventDisableTiming));
   }
   const int To = (int)o_pm.size(), Tl = (int)l_pm.size(), Tr = (int)r_pm.size();
-  static const int e2e_mode = [] { const char* e = getenv("PGS_E2E_MODE"); return e ? atoi(e) : 1; }();   // 0 chunked copies, 1 chunked reads of pinned memory, 2 one shot
+  const char* e2e_env = getenv("PGS_E2E_MODE");                                   // 0 chunked copies, 1 chunked reads of pinned memory, 2 one shot
+  const int e2e_mode = e2e_env ? atoi(e2e_env) : 0;
   if (!(q && t) || N < 4096 || e2e_mode == 2) {
     // nothing to overlap: one shot
     if (q && N) {
