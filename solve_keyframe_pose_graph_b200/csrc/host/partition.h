@@ -36,8 +36,9 @@ struct Partition {
 // Time per eliminated node of a range that carries a separator relative to one that does not.  The carried separator
 // roughly triples the flops of a panel's trailing update; a free range is bound by its panel chain (diagonal block +
 // panel solve).  Measured on BASELINE config 5 over 8 GPUs with the round's kernels: 122 us per panel carried against
-// 40.6 us free = 3.0 (with round 1's 32 us diagonal kernel it was 2).  PGS_CARRY_COST in the environment overrides it.
-constexpr double kCarryCost = 3.0;
+// 40.6 us free, plus 6.6 us per panel of backward sweep on either: (122 + 6.6) / (40.6 + 6.6) = 2.75 (with round 1's
+// 32 us diagonal kernel it was 2).  PGS_CARRY_COST in the environment overrides it.
+constexpr double kCarryCost = 2.75;
 
 // chains_per_rank: 0 = default (world == 1: two chains burning from both ends when the graph is large enough,
 // else one; world > 1: one chain per rank).  Odometry edge e couples (oc1[e], oc2[e]); loop edge e couples
