@@ -80,6 +80,26 @@ struct SkylineFactor {
   long long tail = 0;              // extra doubles behind the envelope (travel with it in the border all-reduce)
 };
 
+#ifdef SKY_TIMELINE   // tools/timeline_lab.py: first-CTA-in / last-CTA-out wall-clock stamps (%globaltimer, ns) of every factorisation
+                      // kernel for panels [TL_D0, TL_D0 + TL_ND) of up to four factors that run at the same time
+constexpr int TL_D0 = 1000, TL_ND = 24, TL_KINDS = 5;
+__device__ unsigned long long g_tl[4][TL_KINDS][TL_ND][2];
+__device__ const double* g_tl_val[4];
+__device__ __forceinline__ void tl_stamp(const double* val, int kind, int d, int which) {
+  if (threadIdx.x != 0 || d < TL_D0 || d >= TL_D0 + TL_ND) return;
+  int ch = -1;
+  for (int i = 0; i < 4; ++i) if (g_tl_val[i] == val) ch = i;
+  if (ch < 0) return;
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (which == 0) atomicMin(&g_tl[ch][kind][d - TL_D0][0], t); else atomicMax(&g_tl[ch][kind][d - TL_D0][1], t);
+}
+#define TL_IN(val, kind, d) tl_stamp(val, kind, d, 0)
+#define TL_OUT(val, kind, d) tl_stamp(val, kind, d, 1)
+#else
+#define TL_IN(val, kind, d) do { } while (0)
+#define TL_OUT(val, kind, d) do { } while (0)
+#endif
+
 #define SK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { if (err) *err = std::string("skyline: ") + cudaGetErrorString(e__) + " at " #x; return e__ == cudaErrorMemoryAllocation ? PGS_ERR_OUT_OF_MEMORY : PGS_ERR_CUDA; } } while (0)
 
 void skyline_destroy(SkylineFactor* f) {
@@ -178,6 +198,11 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
   if (n_pairs) { cudaMemcpyAsync(f->pair_hi, pair_hi, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream);
                  cudaMemcpyAsync(f->pair_lo, pair_lo, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream); }
   if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return bad(e, "upload");
+#ifdef SKY_TIMELINE
+  { static int n_reg = 0;
+    if (n_reg == 0) { static unsigned long long init[4][TL_KINDS][TL_ND][2]; for (auto& a : init) for (auto& b : a) for (auto& c : b) { c[0] = ~0ull; c[1] = 0; } cudaMemcpyToSymbol(g_tl, init, sizeof(init)); }
+    if (n_reg < 4) { const double* v = f->val; cudaMemcpyToSymbol(g_tl_val, &v, sizeof(v), sizeof(v) * n_reg); ++n_reg; } }
+#endif
   return f;
 }
 
@@ -210,6 +235,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool va
   const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled, nothing is read
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
 }
+// programmatic dependent launch: wait = the launch before this one on the stream is complete and its writes are visible;
+// launch = the launch after this one may be scheduled (it runs up to its own wait)
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int NGROUPS>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NGROUPS)); }
@@ -494,6 +523,7 @@ __global__ void __launch_bounds__(DG2_THREADS) sky_diag2_kernel(int d, int n, in
                                                                  double* __restrict__ val, double* __restrict__ dinv, int* __restrict__ fail) {
   constexpr int NB = PW / 8, LDQ = LDT, NW = DG2_THREADS / 32;
   DIAG_STAMP(0);
+  TL_IN(val, 0, d);
   extern __shared__ __align__(16) double sm_diag[];
   double* L = sm_diag;                 // [PW][LDQ]
   double* X = sm_diag + PW * LDQ;      // [PW][LDQ]  only the lower block triangle is ever written or read
@@ -697,6 +727,7 @@ __global__ void __launch_bounds__(DG2_THREADS) sky_diag2_kernel(int d, int n, in
   }
   if (tid == 0 && bad) *fail = 1;
   DIAG_STAMP(3 + 2 * NB);
+  TL_OUT(val, 0, d);
 }
 
 // trsm: X[r][j] = sum_k A[r][c0+k] * Linv[j][k] for the rows r in R_d, in place.  32 rows x 96 columns per CTA;
@@ -713,6 +744,7 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
   const int c0 = d * PW, tid = threadIdx.x;
   const int rb = rows_ptr[d], nr = rows_ptr[d + 1] - rb;
   const int row0 = blockIdx.x * TR;
+  TL_IN(val, 1, d);
   if (tid < TR) {
     long long b = -1; int r = -1;
     if (row0 + tid < nr) { r = rows_idx[rb + row0 + tid]; b = ptr[r] + (c0 - start[r]); }
@@ -774,6 +806,7 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
       *reinterpret_cast<double2*>(xp + ((size_t)(c / KC) * rpad + row0 + rl) * LDK + c % KC) = v;
     }
   }
+  TL_OUT(val, 1, d);
 }
 
 // update: A[r][c] -= X[r,:] . X[c,:] over the tiles (ti, tj) of R_d x R_d that intersect the lower triangle, except
@@ -998,6 +1031,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int
   const int g = lane >> 2, t = lane & 3;
   const int wm = wid % WARPS_M, wn = wid / WARPS_M;
   WS_STAMP(0);
+  TL_IN(val, 2 + PART, d);
   if (tid == 0) {
     for (int s = 0; s < WS_NS; ++s) { mbar_init(full + s, 1); done[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1111,6 +1145,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int
     WS_STAMP(11 + 12 * it);
     ti = tin; tj = tjn;
   }
+  TL_OUT(val, 2 + PART, d);
 }
 
 // backward sweep, one launch per panel d = D-1 .. 0 (plus one leading launch that only computes x of the last panel):
@@ -1121,10 +1156,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sky_update_ws_kernel(int d, int
 //             x_{d-1} = Linv_{d-1}^T (y_{d-1} + acc_{d-1}) while the other CTAs push into the columns further left.
 //             No counter, no fence: every accumulator entry is touched by one CTA per launch.
 // Border panels of a partial factorisation (d >= D_elim) take x as given: they push, nobody computes them.
+// The sweep is a chain of thousands of launches, each waiting for the one before and each a few microseconds long, so
+// what it costs is latency.  Launches are therefore programmatic dependent launches: everything a launch needs that no
+// earlier launch of the sweep writes — the factor entries, Linv, the right-hand side, the row tables — is fetched BEFORE
+// griddepcontrol.wait, i.e. while the launch before is still running; only x of panel d and the accumulators are read
+// after it.  launch_dependents follows the wait, so at most two launches of a sweep are resident at a time.
 __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo, int do_push, int next_d, long long rhs_off, const long long* __restrict__ ptr,
                                                            const int* __restrict__ start, const double* __restrict__ val, const double* __restrict__ dinv,
                                                            double* __restrict__ acc, double* __restrict__ x) {
-  __shared__ double xs[PW], red[8][33];
+  constexpr int BWB = 4;                // blocks of 32 columns per CTA and round (BW_COLS = 32 BWB columns)
+  __shared__ double xs[PW], red[BWB][8][33];
   __shared__ long long rbase[PW];       // ptr[r] - start[r]
   __shared__ int rstart[PW];
   const int tid = threadIdx.x;
@@ -1133,56 +1174,79 @@ __global__ void __launch_bounds__(256) sky_backward_kernel(int d, int n, int lo,
   if (do_push && tid < PW) {
     const int r = c0 + tid;
     rbase[tid] = tid < w ? ptr[r] - start[r] : 0; rstart[tid] = tid < w ? start[r] : 0x7fffffff;
-    xs[tid] = tid < w ? x[c0 + tid] : 0.0;
   }
+  __syncthreads();
   if (blockIdx.x != 0) {
-    // ---- CTAs 1..: the columns left of panel d-1
-    __syncthreads();
+    // ---- CTAs 1..: the columns left of panel d-1, 128 per CTA and round: thread (column cx of each of the four blocks,
+    // row group g of 12 rows) has its 48 factor entries in flight at once; one reduction over the row groups per round
     const int cx = tid & 31, g = tid >> 5;
     const int cend = max(lo, c0 - PW);
-    for (int cb = lo + (blockIdx.x - 1) * 32; cb < cend; cb += (gridDim.x - 1) * 32) {
-      const int c = cb + cx;
-      double s = 0.0;
-      if (c < cend) {
+    const int cb0 = lo + (blockIdx.x - 1) * (32 * BWB), cstep = (gridDim.x - 1) * (32 * BWB);
+    double v[BWB][PW / 8];
+    auto fetch = [&](int cb) {
 #pragma unroll
-        for (int q = 0; q < PW / 8; ++q) {
-          const int i = g * (PW / 8) + q;
-          if (c >= rstart[i]) s += val[rbase[i] + c] * xs[i];
-        }
+      for (int k = 0; k < BWB; ++k) {
+        const int c = cb + 32 * k + cx;
+#pragma unroll
+        for (int q = 0; q < PW / 8; ++q) { const int i = g * (PW / 8) + q; v[k][q] = (c < cend && c >= rstart[i]) ? val[rbase[i] + c] : 0.0; }
       }
-      red[g][cx] = s;
+    };
+    if (cb0 < cend) fetch(cb0);                       // the first (mostly the only) round: before the wait
+    grid_dep_wait();
+    grid_dep_launch();
+    if (tid < PW) xs[tid] = tid < w ? x[c0 + tid] : 0.0;
+    const int ck = tid >> 5, cc = tid & 31;           // threads 0..127 own column 32 ck + cc of the round
+    double a_old = 0.0;
+    if (tid < 32 * BWB && cb0 + tid < cend) a_old = acc[cb0 + tid];
+    __syncthreads();
+    for (int cb = cb0; cb < cend; cb += cstep) {
+      if (cb != cb0) { fetch(cb); if (tid < 32 * BWB && cb + tid < cend) a_old = acc[cb + tid]; }
+#pragma unroll
+      for (int k = 0; k < BWB; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < PW / 8; ++q) s += v[k][q] * xs[g * (PW / 8) + q];
+        red[k][g][cx] = s;
+      }
       __syncthreads();
-      if (g == 0 && c < cend) {
+      if (tid < 32 * BWB && cb + tid < cend) {
         double tt = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) tt += red[q][cx];
-        acc[c] -= tt;
+        for (int q = 0; q < 8; ++q) tt += red[ck][q][cc];
+        acc[cb + tid] = a_old - tt;
       }
       __syncthreads();
     }
     return;
   }
-  // ---- CTA 0: finish panel d-1.  Everything that does not depend on this launch's push is fetched first: the
-  // right-hand side, the accumulator as the earlier launches left it, and this thread's share of Linv_{d-1}.
+  // ---- CTA 0: finish panel d-1.  Everything that does not depend on the earlier launches is fetched first: the
+  // right-hand side, this thread's share of Linv_{d-1} and of the factor block (panel d rows, panel d-1 columns).
   __shared__ double half[2][PW], part[8][PW];
   const int cn0 = next_d * PW, wn = next_d >= 0 ? min(PW, n - cn0) : 0;
   const int ln = tid & 31, wq = tid >> 5;
   double rhs_pref = 0.0, li[PW / 8][3];
   if (next_d >= 0) {
-    if (tid < wn) rhs_pref = val[rhs_off + cn0 + tid] + acc[cn0 + tid];
+    if (tid < wn) rhs_pref = val[rhs_off + cn0 + tid];
     const double* Li = dinv + (size_t)next_d * PW * PW;
 #pragma unroll
     for (int q = 0; q < PW / 8; ++q) { const int i = wq + 8 * q; li[q][0] = Li[i * PW + ln]; li[q][1] = Li[i * PW + 32 + ln]; li[q][2] = Li[i * PW + 64 + ln]; }
   }
-  __syncthreads();
-  // push of panel d into the 96 columns of panel d-1 in one round trip: thread (column, row half)
-  if (tid < 2 * PW) {
-    const int cl = tid % PW, h = tid / PW, c = c0 - PW + cl;
-    double s = 0.0;
-    if (do_push && c >= lo) {
-      double v[PW / 2];                     // all 48 loads in flight: one round trip
+  // push of panel d into the 96 columns of panel d-1 in one round trip: thread (column, row half), all 48 loads in flight
+  const int cl = tid % PW, h = tid / PW, cpush = c0 - PW + cl;
+  const bool pusher = tid < 2 * PW && do_push && cpush >= lo;
+  double v[PW / 2];
+  if (pusher) {
 #pragma unroll
-      for (int q = 0; q < PW / 2; ++q) { const int i = h * (PW / 2) + q; v[q] = c >= rstart[i] ? val[rbase[i] + c] : 0.0; }
+    for (int q = 0; q < PW / 2; ++q) { const int i = h * (PW / 2) + q; v[q] = cpush >= rstart[i] ? val[rbase[i] + cpush] : 0.0; }
+  }
+  grid_dep_wait();
+  grid_dep_launch();
+  if (tid < PW) xs[tid] = tid < w ? x[c0 + tid] : 0.0;
+  if (next_d >= 0 && tid < wn) rhs_pref += acc[cn0 + tid];     // the accumulator as the earlier launches left it
+  __syncthreads();
+  if (tid < 2 * PW) {
+    double s = 0.0;
+    if (pusher) {
 #pragma unroll
       for (int q = 0; q < PW / 2; ++q) s += v[q] * xs[h * (PW / 2) + q];
     }
@@ -1219,6 +1283,7 @@ static const size_t SM_UPD_WS = sizeof(double) * (size_t)WS_NS * WS_STAGE + 2 * 
 
 static int g_rest_ctas = 132;     // grid of the persistent update kernel
 static int g_diag_mode = 1;       // 0: two barrier phases per step (sky_diag_kernel), 1: panel / update warps pipelined (sky_diag2_kernel)
+static int g_backward_pdl = 1;    // backward sweep as programmatic dependent launches (PGS_BACKWARD_PDL=0: plain launches)
 static int g_update_mode = 1;     // 0: one tile per CTA (sky_update_kernel), 1: warp-specialised persistent pipeline for rest(d), 2: for next(d) too
 static int set_attrs(std::string* err) {
   // per device (the attributes live in the context) and under a lock (chains are enqueued from several host threads)
@@ -1237,7 +1302,8 @@ static int set_attrs(std::string* err) {
     // the persistent update CTAs fill a whole SM each; a few SMs stay free for the kernels of the panel chain
     const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 16; if (g_rest_ctas < 1) g_rest_ctas = 1;
     const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 2;
-    const char* dm = getenv("PGS_DIAG_MODE"); g_diag_mode = dm ? atoi(dm) : 1; }
+    const char* dm = getenv("PGS_DIAG_MODE"); g_diag_mode = dm ? atoi(dm) : 1;
+    const char* bp = getenv("PGS_BACKWARD_PDL"); g_backward_pdl = bp ? atoi(bp) : 1; }
   ready.insert(cur);
   return PGS_OK;
 }
@@ -1315,19 +1381,33 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
 }
 
 // Backward substitution L^T x = y.  Panels >= D_elim (border, multi-GPU) take x as given in y[] beforehand.
-static int skyline_backward_launches(SkylineFactor* f, double* y, std::string* err) {
+// Every launch but the first is a programmatic dependent launch of the one before (see the kernel); the first one is an
+// ordinary launch, so nothing of the sweep starts before the work queued ahead of it on the stream is complete.
+static int skyline_backward_launches(SkylineFactor* f, double* y, std::string* err, bool allow_pdl = true) {
   cudaStream_t st = f->stream;
   const int n = f->n, D = f->D;
   const long long rhs_off = f->h_ptr[n];
+  bool first = true;
+  auto launch = [&](int grid, int d, int lo, int do_push, int next_d) -> cudaError_t {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    const bool pdl = allow_pdl && g_backward_pdl && !first;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    first = false;
+    return cudaLaunchKernelEx(&cfg, sky_backward_kernel, d, n, lo, do_push, next_d, rhs_off, (const long long*)f->ptr, (const int*)f->start,
+                              (const double*)f->val, (const double*)f->dinv, f->xacc, y);
+  };
   // x of the last panel (unless it is a given border panel)
-  if (D - 1 < f->D_elim) sky_backward_kernel<<<1, 256, 0, st>>>(D, n, 0, 0, D - 1, rhs_off, f->ptr, f->start, f->val, f->dinv, f->xacc, y);
+  if (D - 1 < f->D_elim) SK(launch(1, D, 0, 0, D - 1));
   for (int d = D - 1; d >= 0; --d) {
     const int cols = d * PW - f->h_lo[d];
     const int next_d = (d - 1 >= 0 && d - 1 < f->D_elim) ? d - 1 : -1;
     if (cols <= 0 && next_d < 0) continue;
-    const int left = std::max(0, cols - PW);                      // columns left of panel d-1, shared by CTAs 1..
-    const int grid = 1 + std::min(591, (left + 31) / 32);
-    sky_backward_kernel<<<grid, 256, 0, st>>>(d, n, f->h_lo[d], cols > 0 ? 1 : 0, next_d, rhs_off, f->ptr, f->start, f->val, f->dinv, f->xacc, y);
+    const int left = std::max(0, cols - PW);                      // columns left of panel d-1, shared by CTAs 1.. (128 per CTA and round)
+    const int grid = 1 + std::min(147, (left + 127) / 128);
+    SK(launch(grid, d, f->h_lo[d], cols > 0 ? 1 : 0, next_d));
   }
   SK(cudaGetLastError());
   return PGS_OK;
@@ -1345,7 +1425,7 @@ int skyline_backward(SkylineFactor* f, double* y, std::string* err) {
     cudaGraph_t g = nullptr;
     bool ok = cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
-      const int rc = skyline_backward_launches(f, y, err);
+      const int rc = skyline_backward_launches(f, y, err, false);
       ok = cudaStreamEndCapture(f->stream, &g) == cudaSuccess && rc == PGS_OK && g;
     }
     if (ok) ok = cudaGraphInstantiate(&f->bw_graph, g, 0) == cudaSuccess;
@@ -1406,6 +1486,12 @@ int skyline_add_diagonal(SkylineFactor* f, const double* add, std::string* err) 
   SK(cudaGetLastError());
   return PGS_OK;
 }
+#ifdef SKY_TIMELINE
+extern "C" int pgs_debug_timeline(unsigned long long* out, int* d0, int* nd, int* kinds) {
+  *d0 = TL_D0; *nd = TL_ND; *kinds = TL_KINDS;
+  return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * TL_KINDS * TL_ND * 2) == cudaSuccess ? 0 : 1;
+}
+#endif
 int skyline_interior_scalars(const SkylineFactor* f) { return f->D_elim * PW; }
 const int* skyline_fail_flag(const SkylineFactor* f) { return f->fail; }
 
