@@ -35,10 +35,11 @@ struct Partition {
 
 // Time per eliminated node of a range that carries a separator relative to one that does not.  The carried separator
 // roughly triples the flops of a panel's trailing update; a free range is bound by its panel chain (diagonal block +
-// panel solve).  Measured on BASELINE config 5 over 8 GPUs with the round's kernels: 122 us per panel carried against
-// 40.6 us free, plus 6.6 us per panel of backward sweep on either: (122 + 6.6) / (40.6 + 6.6) = 2.75 (with round 1's
-// 32 us diagonal kernel it was 2).  PGS_CARRY_COST in the environment overrides it.
-constexpr double kCarryCost = 2.75;
+// panel solve).  Measured with the round's kernels: 122 us per panel carried (BASELINE config 5 over 8 GPUs) against
+// 38.8 us free (chain mode 1, profiles/r02_timeline_c3_one_chain_mode1.txt), plus 2.2 us per panel of backward sweep on
+// either since it became a chain of programmatic dependent launches: (122 + 2.2) / (38.8 + 2.2) = 3.0 (2.75 with the
+// 6.6 us backward launches and the 40.6 us chain; 2 with round 1's 32 us diagonal kernel).  PGS_CARRY_COST overrides it.
+constexpr double kCarryCost = 3.0;
 
 // chains_per_rank: 0 = default (world == 1: two chains burning from both ends when the graph is large enough,
 // else one; world > 1: one chain per rank).  Odometry edge e couples (oc1[e], oc2[e]); loop edge e couples

@@ -56,7 +56,7 @@ struct SkylineFactor {
   int D_elim = 0;                  // panels to eliminate (== D for a full factorisation)
   int share = 1;                   // factorisations that run on this GPU at the same time (chains): the persistent update takes 1/share of its SMs
   cudaStream_t stream = nullptr, s1 = nullptr, s2 = nullptr;   // main (rest), chain (C), panel (trsm + next)
-  cudaEvent_t ev_trsm[NEV], ev_rest[NEV], ev_c[NEV], ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  cudaEvent_t ev_trsm[NEV], ev_rest[NEV], ev_c[NEV], ev_next[NEV], ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   unsigned int* sched = nullptr;   // [2] CTAs-done counter of the backward sweep (self-resetting)
   std::vector<int> h_start;        // per scalar row (n+1 entries, last = rhs row)
   std::vector<long long> h_ptr;    // n+2
@@ -108,7 +108,7 @@ void skyline_destroy(SkylineFactor* f) {
   cudaFree(f->xacc); cudaFree(f->fail); cudaFree(f->pair_hi); cudaFree(f->pair_lo); cudaFree(f->sched); cudaFree(f->node_src); cudaFree(f->pair_src); cudaFree(f->xp); cudaFree(f->rinfo);
   if (f->bw_graph) cudaGraphExecDestroy(f->bw_graph);
   if (f->h_fail) cudaFreeHost(f->h_fail);
-  for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); if (f->ev_c[i]) cudaEventDestroy(f->ev_c[i]); }
+  for (int i = 0; i < NEV; ++i) { if (f->ev_trsm[i]) cudaEventDestroy(f->ev_trsm[i]); if (f->ev_rest[i]) cudaEventDestroy(f->ev_rest[i]); if (f->ev_c[i]) cudaEventDestroy(f->ev_c[i]); if (f->ev_next[i]) cudaEventDestroy(f->ev_next[i]); }
   if (f->ev_fork) cudaEventDestroy(f->ev_fork);
   if (f->ev_join) cudaEventDestroy(f->ev_join);
   if (f->ev_join2) cudaEventDestroy(f->ev_join2);
@@ -123,7 +123,7 @@ int skyline_panel_width() { return PW; }
 SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int* pair_lo, cudaStream_t stream, std::string* err,
                               int n_border_nodes, bool dense, const int* node_src, const int* pair_src, long long tail) {
   SkylineFactor* f = new SkylineFactor();
-  for (int i = 0; i < NEV; ++i) { f->ev_trsm[i] = nullptr; f->ev_rest[i] = nullptr; f->ev_c[i] = nullptr; }
+  for (int i = 0; i < NEV; ++i) { f->ev_trsm[i] = nullptr; f->ev_rest[i] = nullptr; f->ev_c[i] = nullptr; f->ev_next[i] = nullptr; }
   f->N = N; f->n = 6 * N; f->D = (f->n + PW - 1) / PW; f->stream = stream; f->n_pairs = n_pairs; f->tail = tail;
   const int n = f->n, D = f->D;
   const int N_int = dense ? 0 : N - n_border_nodes;           // interior nodes come first, border nodes last
@@ -169,6 +169,7 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
   if ((e = cudaMalloc((void**)&f->rows_ptr, sizeof(int) * (D + 1))) != cudaSuccess) return bad(e, "rows_ptr");
   if ((e = cudaMalloc((void**)&f->rows_idx, sizeof(int) * std::max<size_t>(rows_idx.size(), 1))) != cudaSuccess) return bad(e, "rows_idx");
   if ((e = cudaMalloc((void**)&f->dinv, sizeof(double) * (size_t)std::max(D, 1) * PW * PW)) != cudaSuccess) return bad(e, "dinv");
+  if ((e = cudaMemsetAsync(f->dinv, 0, sizeof(double) * (size_t)std::max(D, 1) * PW * PW, stream)) != cudaSuccess) return bad(e, "dinv");   // the kernels write the lower triangles only
   if ((e = cudaMalloc((void**)&f->xacc, sizeof(double) * (size_t)std::max(D, 1) * PW)) != cudaSuccess) return bad(e, "xacc");
   if ((e = cudaMalloc((void**)&f->fail, sizeof(int))) != cudaSuccess) return bad(e, "fail");
   f->rpad = ((f->max_rows + UM - 1) / UM) * UM;
@@ -187,6 +188,7 @@ SkylineFactor* skyline_create(int N, int n_pairs, const int* pair_hi, const int*
     if ((e = cudaEventCreateWithFlags(&f->ev_trsm[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
     if ((e = cudaEventCreateWithFlags(&f->ev_rest[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
     if ((e = cudaEventCreateWithFlags(&f->ev_c[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
+    if ((e = cudaEventCreateWithFlags(&f->ev_next[i], cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
   }
   if ((e = cudaEventCreateWithFlags(&f->ev_join2, cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
   if ((e = cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bad(e, "event");
@@ -555,7 +557,11 @@ __global__ void __launch_bounds__(DG2_THREADS) sky_diag2_kernel(int d, int n, in
       const bool ok = row_ok && 2 * j2 <= i;
       cp_async16(&L[i * LDQ + 2 * j2], ok ? (const void*)(src + 2 * j2) : (const void*)val, ok);
     }
-    if (prev) {
+  }
+  if (prev) {
+#pragma unroll 2
+    for (int i = wid; i < PW; i += NW) {
+      const double* src = val + rbase[i];
       const bool ok = rprev[i] != 0;
       cp_async16(&X[i * LDQ + 2 * lane], ok ? (const void*)(src - PW + 2 * lane) : (const void*)val, ok);
       if (lane < PW / 2 - 32) cp_async16(&X[i * LDQ + 2 * (lane + 32)], ok ? (const void*)(src - PW + 2 * (lane + 32)) : (const void*)val, ok);
@@ -712,16 +718,17 @@ __global__ void __launch_bounds__(DG2_THREADS) sky_diag2_kernel(int d, int n, in
   }
   __syncthreads();
   DIAG_STAMP(2 + 2 * NB);
-  // Only Linv goes back to memory (L_dd itself has no reader).
+  // Only Linv goes back to memory (L_dd itself has no reader), and only its lower triangle: the array is zeroed when the
+  // factor is created and nothing else is ever written above the diagonal or into the padding rows of a short last panel.
   double* dout = dinv + (size_t)d * PW * PW;
 #pragma unroll 2
-  for (int i = wid; i < PW; i += NW) {
+  for (int i = wid; i < w; i += NW) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = 2 * (lane + 32 * h);                        // j even: (j, j+1) both in the lower triangle unless j == i
-      if (j >= PW) break;
-      double2 x = make_double2(0.0, 0.0);
-      if (i < w && j <= i) { x = *reinterpret_cast<const double2*>(&X[i * LDQ + j]); if (j == i) x.y = 0.0; }
+      if (j > i) break;
+      double2 x = *reinterpret_cast<const double2*>(&X[i * LDQ + j]);
+      if (j == i) x.y = 0.0;
       *reinterpret_cast<double2*>(dout + i * PW + j) = x;
     }
   }
@@ -768,7 +775,7 @@ __global__ void __launch_bounds__(256, 2) sky_trsm_kernel(int d, int n, const lo
   }
   for (int e = tid; e < PW * (PW / 2); e += blockDim.x) {
     const int i = e / (PW / 2), j2 = e % (PW / 2);
-    cp_async16(&Li[i * LDT + 2 * j2], dsrc + i * PW + 2 * j2, true);
+    cp_async16(&Li[i * LDT + 2 * j2], dsrc + i * PW + 2 * j2, 2 * j2 <= i);   // above the diagonal: zero-filled, nothing read
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -1283,6 +1290,7 @@ static const size_t SM_UPD_WS = sizeof(double) * (size_t)WS_NS * WS_STAGE + 2 * 
 
 static int g_rest_ctas = 132;     // grid of the persistent update kernel
 static int g_diag_mode = 1;       // 0: two barrier phases per step (sky_diag_kernel), 1: panel / update warps pipelined (sky_diag2_kernel)
+static int g_chain_mode = 1;      // 1: C(d) and trsm(d) alternate on the chain stream, 0: trsm(d) on the panel stream (PGS_CHAIN_MODE)
 static int g_backward_pdl = 1;    // backward sweep as programmatic dependent launches (PGS_BACKWARD_PDL=0: plain launches)
 static int g_update_mode = 1;     // 0: one tile per CTA (sky_update_kernel), 1: warp-specialised persistent pipeline for rest(d), 2: for next(d) too
 static int set_attrs(std::string* err) {
@@ -1303,7 +1311,8 @@ static int set_attrs(std::string* err) {
     const char* e = getenv("PGS_REST_SMS"); g_rest_ctas = e ? atoi(e) : nsm - 16; if (g_rest_ctas < 1) g_rest_ctas = 1;
     const char* m = getenv("PGS_UPDATE_MODE"); g_update_mode = m ? atoi(m) : 2;
     const char* dm = getenv("PGS_DIAG_MODE"); g_diag_mode = dm ? atoi(dm) : 1;
-    const char* bp = getenv("PGS_BACKWARD_PDL"); g_backward_pdl = bp ? atoi(bp) : 1; }
+    const char* bp = getenv("PGS_BACKWARD_PDL"); g_backward_pdl = bp ? atoi(bp) : 1;
+    const char* cm = getenv("PGS_CHAIN_MODE"); g_chain_mode = cm ? atoi(cm) : 1; }
   ready.insert(cur);
   return PGS_OK;
 }
@@ -1345,24 +1354,44 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
   // The persistent update CTAs fill a whole SM each; g_rest_ctas SMs are theirs, split between the factorisations that
   // share the GPU, the others stay free for the kernels of the panel chains (diag, trsm, next) at all times.
   const int rest_ctas = std::max(1, g_rest_ctas / f->share);
+  // Chain mode 1 (the default): C(d) and trsm(d) alternate on the chain stream, so the critical path C(d) -> trsm(d) ->
+  // C(d+1) has no cross-stream event hop of its own, and next(d) has the panel stream to itself:
+  //   chain stream s1:  [wait rest(d-2)] C(d)   [wait next(d-1)] trsm(d) -> ev_trsm[d]
+  //   panel stream s2:  [wait trsm(d), rest(d-1)] next(d) -> ev_next[d]
+  //   main  stream s0:  [wait trsm(d)] rest(d) -> ev_rest[d]
+  // Measured 38.8 us per panel against 41.0 for one chain on config 3 (profiles/r02_timeline_c3_one_chain*.txt).  The two
+  // are plain launches: with a wait for another stream's event between them a programmatic dependent launch does not start
+  // early (tools/pdl_lab.cu), and waiting on the device instead, with event records left between the launches, stalled
+  // the events (profiles/r02_backward_pdl_and_chain_labs.txt).
+  const bool chain1 = g_chain_mode == 1 && g_diag_mode == 1;
   for (int d = 0; d < f->D_elim; ++d) {
     const int nr = f->h_rows_ptr[d + 1] - f->h_rows_ptr[d];
     const int Tr = (nr + UM - 1) / UM, Tc = (nr + UN - 1) / UN;
-    if (d > 0) SK(cudaStreamWaitEvent(s1, f->ev_trsm[(d - 1) % NEV], 0));
-    if (d > 1) SK(cudaStreamWaitEvent(s1, f->ev_rest[(d - 2) % NEV], 0));   // rest(d-2) holds part of panel d-2's update of A_dd
-    if (g_diag_mode == 1) sky_diag2_kernel<<<1, DG2_THREADS, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
-    else sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
-    SK(cudaEventRecord(f->ev_c[d % NEV], s1));
-    SK(cudaStreamWaitEvent(s2, f->ev_c[d % NEV], 0));
     double* xp = f->xp + (size_t)(d % XP_RING) * f->xp_stride; long long* rinfo = f->rinfo + (size_t)(d % XP_RING) * f->rinfo_stride;
-    sky_trsm_kernel<<<Tr * (UM / TR), 256, SM_TRSM, s2>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val, xp, rinfo, f->rpad);
-    SK(cudaEventRecord(f->ev_trsm[d % NEV], s2));
+    if (chain1) {
+      if (d > 1) SK(cudaStreamWaitEvent(s1, f->ev_rest[(d - 2) % NEV], 0));
+      sky_diag2_kernel<<<1, DG2_THREADS, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
+      if (d > 0) SK(cudaStreamWaitEvent(s1, f->ev_next[(d - 1) % NEV], 0));
+      sky_trsm_kernel<<<Tr * (UM / TR), 256, SM_TRSM, s1>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val, xp, rinfo, f->rpad);
+      SK(cudaEventRecord(f->ev_trsm[d % NEV], s1));
+      SK(cudaStreamWaitEvent(s2, f->ev_trsm[d % NEV], 0));
+    } else {
+      if (d > 0) SK(cudaStreamWaitEvent(s1, f->ev_trsm[(d - 1) % NEV], 0));
+      if (d > 1) SK(cudaStreamWaitEvent(s1, f->ev_rest[(d - 2) % NEV], 0));   // rest(d-2) holds part of panel d-2's update of A_dd
+      if (g_diag_mode == 1) sky_diag2_kernel<<<1, DG2_THREADS, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
+      else sky_diag_kernel<<<1, 256, SM_DIAG, s1>>>(d, n, d > 0 ? 1 : 0, f->ptr, f->start, f->val, f->dinv, f->fail);
+      SK(cudaEventRecord(f->ev_c[d % NEV], s1));
+      SK(cudaStreamWaitEvent(s2, f->ev_c[d % NEV], 0));
+      sky_trsm_kernel<<<Tr * (UM / TR), 256, SM_TRSM, s2>>>(d, n, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->dinv, f->val, xp, rinfo, f->rpad);
+      SK(cudaEventRecord(f->ev_trsm[d % NEV], s2));
+    }
     // C(d+1) applies panel d's update to its own diagonal block; past the eliminated part nobody does, so next(d) keeps it.
     // The rhs row (index n) is always live, also when the last panel is short.
     const int skip_below = (d + 1 < f->D_elim) ? std::min((d + 2) * PW, n) : 0;
     if (d > 0) SK(cudaStreamWaitEvent(s2, f->ev_rest[(d - 1) % NEV], 0));
     if (g_update_mode >= 2) sky_update_ws_kernel<0><<<std::min(2 * Tr, g_rest_ctas), WS_THREADS, SM_UPD_WS, s2>>>(d, n, skip_below, Tr, Tc, 2 * Tr, f->rpad, xp, rinfo, f->val);
     else sky_update_kernel<0><<<2 * Tr, 256, SM_UPD, s2>>>(d, n, skip_below, Tr, Tc, f->ptr, f->start, f->rows_ptr, f->rows_idx, f->val);
+    if (chain1) SK(cudaEventRecord(f->ev_next[d % NEV], s2));
     SK(cudaStreamWaitEvent(s0, f->ev_trsm[d % NEV], 0));
     if (Tr > 1) {
       const int nt = Tr * (Tr - 1);

@@ -23,9 +23,9 @@ def test_partition_rule_properties(world):
     cut = list(P["cut"])
     assert cut[0] == 0 and cut[-1] == N and all(a < b for a, b in zip(cut, cut[1:]))
     if world >= 3:
-        # ranges between the two free ends carry a separator through their elimination: 1 / 2.75 of the nodes (kCarryCost)
+        # ranges between the two free ends carry a separator through their elimination: 1 / 3.0 of the nodes (kCarryCost)
         sizes = np.diff(cut)
-        assert abs(sizes[0] - sizes[-1]) <= 1 and all(abs(2.75 * m - sizes[0]) <= 3 for m in sizes[1:-1])
+        assert abs(sizes[0] - sizes[-1]) <= 1 and all(abs(3.0 * m - sizes[0]) <= 3 for m in sizes[1:-1])
         assert list(P["chain_down"]) == [0] * (world - 1) + [1]      # the last range burns downwards from the free top end
     rng = np.searchsorted(cut, np.arange(N), side="right") - 1
     # interior nodes stay in their range; removing the border disconnects the ranges
