@@ -118,6 +118,19 @@ int64_t NodeDataManager::getNodeTimestamp(int i) const {
   if (i < 0 || i >= (int)node_timestamps.size()) return -1;
   return node_timestamps[i];
 }
+void NodeDataManager::snapshot_nodes(int from, int to, std::vector<Matrix4d>& poses, std::vector<int>& world_of) const {
+  std::vector<int64_t> stamps;
+  {
+    std::lock_guard<std::mutex> lk(node_mutex);
+    from = std::max(from, 0); to = std::min(to, (int)node_pose.size());
+    const int n = std::max(0, to - from);
+    poses.assign(node_pose.begin() + from, node_pose.begin() + from + n);
+    stamps.assign(node_timestamps.begin() + from, node_timestamps.begin() + from + n);
+  }
+  std::lock_guard<std::mutex> lk(mutex_kidnap);
+  world_of.resize(stamps.size());
+  for (size_t i = 0; i < stamps.size(); ++i) world_of[i] = which_world_nolock(stamps[i]);
+}
 int NodeDataManager::getEdgeLen() const { std::lock_guard<std::mutex> lk(edge_mutex); return (int)loopclosure_edges.size(); }
 const Matrix4d& NodeDataManager::getEdgePose(int i) const { std::lock_guard<std::mutex> lk(edge_mutex); return loopclosure_p_T_c[i]; }
 const std::pair<int, int>& NodeDataManager::getEdgeIdxInfo(int i) const { std::lock_guard<std::mutex> lk(edge_mutex); return loopclosure_edges[i]; }

@@ -44,6 +44,9 @@ class NodeDataManager {
   bool nodePoseExists(int i) const;
   bool getNodeCov(int i, double* cov36) const;               // reference NodeDataManager.cpp:363-381
   int64_t getNodeTimestamp(int i) const;
+  // Keyframes [from, to) in one locked pass: odometry pose and which_world_is_this(stamp) of each (what the trigger otherwise asks
+  // for keyframe by keyframe, a lock per call)
+  void snapshot_nodes(int from, int to, std::vector<Matrix4d>& poses, std::vector<int>& world_of) const;
   // ---- edge getters
   int getEdgeLen() const;
   const Matrix4d& getEdgePose(int i) const;                 // b_T_a

@@ -4,9 +4,29 @@
 #include <chrono>
 #include <cmath>
 #include <limits>
+#include <cstdlib>
 #include <thread>
 
 namespace pgs {
+
+namespace {
+// fn(chunk, lo, hi) over [begin, end) in contiguous chunks, one host thread per chunk; the chunks are in index order, so
+// results gathered chunk by chunk come out exactly as a sequential loop would produce them
+template <class F>
+void for_chunks(int begin, int end, int min_per_chunk, std::vector<int>* bounds, F&& fn) {
+  const int n = std::max(0, end - begin);
+  int T = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("PGS_HOST_THREADS")) T = std::max(1, std::min(16, atoi(e)));
+  T = std::max(1, std::min(T, n / std::max(1, min_per_chunk)));
+  bounds->resize(T + 1);
+  for (int k = 0; k <= T; ++k) (*bounds)[k] = begin + (int)((long long)n * k / T);
+  if (T == 1) { fn(0, begin, end); return; }
+  std::vector<std::thread> th;
+  for (int k = 1; k < T; ++k) th.emplace_back([&, k] { fn(k, (*bounds)[k], (*bounds)[k + 1]); });
+  fn(0, (*bounds)[0], (*bounds)[1]);
+  for (std::thread& t : th) t.join();
+}
+}  // namespace
 
 PoseGraphSLAM::PoseGraphSLAM(NodeDataManager* _manager, const PoseGraphSLAMOptions& options) : manager(_manager), opt_(options) {
   solved_until = 0;
@@ -151,7 +171,13 @@ bool PoseGraphSLAM::load_state() {
 bool PoseGraphSLAM::solve_once(bool force) {
   clear_error();
   const int node_len = manager->getNodeLen();
-  const int loopedge_len = manager->getEdgeLen();
+  int loopedge_len = manager->getEdgeLen();
+  // threaded ingest: a loop edge that arrived after node_len was read may name a keyframe this trigger does not know yet;
+  // it and the edges behind it wait for the next trigger
+  for (int e = loops_taken_until_; e < loopedge_len; ++e) {
+    const std::pair<int, int> ab = manager->getEdgeIdxInfo(e);
+    if (ab.first >= node_len || ab.second >= node_len) { loopedge_len = e; break; }
+  }
   // trigger only on new loop edges, never while kidnapped (PoseGraphSLAM.cpp:1306-1319)
   bool explicit_pending;
   { std::lock_guard<std::mutex> lk(mutex_pending_); explicit_pending = !pending_explicit_odom_.empty(); }
@@ -162,24 +188,33 @@ bool PoseGraphSLAM::solve_once(bool force) {
   Worlds* worlds = manager->getWorldsPtr();
 
   // -0- new optimisation variables (identity for now; step 4 writes the guesses)   [:1340-1367]
-  for (int yp = n_opt_variables(); yp < node_len; ++yp) allocate_and_append_new_opt_variable_withpose(Matrix4d::Identity());
-  for (int yp = n_opt_switch(); yp < loopedge_len; ++yp) allocate_and_append_new_edge_switch_var();
+  {
+    double qi[4], ti[3];
+    mat_to_raw_xyzw(Matrix4d::Identity(), qi, ti);
+    std::lock_guard<std::mutex> lk(mutex_opt_vars);
+    for (int yp = (int)(_opt_t_.size() / 3); yp < node_len; ++yp) { _opt_quat_.insert(_opt_quat_.end(), qi, qi + 4); _opt_t_.insert(_opt_t_.end(), ti, ti + 3); }
+    if ((int)_opt_switch_.size() < loopedge_len) _opt_switch_.resize(loopedge_len, opt_.solver.switch_init);   // 0.99, PoseGraphSLAM.cpp:353
+  }
+
+  // odometry pose and world of every keyframe: one locked snapshot instead of a lock per call
+  std::vector<Matrix4d> m_pose; std::vector<int> world_of;
+  manager->snapshot_nodes(0, node_len, m_pose, world_of);
 
   // -1/2- loop edges, intra and inter world   [:1381-1559]
   loop_slot_.resize(loopedge_len, -1);
+  { std::lock_guard<std::mutex> lk(mutex_residue_info); loop_edges_terms.reserve(loop_edges_terms.size() + (size_t)std::max(0, loopedge_len - loops_taken_until_)); }
   for (int e = loops_taken_until_; e < loopedge_len; ++e) {
     const Matrix4d bTa = manager->getEdgePose(e);
     const double weight = manager->getEdgeWeight(e);
     const std::pair<int, int> paur = manager->getEdgeIdxInfo(e);
     const int _a = paur.first, _b = paur.second;
     if (_a == _b) continue;                     // both stamps resolved to the same keyframe: no constraint, no block
-    const int a_world = manager->which_world_is_this(manager->getNodeTimestamp(_a));
-    const int b_world = manager->which_world_is_this(manager->getNodeTimestamp(_b));
+    const int a_world = world_of[_a], b_world = world_of[_b];              // which_world_is_this(getNodeTimestamp(.))
     if (a_world < 0 || b_world < 0) continue;   // an endpoint lies in a dead zone; its switch slot stays unused
     if (a_world != b_world && !worlds->is_exist(b_world, a_world)) {
       // first edge between two unconnected sets fixes the relative pose of the worlds from ODOMETRY poses [:1459-1464]
-      const Matrix4d wa_T_a = manager->getNodePose(_a);
-      const Matrix4d wb_T_b = manager->getNodePose(_b);
+      const Matrix4d& wa_T_a = m_pose[_a];
+      const Matrix4d& wb_T_b = m_pose[_b];
       const Matrix4d wb_T_wa = (wb_T_b * bTa) * wa_T_a.inverse();
       std::map<int, int> before, after;
       worlds->getWorld2SetIDMap(before);
@@ -201,36 +236,47 @@ bool PoseGraphSLAM::solve_once(bool force) {
 
   loops_taken_until_ = loopedge_len;
 
+  // The per-keyframe rules below read nothing but the snapshot and the set of a world, so the loops run in contiguous chunks on
+  // the host's cores (every keyframe's terms depend on that keyframe alone; the chunks are concatenated in order, so the lists
+  // are those of the sequential loop).  PGS_HOST_THREADS caps the thread count (default: the host's cores, at most 16).
+  std::vector<int> set_of_world;
+  { std::map<int, int> w2s; worlds->getWorld2SetIDMap(w2s); for (const auto& kv : w2s) { if (kv.first >= (int)set_of_world.size()) set_of_world.resize(kv.first + 1, -1); set_of_world[kv.first] = kv.second; } }
+  auto set_of = [&](int world) { return (world >= 0 && world < (int)set_of_world.size()) ? set_of_world[world] : -1; };   // find_setID_of_world_i
+
   // -3- odometry edges u <-> u-f for u in (solvedUntil, node_len)   [:1570-1639]
   std::vector<OdomTerm> new_odom;
   if (opt_.derive_odometry) {
-    for (int u = std::max(solvedUntil(), odom_added_until_) + 1; u < node_len; ++u) {
-      const int world_of_u = manager->which_world_is_this(manager->getNodeTimestamp(u));
-      const int set_u = worlds->find_setID_of_world_i(world_of_u);
-      for (int f = 1; f <= opt_.odom_fanout; ++f) {
-        int world_umf = -1;
-        if (u - f >= 0) world_umf = manager->which_world_is_this(manager->getNodeTimestamp(u - f));
-        const int set_umf = worlds->find_setID_of_world_i(world_umf);
-        if (set_u < 0 || set_umf < 0) continue;   // note: same-world is NOT checked, as in the reference
-        if (u - f < 0) continue;
-        const Matrix4d w_M_u = manager->getNodePose(u);
-        const Matrix4d w_M_umf = manager->getNodePose(u - f);
-        const Matrix4d u_M_umf = w_M_u.inverse() * w_M_umf;
-        double ypr[3];
-        R2ypr(u_M_umf, ypr);   // degrees
-        OdomTerm o; o.u = u; o.umf = u - f;
-        o.weight = std::pow(opt_.odom_decay, f) * std::exp(-ypr[0] * ypr[0] / opt_.odom_yaw_divisor);
-        mat_to_raw_xyzw(u_M_umf, o.q, o.t);
-        new_odom.push_back(o);
+    const int u0 = std::max(solvedUntil(), odom_added_until_) + 1;
+    std::vector<int> bounds; std::vector<std::vector<OdomTerm>> part(16);
+    for_chunks(u0, node_len, 2048, &bounds, [&](int k, int lo, int hi) {
+      std::vector<OdomTerm>& out = part[k];
+      out.reserve((size_t)std::max(0, hi - lo) * (size_t)std::max(1, opt_.odom_fanout));
+      for (int u = lo; u < hi; ++u) {
+        const int set_u = set_of(world_of[u]);
+        if (set_u < 0) continue;
+        const Matrix4d u_M_w = m_pose[u].inverse();
+        for (int f = 1; f <= opt_.odom_fanout; ++f) {
+          if (u - f < 0) continue;
+          if (set_of(world_of[u - f]) < 0) continue;   // note: same-world is NOT checked, as in the reference
+          const Matrix4d u_M_umf = u_M_w * m_pose[u - f];
+          double ypr[3];
+          R2ypr(u_M_umf, ypr);   // degrees
+          OdomTerm o; o.u = u; o.umf = u - f;
+          o.weight = std::pow(opt_.odom_decay, f) * std::exp(-ypr[0] * ypr[0] / opt_.odom_yaw_divisor);
+          mat_to_raw_xyzw(u_M_umf, o.q, o.t);
+          out.push_back(o);
+        }
       }
-    }
+    });
+    for (size_t k = 0; k + 1 < bounds.size(); ++k) new_odom.insert(new_odom.end(), part[k].begin(), part[k].end());
   }
   { std::lock_guard<std::mutex> lk(mutex_pending_);
     for (const OdomTerm& o : pending_explicit_odom_) new_odom.push_back(o);
     pending_explicit_odom_.clear(); }
   {
     std::lock_guard<std::mutex> lk(mutex_residue_info);
-    for (const OdomTerm& o : new_odom) odometry_edges_terms.push_back(std::make_tuple(o.u, o.umf, (float)o.weight, std::string("")));
+    odometry_edges_terms.reserve(odometry_edges_terms.size() + new_odom.size());
+    for (const OdomTerm& o : new_odom) odometry_edges_terms.emplace_back(o.u, o.umf, (float)o.weight, std::string());
   }
   odom_terms_.insert(odom_terms_.end(), new_odom.begin(), new_odom.end());
   if (opt_.derive_odometry) odom_added_until_ = std::max(odom_added_until_, node_len - 1);
@@ -239,39 +285,78 @@ bool PoseGraphSLAM::solve_once(bool force) {
   // -4- initial guesses for every node   [:1649-1793]
   {
     const int su = solvedUntil();
-    int su_world = manager->which_world_is_this(manager->getNodeTimestamp(su));
+    int su_world = (su >= 0 && su < node_len) ? world_of[su] : manager->which_world_is_this(manager->getNodeTimestamp(su));
     if (su_world < 0) su_world = -su_world - 1;
-    for (int u = 0; u < node_len; ++u) {
-      const int world_of_u = manager->which_world_is_this(manager->getNodeTimestamp(u));
-      const int set_u = worlds->find_setID_of_world_i(world_of_u);
-      if (set_u < 0) continue;   // kidnapped node
-      Matrix4d wset_T_w = Matrix4d::Identity();
-      if (set_u != world_of_u) {
-        bool ok = true;
-        if (worlds->is_exist(set_u, world_of_u)) wset_T_w = worlds->getPoseBetweenWorlds(set_u, world_of_u, &ok); else ok = false;
-        if (!ok) return fail("initial guess: no pose between set " + std::to_string(set_u) + " and world " + std::to_string(world_of_u) + " (reference exit(3))");
-      }
+    // relative poses between a world and its set root, and between the sets a merge of this trigger changed: looked up once
+    std::vector<Matrix4d> wset_T_w_of(set_of_world.size(), Matrix4d::Identity());
+    std::vector<char> wset_ok(set_of_world.size(), 1);
+    for (int w = 0; w < (int)set_of_world.size(); ++w) {
+      const int set_w = set_of_world[w];
+      if (set_w < 0 || set_w == w) continue;
+      bool ok = true;
+      if (worlds->is_exist(set_w, w)) wset_T_w_of[w] = worlds->getPoseBetweenWorlds(set_w, w, &ok); else ok = false;
+      wset_ok[w] = ok ? 1 : 0;
+    }
+    std::map<int, Matrix4d> wsetnew_T_wsetold_of; std::map<int, char> change_ok;
+    for (const auto& kv : changes_to_setid_on_set_union) {
+      bool ok = true;
+      wsetnew_T_wsetold_of[kv.first] = worlds->getPoseBetweenWorlds(std::get<1>(kv.second), std::get<0>(kv.second), &ok);
+      change_ok[kv.first] = ok ? 1 : 0;
+    }
+    std::vector<double> q, t;
+    { std::lock_guard<std::mutex> lk(mutex_opt_vars); q = _opt_quat_; t = _opt_t_; }
+    const Matrix4d su_M_w = (su >= 0 && su < node_len) ? m_pose[su].inverse() : Matrix4d::Identity();
+    Matrix4d opt_su = Matrix4d::Identity();                                         // this->getNodePose(su) as the keyframes after su see it
+    auto put = [&](int u, const Matrix4d& pose) { mat_to_raw_xyzw(pose, &q[4 * (size_t)u], &t[3 * (size_t)u]); };   // update_opt_variable_with
+    auto guess = [&](int u) -> int {                                                // 0, or why the reference would have exited
+      const int world_of_u = world_of[u];
+      const int set_u = set_of(world_of_u);
+      if (set_u < 0) return 0;   // kidnapped node
+      if (set_u != world_of_u && !wset_ok[world_of_u]) return 1;
       const bool before = (u <= su);
       const bool in_change = changes_to_setid_on_set_union.count(world_of_u) > 0;
       if (in_change && before) {
-        if (set_u == su_world) return fail("initial guess: changed set equals the last solved world (reference exit(8))");
-        const int old_setid = std::get<0>(changes_to_setid_on_set_union[world_of_u]);
-        const int new_setid = std::get<1>(changes_to_setid_on_set_union[world_of_u]);
-        bool ok = true;
-        const Matrix4d wsetnew_T_wsetold = worlds->getPoseBetweenWorlds(new_setid, old_setid, &ok);
-        if (!ok) return fail("initial guess: no pose between new and old set");
-        update_opt_variable_with(u, wsetnew_T_wsetold * this->getNodePose(u));
+        if (set_u == su_world) return 2;
+        if (!change_ok.at(world_of_u)) return 3;
+        put(u, wsetnew_T_wsetold_of.at(world_of_u) * raw_xyzw_to_mat(&q[4 * (size_t)u], &t[3 * (size_t)u]));
       } else if (!before) {
         // both !before branches of the reference are identical [:1727-1751, :1766-1786]
-        if (su_world == world_of_u) {
-          const Matrix4d last_M_u = manager->getNodePose(su).inverse() * manager->getNodePose(u);
-          update_opt_variable_with(u, this->getNodePose(su) * last_M_u);     // dead-reckon from the last solved node
-        } else {
-          update_opt_variable_with(u, wset_T_w * manager->getNodePose(u));   // odometry pose mapped into the set root's frame
-        }
+        if (su_world == world_of_u) put(u, opt_su * (su_M_w * m_pose[u]));         // dead-reckon from the last solved node
+        else put(u, wset_T_w_of[world_of_u] * m_pose[u]);                           // odometry pose mapped into the set root's frame
       } else if (su == 0) {
-        update_opt_variable_with(u, manager->getNodePose(u));                // very first trigger [:1756-1760]
-      }                                                                      // else: keep the previous solution
+        put(u, m_pose[u]);                                                          // very first trigger [:1756-1760]
+      }                                                                             // else: keep the previous solution
+      return 0;
+    };
+    // Keyframe su first: the keyframes after it dead-reckon from its pose as this very loop leaves it (re-based by a set
+    // merge, or the odometry pose on the very first trigger); every other keyframe reads only its own entry.
+    int su_why = 0;
+    if (su >= 0 && su < node_len) {
+      su_why = guess(su);
+      opt_su = raw_xyzw_to_mat(&q[4 * (size_t)su], &t[3 * (size_t)su]);
+    }
+    // first failing keyframe of every chunk (the sequential loop stops at the first one overall)
+    std::vector<int> bounds; std::vector<int> bad_u(16, -1), bad_why(16, 0);
+    for_chunks(0, node_len, 4096, &bounds, [&](int k, int lo, int hi) {
+      for (int u = lo; u < hi; ++u) {
+        const int why_u = (u == su) ? su_why : guess(u);
+        if (why_u) { bad_u[k] = u; bad_why[k] = why_u; return; }
+      }
+    });
+    int first_bad = -1, why = 0;
+    for (size_t k = 0; k + 1 < bounds.size(); ++k) if (bad_u[k] >= 0) { first_bad = bad_u[k]; why = bad_why[k]; break; }
+    // keyframes before the first failing one have their guesses, as after the sequential loop's early return
+    {
+      std::lock_guard<std::mutex> lk(mutex_opt_vars);
+      const size_t upto = first_bad >= 0 ? (size_t)first_bad : (size_t)node_len;
+      std::copy(q.begin(), q.begin() + 4 * upto, _opt_quat_.begin());
+      std::copy(t.begin(), t.begin() + 3 * upto, _opt_t_.begin());
+    }
+    if (first_bad >= 0) {
+      const int world_of_u = world_of[first_bad];
+      if (why == 1) return fail("initial guess: no pose between set " + std::to_string(set_of(world_of_u)) + " and world " + std::to_string(world_of_u) + " (reference exit(3))");
+      if (why == 2) return fail("initial guess: changed set equals the last solved world (reference exit(8))");
+      return fail("initial guess: no pose between new and old set");
     }
   }
 

@@ -314,3 +314,38 @@ def test_loop_edge_onto_the_same_keyframe_builds_no_block_and_later_triggers_go_
     assert len(F.odom_terms()["u"]) == n_odom            # nothing new to derive, nothing derived twice
     assert not F.solve_once() and F.solve_once(force=True) and len(F.odom_terms()["u"]) == n_odom
     F.close()
+
+
+@pytest.mark.parametrize("config,kw", [(2, dict(n_nodes=9000, n_loop=900)), (4, dict(n_nodes=2500, n_interworld=40))])
+def test_trigger_on_several_host_threads_equals_the_sequential_trigger(config, kw, monkeypatch):
+    """solve_once runs its per-keyframe rules (odometry terms, initial guesses) in contiguous chunks on the host's cores
+    (csrc/host/PoseGraphSLAM.cpp for_chunks); the lists and guesses must be those of one thread, bit for bit — across
+    worlds (config 4), and for a second wake-up that dead-reckons the new keyframes from the last solved one (config 2)."""
+    g = synth.generate_config(config, **kw)
+    runs = {}
+    for threads in ("1", "5"):
+        monkeypatch.setenv("PGS_HOST_THREADS", threads)
+        F = facade.Facade(odom_fanout=3, dry_run=True)
+        if config == 4:
+            F.ingest(g)
+            assert F.solve_once()
+            snap = [F.odom_terms(), F.poses(), F.reg_terms()]
+        else:
+            cut = int(0.6 * g["N"])
+            keep = (g["la"] < cut) & (g["lb"] < cut)
+            F.add_nodes(g["stamps"][:cut], g["q"][:cut], g["t"][:cut])
+            F.add_loop_edges(g["la"][keep], g["lb"][keep], g["lq"][keep], g["lt"][keep], g["lw"][keep])
+            assert F.solve_once()
+            snap = [F.odom_terms(), F.poses(), F.reg_terms()]
+            F.add_nodes(g["stamps"][cut:], g["q"][cut:], g["t"][cut:])
+            F.add_loop_edges(g["la"][~keep], g["lb"][~keep], g["lq"][~keep], g["lt"][~keep], g["lw"][~keep])
+            assert F.solve_once()
+            snap += [F.odom_terms(), F.poses(), F.reg_terms()]
+        runs[threads] = snap
+        F.close()
+    for a, b in zip(runs["1"], runs["5"]):
+        if isinstance(a, dict):
+            assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) for k in a)
+        else:
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert len(runs["1"][0]["u"]) > 3 * 2048   # several chunks were in play
