@@ -1,4 +1,5 @@
 #include "PoseGraphSLAM.h"
+#include "host_lap.h"
 
 #include <algorithm>
 #include <chrono>
@@ -186,6 +187,7 @@ bool PoseGraphSLAM::solve_once(bool force) {
   if (node_len == 0) { status = 0; return false; }
   status = 1;
   Worlds* worlds = manager->getWorldsPtr();
+  HostLap lap;
 
   // -0- new optimisation variables (identity for now; step 4 writes the guesses)   [:1340-1367]
   {
@@ -377,6 +379,7 @@ bool PoseGraphSLAM::solve_once(bool force) {
   }
   changes_to_setid_on_set_union.clear();
 
+  lap.lap("trigger rules (host)");
   // -6- hand the problem to the device and solve   [:1887-1924]
   if (!opt_.dry_run) {
     if (!handle_) {
@@ -414,11 +417,13 @@ bool PoseGraphSLAM::solve_once(bool force) {
     }
     if (rc != PGS_OK) return fail(std::string("device problem update: ") + pgs_last_error(handle_));
 
+    lap.lap("problem -> C-ABI");
     status = 2;
     pgs_summary sum{};
     std::vector<pgs_iteration> its(opt_.solver.max_num_iterations + 8, pgs_iteration{});
     rc = pgs_solve(handle_, &sum, its.data(), (int)its.size());
     if (rc != PGS_OK) return fail(std::string("pgs_solve: ") + pgs_last_error(handle_));
+    lap.lap("pgs_solve");
     its.resize(std::min<size_t>(its.size(), (size_t)std::max(sum.num_iterations, 0)));
     { std::lock_guard<std::mutex> lk(mutex_summary_); summary_ = sum; iterations_.swap(its); }   // readers on other threads get copies
     // read the solution back and publish it under the mutex in one go: like Ceres with
@@ -432,6 +437,7 @@ bool PoseGraphSLAM::solve_once(bool force) {
       _opt_quat_ = q; _opt_t_ = t;
       for (int e = 0; e < loopedge_len; ++e) if (loop_slot_[e] >= 0) _opt_switch_[e] = sw[loop_slot_[e]];
     }
+    lap.lap("poses + switches back");
   } else {
     n_device_loops_ = (int)loop_a_.size();
   }

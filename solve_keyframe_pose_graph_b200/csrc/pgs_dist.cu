@@ -308,6 +308,7 @@ bool Solver::want_chains() const {
 int Solver::solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap) {
   Comm* C = comm_owned.get();
   const int rank = C ? C->rank : 0, world = C ? C->world : 1;
+  HostLap lap;
   if (int rc = sync_params_to_host()) return rc;
   const int Eo = (int)o_c1.size(), El = (int)l_a.size(), K = (int)r_node.size();
   const int PN = skyline_panel_width() / 6;
@@ -426,7 +427,9 @@ int Solver::solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap) {
   if (C) { const int a = C->agree(build_rc, stream, &err); if (a) { inner.reset(); inner_dirty = true; return build_rc ? build_rc : a; } }
   else if (build_rc) { inner.reset(); inner_dirty = true; return build_rc; }
   if (C) { C->n_collectives = 0; C->bytes_reduced = 0; }
+  lap.lap("plan + local problem");
   if (int rc = inner->solve(sum, iters, cap)) { err = inner->err; return rc; }
+  lap.lap("inner solve (all of it)");
   if (sum && world == 1) sum->factor_flops = est_flops;   // natural-order estimate: two chains meeting in the middle do the same work
 
   // gather: every rank contributes its interior poses, the border poses it counts and its owned switches
@@ -443,6 +446,7 @@ int Solver::solve_dist(pgs_summary* sum, pgs_iteration* iters, int cap) {
     }
     for (size_t l = 0; l < s.size(); ++l) h_sw[loop2glob[l]] = s[l];
     host_params_newer = true; device_params_newer = false;
+    lap.lap("read-back");
     return PGS_OK;
   }
   // summed into a zero-initialised global vector -> every rank ends up with the complete solution

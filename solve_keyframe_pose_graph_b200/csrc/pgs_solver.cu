@@ -864,7 +864,9 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     if (inner_dirty) plain_chain = false;
     if (!plain_chain) { const int rc = solve_dist(sum, iters, cap); if (rc != PGS_PLAIN_CHAIN) return rc; }
   }
+  HostLap lap;
   if (int rc = sync_params_to_device()) return rc;
+  lap.lap(is_inner ? "inner: structure + upload" : "structure + upload");
   const bool sharded = !chains.empty();
   border_scale_ready = false;
   ms_sweep = ms_asm = ms_lin = ms_comm = ms_eliminate = ms_exchange = ms_border = 0.0;
@@ -875,6 +877,7 @@ int Solver::solve(pgs_summary* sum, pgs_iteration* iters, int cap) {
     if (comm) { const int a = comm->agree(prc, stream, &err); if (a) return prc ? prc : a; }
     else if (prc) return prc;
   }
+  lap.lap("factor symbolic + allocation");
   CU(cudaEventRecord(ev_t0, stream));
   const int El = (int)l_a.size(), Eo = (int)o_c1.size(), K = (int)r_node.size();
   const int rgrid = std::max(1, std::min(1024, cdiv(std::max(N, El), 256)));

@@ -12,9 +12,12 @@
 #include <vector>
 #include <memory>
 #include "../../include/pgs.h"
+#include "host/host_lap.h"
 #include "pgs_comm.h"
 
 namespace pgs {
+
+
 
 template <class T>
 struct DBuf {
