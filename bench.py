@@ -30,6 +30,9 @@ import sys
 import threading
 import time
 
+# before anything creates the CUDA context: see solve_keyframe_pose_graph_b200/__init__.py (streams of one solve must not share a hardware queue)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

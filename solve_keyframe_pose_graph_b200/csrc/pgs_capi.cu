@@ -1,4 +1,5 @@
 // extern "C" surface declared in include/pgs.h.  Thin: argument checks + dispatch into pgs::Solver.
+#include <cstdlib>
 #include <exception>
 #include <new>
 #include <string>
@@ -7,6 +8,13 @@
 
 using pgs::Solver;
 static thread_local std::string g_create_error;
+
+// A factorisation needs its streams (panel chain, next-panel tiles, trailing update; per elimination chain) to overlap.  With
+// the driver's default of 8 hardware work queues per context, streams of a process that runs other streams as well (NCCL, a
+// framework) come to share a queue and serialise each other — measured 56 us per panel instead of 38 on every rank of a 2-
+// and a 4-GPU solve.  The variable is read when the CUDA context is created: it is set here, when the library is loaded,
+// unless the host has chosen a value itself; a host that creates its context before loading libpgs.so has to set it itself.
+__attribute__((constructor)) static void pgs_more_hardware_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 struct pgs_solver_s { Solver* s; };
 
 #define H(h) do { if (!(h) || !(h)->s) return PGS_ERR_INVALID_ARGUMENT; } while (0)
