@@ -791,6 +791,9 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
     CU(cudaEventCreateWithFlags(&ev_copy_go, cudaEventDisableTiming));
   }
   const int To = (int)o_pm.size(), Tl = (int)l_pm.size(), Tr = (int)r_pm.size();
+  // The cost goes straight into the pinned read-back buffer (device-visible under unified addressing): the CTA that reduces the
+  // tile partials stores it over the bus, and the stream synchronisation below is all the host waits for — no 8-byte copy.
+  double* cost_dst = h_scal + L_COST;
   const char* e2e_env = getenv("PGS_E2E_MODE");                                   // 0 chunked copies, 1 chunked reads of pinned memory, 2 one shot
   const int e2e_mode = e2e_env ? atoi(e2e_env) : 0;
   if (!(q && t) || N < 4096 || e2e_mode == 2) {
@@ -804,7 +807,7 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
       CU(cudaMemcpyAsync(d_stage_s.p, s, sizeof(double) * (size_t)El, cudaMemcpyHostToDevice, stream));
       gather_kernel<<<cdiv(El, 256), 256, 0, stream>>>(El, d_perm_l.p, d_stage_s.p, d_sw.p);
     }
-    if (int rc = launch_sweep(0, d_pose.p, d_sw.p, d_scal.p + L_COST)) return rc;
+    if (int rc = launch_sweep(0, d_pose.p, d_sw.p, cost_dst)) return rc;
   } else {
     constexpr int NCHUNK = (int)(sizeof(ev_chunk) / sizeof(ev_chunk[0]));
     // Pinned (registered) host memory is visible to the device: the pack kernel then reads q and t straight over the bus,
@@ -825,6 +828,7 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
     }
     int done_o = 0, done_l = 0, done_r = 0;
     for (int k = 0; k < NCHUNK; ++k) {
+      // equal chunks: chunks that shrink towards the end (a last chunk of 4.5 % of the keyframes) were measured no faster, 188.4 vs 189.0 us
       const int n0 = (int)((long long)N * k / NCHUNK), n1 = (int)((long long)N * (k + 1) / NCHUNK);
       if (direct) {
         // few CTAs: the bus is the bound, and the SMs are wanted by the sweep of the previous chunk
@@ -843,11 +847,10 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
       const int up_l = last ? Tl : (int)(std::upper_bound(l_pm.begin(), l_pm.end(), n1 - 1) - l_pm.begin());
       const int up_r = last ? Tr : (int)(std::upper_bound(r_pm.begin(), r_pm.end(), n1 - 1) - r_pm.begin());
       const int ranges[6] = {done_o, up_o, done_l, up_l, done_r, up_r};
-      if (int rc = launch_sweep(0, d_pose.p, d_sw.p, d_scal.p + L_COST, nullptr, ranges, last ? 1 : 0)) return rc;
+      if (int rc = launch_sweep(0, d_pose.p, d_sw.p, cost_dst, nullptr, ranges, last ? 1 : 0)) return rc;
       done_o = up_o; done_l = up_l; done_r = up_r;
     }
   }
-  CU(cudaMemcpyAsync(h_scal + L_COST, d_scal.p + L_COST, sizeof(double), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));
   if (cost) *cost = h_scal[L_COST];
   device_params_newer = true;   // host mirrors are refreshed lazily by the getters
