@@ -154,7 +154,7 @@ def test_regulariser_autodiff_closed_fd_and_sign_branches():
         Jf = fd_tangent(f, [q], [t], None, 6)
         assert np.abs(Jf - Ja).max() < 5e-8
     r = pgo.node_reg(qf, tf, qf, tf, 3.0, jac=False)
-    assert np.allclose(r, 0, atol=1e-14)
+    assert np.allclose(r, 0, atol=1e-13)   # w * |t| * a few ulp: translations here are ~5 m, the weight 3
 
 
 def test_plus_and_plus_jacobian():
