@@ -14,15 +14,15 @@
 //   chain stream   C(d):     1 CTA.  Applies the one update the bulk has not yet given the diagonal block — the
 //                            rank-96 product of X[d, d-1] from trsm(d-1) — then L_dd = chol(A_dd) and Linv = L_dd^-1,
 //                            every matrix-shaped piece on FP64 tensor cores (DMMA).  Waits for trsm(d-1), rest(d-2).
-//   panel stream   trsm(d):  X = A[R, panel] * Linv^T for the rows R below the panel whose envelope reaches it.
-//                            Waits for C(d).
-//                  next(d):  the update tiles that hold the columns of panel d+1 (what trsm(d+1) needs), except the
+//                  trsm(d):  X = A[R, panel] * Linv^T for the rows R below the panel whose envelope reaches it.
+//                            Behind C(d) on the same stream (chain mode 1); waits for next(d-1).
+//   panel stream   next(d):  the update tiles that hold the columns of panel d+1 (what trsm(d+1) needs), except the
 //                            diagonal block of panel d+1: C(d+1) does that one itself, which is what lets it start
-//                            right after trsm(d) instead of after the update.  Waits for rest(d-1).
-//   main stream    rest(d):  every other tile of A[r, c] -= X[r,:] . X[c,:], r, c in R, c <= r.  128x64 DMMA tiles,
-//                            accumulators preloaded with A so the epilogue is a plain store.  Waits for trsm(d).
-// so C(d+1), next(d) and rest(d) overlap, and a panel costs max(C + trsm, rest) (c3: ~55 us).
-// then a backward sweep (one launch per panel) solves L^T x = y.
+//                            right after trsm(d) instead of after the update.  Waits for trsm(d), rest(d-1).
+//   main stream    rest(d):  every other tile of A[r, c] -= X[r,:] . X[c,:], r, c in R, c <= r.  128x64 DMMA tiles in a
+//                            persistent kernel fed by bulk copies of the packed panel.  Waits for trsm(d).
+// so C(d+1), next(d) and rest(d) overlap, and a panel costs max(C + trsm + two launch gaps, rest) (c3, one chain: 38.8 us).
+// Then a backward sweep (one launch per panel, programmatic dependent launches) solves L^T x = y.
 //
 // Partial factorisation (multi-GPU domain decomposition): only the first n_elim panels are
 // eliminated; the trailing rows then hold the Schur complement on the border unknowns and the border part of
@@ -1346,11 +1346,11 @@ int skyline_factor_numeric(SkylineFactor* f, std::string* err) {
   SK(cudaEventRecord(f->ev_fork, s0));
   SK(cudaStreamWaitEvent(s1, f->ev_fork, 0));
   SK(cudaStreamWaitEvent(s2, f->ev_fork, 0));
-  // chain stream s1:  [wait trsm(d-1), rest(d-2)] C(d)    -> ev_c[d]
-  // panel stream s2:  [wait C(d)]                 trsm(d) -> ev_trsm[d]   [wait rest(d-1)] next(d)
-  // main  stream s0:  [wait trsm(d)]              rest(d) -> ev_rest[d]
-  // next(d-1) precedes trsm(d) on s2, rest(d-1) precedes rest(d) on s0.  (trsm on the chain stream, back to back
-  // with C, saves the two event hops but was measured no faster on c3 and slower on heavier fronts.)
+  // Chain mode 0 (PGS_CHAIN_MODE=0, the earlier arrangement):
+  //   chain stream s1:  [wait trsm(d-1), rest(d-2)] C(d)    -> ev_c[d]
+  //   panel stream s2:  [wait C(d)]                 trsm(d) -> ev_trsm[d]   [wait rest(d-1)] next(d)
+  //   main  stream s0:  [wait trsm(d)]              rest(d) -> ev_rest[d]
+  // next(d-1) precedes trsm(d) on s2, rest(d-1) precedes rest(d) on s0.
   // The persistent update CTAs fill a whole SM each; g_rest_ctas SMs are theirs, split between the factorisations that
   // share the GPU, the others stay free for the kernels of the panel chains (diag, trsm, next) at all times.
   const int rest_ctas = std::max(1, g_rest_ctas / f->share);
