@@ -349,3 +349,20 @@ def test_trigger_on_several_host_threads_equals_the_sequential_trigger(config, k
         else:
             assert all(np.array_equal(x, y) for x, y in zip(a, b))
     assert len(runs["1"][0]["u"]) > 3 * 2048   # several chunks were in play
+
+
+def test_library_asks_for_more_hardware_queues_unless_the_host_chose():
+    """The streams of a factorisation must not share a hardware work queue with each other ("Hardware work
+    queues"): libpgs.so puts CUDA_DEVICE_MAX_CONNECTIONS=32 into the environment when it is loaded — before a CUDA context
+    can exist in a host that links it — and leaves a value the host chose alone; the Python package does the same on import."""
+    import subprocess, sys, os
+    from solve_keyframe_pose_graph_b200 import capi
+    getenv = ("import ctypes; L = ctypes.CDLL(None); L.getenv.restype = ctypes.c_char_p; ctypes.CDLL(%r); "
+              "print(L.getenv(b'CUDA_DEVICE_MAX_CONNECTIONS').decode())") % capi.library_path()
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+    assert subprocess.check_output([sys.executable, "-c", getenv], env=env).decode().strip() == "32"
+    env["CUDA_DEVICE_MAX_CONNECTIONS"] = "4"
+    assert subprocess.check_output([sys.executable, "-c", getenv], env=env).decode().strip() == "4"
+    del env["CUDA_DEVICE_MAX_CONNECTIONS"]
+    pkg = "import os, sys; sys.path.insert(0, %r); import solve_keyframe_pose_graph_b200; print(os.environ['CUDA_DEVICE_MAX_CONNECTIONS'])" % ROOT
+    assert subprocess.check_output([sys.executable, "-c", pkg], env=env).decode().strip() == "32"
