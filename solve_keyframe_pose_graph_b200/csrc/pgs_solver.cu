@@ -809,7 +809,12 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
     }
     if (int rc = launch_sweep(0, d_pose.p, d_sw.p, cost_dst)) return rc;
   } else {
-    constexpr int NCHUNK = (int)(sizeof(ev_chunk) / sizeof(ev_chunk[0]));
+    constexpr int MAXCHUNK = (int)(sizeof(ev_chunk) / sizeof(ev_chunk[0]));
+    // Two chunks, the first 70 % of the keyframes: every copy costs a few microseconds of set-up on the copy engine, so few
+    // chunks beat many (4 equal chunks 188 us, 3: 182, 2: 176), and with the sweep ~2.4x faster than the bus the share of the
+    // first chunk is swept just as the second one lands (first chunk 50 / 60 / 70 / 80 %: 177 / 175 / 171 / 179 us;
+    // profiles/r02_e2e_lab_v2.txt).  PGS_E2E_CHUNKS / PGS_E2E_SPLIT override.
+    static const int NCHUNK = [] { const char* e = getenv("PGS_E2E_CHUNKS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > MAXCHUNK ? MAXCHUNK : v); }();
     // Pinned (registered) host memory is visible to the device: the pack kernel then reads q and t straight over the bus,
     // chunk by chunk, with no staging copy and none of the per-copy set-up cost that nine small cudaMemcpyAsync calls have.
     // Pageable memory goes through cudaMemcpyAsync as before.
@@ -828,8 +833,9 @@ int Solver::evaluate_from_host(const double* q, const double* t, const double* s
     }
     int done_o = 0, done_l = 0, done_r = 0;
     for (int k = 0; k < NCHUNK; ++k) {
-      // equal chunks: chunks that shrink towards the end (a last chunk of 4.5 % of the keyframes) were measured no faster, 188.4 vs 189.0 us
-      const int n0 = (int)((long long)N * k / NCHUNK), n1 = (int)((long long)N * (k + 1) / NCHUNK);
+      int n0 = (int)((long long)N * k / NCHUNK), n1 = (int)((long long)N * (k + 1) / NCHUNK);
+      if (NCHUNK == 2) { static const double f = [] { const char* e = getenv("PGS_E2E_SPLIT"); const double v = e ? atof(e) : 0.7; return (v > 0.05 && v < 0.95) ? v : 0.7; }();
+                         const int cut = (int)(f * N); if (k == 0) n1 = cut; else n0 = cut; }
       if (direct) {
         // few CTAs: the bus is the bound, and the SMs are wanted by the sweep of the previous chunk
         pack_pose_kernel<<<std::min(cdiv(n1 - n0, 256), 64), 256, 0, copy_stream>>>(n0, n1 - n0, q + 4 * (size_t)n0, t + 3 * (size_t)n0, d_node_const.p, d_pose.p);
